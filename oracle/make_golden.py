@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python oracle/make_golden.py
+
+Imports /root/reference/src/architectures/nets.py::ConvNet1 and
+/root/reference/src/models/imitation.py::Imitation through the import stubs in
+oracle/_stubs (pytorch_lightning, matplotlib are not installed here), seeds as
+train.py:103 does, and records what the reference produces for seeded synthetic
+inputs. The GPU box has no /root/reference, so these files are how the reference's
+behaviour travels. TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("BC_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "_stubs"), REF, ROOT]
+
+from src.architectures.nets import ConvNet1 as RefNet  # noqa: E402  (reference)
+from src.models.imitation import Imitation as RefImitation  # noqa: E402  (reference)
+from src.dataset.imitation_dataset import continous_to_discreet  # noqa: E402 (reference; needs pandas only)
+
+from oracle import bc_oracle as O  # noqa: E402
+
+HP = dict(obs_size=4, n_actions=9)
+SEED = 12345  # configs/seeds/default_seeds.yaml:3
+
+
+def build_ref():
+    torch.manual_seed(SEED)
+    net = RefNet(HP)
+    return net, RefImitation(HP, net, {})
+
+
+def flat(named):
+    return np.concatenate([named[k].detach().reshape(-1).numpy() for k in O.PARAM_ORDER])
+
+
+def golden_step(B, data_seed, path):
+    frames, labels = O.synth_frames(data_seed, B + 4)
+    x_np, y_np = O.sequential_samples(frames, labels)
+    x, y = torch.from_numpy(x_np), torch.from_numpy(y_np)
+    net, model = build_ref()
+    init = flat(dict(net.named_parameters()))
+    example = net.example_input_array.numpy().copy()
+    example_logits = net(net.example_input_array).detach().numpy()
+    opt, _ = model.configure_optimizers()
+    opt = opt[0]
+    loss = model.training_step((x, y), 0)
+    logits = model(x).detach().numpy()
+    opt.zero_grad()
+    loss.backward()
+    grads = flat({k: p.grad for k, p in net.named_parameters()})
+    opt.step()
+    after1 = flat(dict(net.named_parameters()))
+    # two more steps so bias-correction with t>1 is pinned as well
+    for i in range(2):
+        l2 = model.training_step((x, y), i + 1)
+        opt.zero_grad(); l2.backward(); opt.step()
+    after3 = flat(dict(net.named_parameters()))
+    val = model.validation_step((x, y), 0)
+    np.savez_compressed(
+        path, B=B, data_seed=data_seed, init=init, loss=float(loss.detach()), logits=logits, grads=grads,
+        after1=after1, after3=after3, val_loss_after3=float(val),
+        example_checksum=float(np.abs(example).sum()), example_logits=example_logits,
+        logged_val=float(model.logged["val_loss"]))
+    print(path, "loss", float(loss), "val", float(val))
+
+
+def golden_curve(B, steps, data_seed, path):
+    """Loss curve of the reference over `steps` optimiser steps on a synthetic frame stream."""
+    net, model = build_ref()
+    opt = model.configure_optimizers()[0][0]
+    frames, labels = O.synth_frames(data_seed, steps * B + 4)
+    gray = torch.from_numpy(O.gray_stack(frames))
+    lab = torch.from_numpy(labels)
+    losses = []
+    for s in range(steps):
+        x = torch.stack([gray[s * B + i: s * B + i + 4] for i in range(B)])
+        y = lab[s * B + 4: s * B + 4 + B]
+        loss = model.training_step((x, y), s)
+        opt.zero_grad(); loss.backward(); opt.step()
+        losses.append(float(loss))
+    np.savez_compressed(path, B=B, steps=steps, data_seed=data_seed, losses=np.asarray(losses, np.float64))
+    print(path, losses[0], losses[steps // 2], losses[-1])
+
+
+def golden_labels(path):
+    # pandas 3 (this image) returns read-only `.values` under copy-on-write, which the
+    # reference's in-place writes (imitation_dataset.py:322-324) predate; feed it a
+    # column holder with the 2021-era semantics (writable arrays) instead of a DataFrame.
+    class _Col:
+        def __init__(self, a):
+            self.values = a
+
+    rng = np.random.Generator(np.random.PCG64(7))
+    n = 512
+    steer = rng.choice([0.0, 2.0, 0.05, -0.05, 0.051, -0.051, 0.3, -0.7, 0.01, -0.02], size=n)
+    throttle = rng.choice([0.0, 0.5, 1.0, 0.75], size=n)
+    brake = rng.choice([0.0, 1.0, 0.5], size=n)
+    df = dict(steer=_Col(steer.copy()), throttle=_Col(throttle.copy()), brake=_Col(brake.copy()))
+    out = continous_to_discreet(df)
+    np.savez_compressed(path, steer=steer, throttle=throttle, brake=brake, action=np.asarray(out, np.float64))
+    print(path, np.unique(out))
+
+
+def golden_gray(path):
+    frames, _ = O.synth_frames(3, 5, 64, 48)
+    ref = np.dot(frames[..., :], [0.299, 0.587, 0.114]) / 255.0   # imitation_dataset.py:121, verbatim formula
+    np.savez_compressed(path, gray_f64=ref, gray_f32=ref.astype(np.float32))
+
+
+if __name__ == "__main__":
+    g = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(g, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    golden_step(4, 0, os.path.join(g, "ref_step_b4.npz"))
+    golden_step(1, 1, os.path.join(g, "ref_step_b1.npz"))
+    golden_labels(os.path.join(g, "ref_labels.npz"))
+    golden_gray(os.path.join(g, "ref_gray.npz"))
+    golden_curve(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k.npz"))
