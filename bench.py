@@ -1,0 +1,327 @@
+"""bench.py -- BC train frames/s on N B200s (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...          (N > 1)
+
+One "step" = one optimisation step of the BC policy on `batch` frames per GPU:
+stage (u8 RGB -> gray planes) -> conv1..4 (+ReLU+pool) -> head + CE -> backward -> [allreduce] -> Adam.
+`value` = frames/s with the u8 frames already resident in HBM; `e2e` = the same step driven
+from pinned HOST buffers (H2D of the frames and labels, D2H of the loss, every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bc_train_frames_per_sec"
+UNIT = "frames/s"
+FLOPS_FWD = (44255232, 14745600, 5308416, 589824)          # SURVEY 8(d), per frame, conv1..4
+FLOPS_TRAIN = 150505152
+FRAME_BYTES = 256 * 256 * 3
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synth_host_frames(seed: int, n: int):
+    """Uniform-noise CARLA-shaped u8 RGB frames + uniform labels (worst case for caches)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(0, 256, size=(n, 256, 256, 3), dtype=np.uint8), rng.integers(0, 9, size=n, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU path (torch-CPU restatement in oracle/, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import bc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 32
+    frames, labels = synth_host_frames(0, B + 4)
+    x, y = O.sequential_samples(frames, labels)
+    x, y = torch.from_numpy(x), torch.from_numpy(y)
+    tr = O.OracleTrainer(O.init_params(12345))
+    for _ in range(args.warmup):
+        tr.step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.step(x, y)
+    dt = time.perf_counter() - t0
+    fps = B * args.steps / dt
+    sample = f"{B}-frame slice of the {args.batch}-frame batch per step, {args.steps} steps, torch {torch.__version__} CPU f32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ConvNet1 BC train step, obs 4x256x256, 9 actions, batch {args.batch}/GPU", "cpu_batch": B},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def cpu_baseline(batch):
+    import torch
+    from oracle import bc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 32
+    frames, labels = synth_host_frames(0, B + 4)
+    x, y = O.sequential_samples(frames, labels)
+    x, y = torch.from_numpy(x), torch.from_numpy(y)
+    tr = O.OracleTrainer(O.init_params(12345))
+    for _ in range(3):
+        tr.step(x, y)
+    n, t0 = 0, time.perf_counter()
+    while n < 200 and time.perf_counter() - t0 < 12.0:
+        tr.step(x, y)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch CPU f32, {cores} threads), {n} steps of a {B}-frame slice of the {batch}-frame batch, {1e3 * dt / n:.1f} ms/step"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from carla_imitation_learning_b200 import FusedAdam, sliding_window, stage_gray
+    from carla_imitation_learning_b200 import _lib
+    from src.architectures.nets import ConvNet1
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (see module docstring)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    _lib.build()
+    B = args.batch
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    opt = FusedAdam(list(net.parameters()), lr=1e-3)
+    if world > 1:
+        opt.set_grad_scale(1.0 / world)
+    staged_dtype = torch.bfloat16 if args.staged == "bf16" else torch.float32
+
+    # ---- data: NBUF distinct frame windows per rank (rotated so inputs are never L2-resident) ----
+    NBUF = args.nbuf
+    host_frames, host_labels, dev_frames, dev_labels = [], [], [], []
+    for i in range(NBUF):
+        f, l = synth_host_frames(1000 * rank + i, B + 4)
+        hf = torch.from_numpy(f).pin_memory()
+        hl = torch.from_numpy(l[4:4 + B].copy()).pin_memory()
+        host_frames.append(hf); host_labels.append(hl)
+        dev_frames.append(hf.to(dev)); dev_labels.append(hl.to(dev))
+    gray = torch.empty((B + 4, 256, 256), dtype=staged_dtype, device=dev)
+    bufs = eng.alloc(B, sliding_window(gray), dev_labels[0], True)
+
+    def device_step(i):
+        stage_gray(dev_frames[i % NBUF], out=gray)
+        bufs.y = dev_labels[i % NBUF]
+        eng.enqueue_train(bufs)
+        if world > 1:
+            dist.all_reduce(eng.grads)
+        opt.step_flat(eng.grads)
+
+    # CUDA graphs: one per input buffer (single GPU; the NCCL exchange stays eager for N > 1)
+    graphs = None
+    if world == 1 and not args.no_graph:
+        for i in range(3):
+            device_step(i)
+        torch.cuda.synchronize()
+        graphs = []
+        for i in range(NBUF):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                device_step(i)
+            graphs.append(g)
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % NBUF].replay()
+        else:
+            device_step(i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_dev = float(bufs.loss)
+
+    # ---- e2e: host buffers in, loss out, every step -------------------------------------------
+    stage_in = torch.empty_like(dev_frames[0])
+    y_in = torch.empty_like(dev_labels[0])
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        stage_in.copy_(host_frames[i % NBUF], non_blocking=True)
+        y_in.copy_(host_labels[i % NBUF], non_blocking=True)
+        stage_gray(stage_in, out=gray)
+        bufs.y = y_in
+        eng.enqueue_train(bufs)
+        if world > 1:
+            dist.all_reduce(eng.grads)
+        opt.step_flat(eng.grads)
+        loss_host.copy_(bufs.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- roofline of the dominant kernel (conv1 forward), timed live on its own stream -----------
+    c = eng.ctx(bufs)
+    import ctypes as C
+    s = torch.cuda.current_stream().cuda_stream
+    reps = 20
+    for _ in range(3):
+        _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, s))
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, s))
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / reps
+
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(times[0]), float(times[1])
+    if rank == 0:
+        peaks = load_peaks()
+        frames = B * world * args.steps
+        value = frames / (ms * 1e-3)
+        achieved = FLOPS_FWD[0] * B / (k_ms * 1e-3) / 1e12
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ConvNet1 BC train step (BASELINE configs[1]), obs 4x256x256, 9 actions, batch {B}/GPU, "
+                                   f"u8 RGB frames staged to {args.staged} gray planes, sliding 4-frame window",
+                       "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graphs is not None,
+                       "l2": f"inputs rotate over {NBUF} x {(B + 4) * FRAME_BYTES / 1e6:.0f} MB device buffers (> 126 MB L2)",
+                       "final_loss": loss_dev},
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (B + 4) * FRAME_BYTES + 8 * B, "d2h_bytes_per_step": 4},
+            "gpu_launches": 16 * args.steps,
+            "roofline": {"kernel": "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)", "bound": "tensor",
+                         "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+                         "traffic": None, "peak_source": peaks["src"], "kernel_ms": k_ms,
+                         "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
+            "clocks": clocks,
+        }
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(B)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--staged", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--nbuf", type=int, default=4)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

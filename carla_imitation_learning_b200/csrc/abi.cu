@@ -1,0 +1,142 @@
+// C-ABI glue: error state, device check, arena layout, forward/backward drivers, fused Adam.
+#include "bc_common.cuh"
+#include <math.h>
+
+namespace bc {
+
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace bc
+
+namespace {
+
+// ---- K10: fused multi-tensor Adam over the flat arena ---------------------------------------
+// state: [0] lr [1] beta1 [2] beta2 [3] eps [4] step [5] step_size [6] bc2_sqrt [7] grad_scale
+__global__ void adam_tick_kernel(float* st) {
+    // torch.optim.Adam computes the bias corrections in Python doubles
+    // (torch/optim/adam.py: bias_correction1 = 1 - beta1 ** step; step_size = lr / bias_correction1;
+    //  bias_correction2_sqrt = sqrt(1 - beta2 ** step)); do the same in f64 here.
+    const double step = (double)st[4] + 1.0;
+    st[4] = (float)step;
+    const double bc1 = 1.0 - pow((double)st[1], step);
+    const double bc2 = 1.0 - pow((double)st[2], step);
+    st[5] = (float)((double)st[0] / bc1);
+    st[6] = (float)sqrt(bc2);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                   float4* __restrict__ m, float4* __restrict__ v,
+                                                   const float* __restrict__ st, int64_t n4) {
+    const float b1 = st[1], b2 = st[2], eps = st[3], step_size = st[5], bc2s = st[6], gs = st[7];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = G[k] * gs;                       // grad_scale folds the DDP 1/world mean
+            M[k] = M[k] + (gk - M[k]) * (1.f - b1);           // exp_avg.lerp_(grad, 1 - beta1)
+            V[k] = V[k] * b2 + (1.f - b2) * gk * gk;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+            const float denom = sqrtf(V[k]) / bc2s + eps;
+            P[k] = P[k] - step_size * (M[k] / denom);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bc_last_error_string(void) { return bc::err_buf(); }
+int bc_abi_version(void) { return 1; }
+
+int bc_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) return bc::fail(BC_ERR_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+    return BC_OK;
+}
+
+int64_t bc_arena_layout(int obs_size, int n_actions, int64_t offsets[14], int64_t sizes[14]) {
+    const bc::Arena a = bc::arena_layout(obs_size, n_actions);
+    for (int l = 0; l < 7; ++l) {
+        offsets[2 * l] = a.w[l]; sizes[2 * l] = a.nw[l];
+        offsets[2 * l + 1] = a.b[l]; sizes[2 * l + 1] = a.nb[l];
+    }
+    return a.total;
+}
+
+size_t bc_partials_floats(int obs_size, int n_actions) {
+    return (size_t)bc::partials_layout(bc::arena_layout(obs_size, n_actions)).total;
+}
+
+int bc_forward(const bc_ctx* c, void* stream) {
+    for (int l = 0; l < 4; ++l) {
+        int rc = bc_conv_relu_pool_fwd(c, l, stream);
+        if (rc) return rc;
+    }
+    return bc_head(c, 0, stream);
+}
+
+int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
+    BC_CHECK_ARG(c, "bc_backward: null ctx");
+    // head: (CE from labels when with_loss, else the caller's dlogits) + MLP backward -> ghead
+    int rc = bc_head(c, with_loss ? 3 : 2, stream);
+    if (rc) return rc;
+    for (int l = 3; l >= 1; --l) {
+        if ((rc = bc_conv_bwd_wgrad(c, l, stream))) return rc;
+        if ((rc = bc_conv_bwd_dgrad(c, l, stream))) return rc;
+    }
+    if ((rc = bc_conv_bwd_wgrad(c, 0, stream))) return rc;
+    return bc_reduce_partials(c, with_loss, stream);
+}
+
+int bc_adam_tick(float* state, void* stream) {
+    BC_CHECK_ARG(state, "bc_adam_tick: null state");
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    BC_CUDA_LAUNCH_CHECK("adam_tick_kernel");
+    return BC_OK;
+}
+
+int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* state,
+                 int64_t n, void* stream) {
+    BC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "bc_adam_step: null pointer");
+    BC_CHECK_ARG(n >= 0 && n % 4 == 0, "bc_adam_step: n=%lld must be a multiple of 4 (the arena is padded)", (long long)n);
+    BC_CHECK_ARG(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "bc_adam_step: 16 B alignment");
+    if (n == 0) return BC_OK;
+    const int64_t n4 = n / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    const int cap = bc::num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (const float4*)grads, (float4*)exp_avg,
+                                                        (float4*)exp_avg_sq, state, n4);
+    BC_CUDA_LAUNCH_CHECK("adam_kernel");
+    return BC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared device/host helpers for the BC hot-path kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/bc_b200.h"
+
+namespace bc {
+
+// ---- error reporting (thread-local message, C-ABI returns the code) -------------------
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+#define BC_CHECK_ARG(cond, ...) do { if (!(cond)) return bc::fail(BC_ERR_ARG, __VA_ARGS__); } while (0)
+#define BC_CUDA_LAUNCH_CHECK(name) do { cudaError_t e_ = cudaPeekAtLastError(); \
+    if (e_ != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: %s", name, cudaGetErrorString(e_)); } while (0)
+
+int num_sms();
+
+// ---- network geometry (nets.py:17-33) at 256x256 ----------------------------------------
+struct LayerGeom { int cin, cout, k, s, p, hin, hc, hp; };
+__host__ __device__ constexpr LayerGeom geom(int layer, int obs) {
+    return layer == 0 ? LayerGeom{obs, 16, 7, 3, 3, 256, 84, 28}
+         : layer == 1 ? LayerGeom{16, 32, 5, 1, 2, 28, 24, 12}
+         : layer == 2 ? LayerGeom{32, 64, 4, 1, 2, 12, 9, 4}
+         :              LayerGeom{64, 128, 3, 1, 2, 4, 2, 1};
+}
+
+// ---- arena layout -------------------------------------------------------------------------
+// order in memory: fc.4 fc.2 fc.0 conv4 conv3 conv2 conv1 (weight, bias), each padded to 32 floats
+struct Arena {
+    int64_t w[7], b[7];     // index 0..3 = conv1..4, 4..6 = fc.0, fc.2, fc.4
+    int64_t nw[7], nb[7];
+    int64_t seg_off[5], seg_len[5];  // gradient segments: head(fc.4..fc.0), conv4, conv3, conv2, conv1
+    int64_t total;
+};
+__host__ inline int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
+__host__ inline Arena arena_layout(int obs, int na) {
+    Arena a{};
+    int64_t off = 0;
+    const int fin[3] = {128, 64, 32};
+    const int fout[3] = {64, 32, na};
+    a.seg_off[0] = 0;
+    for (int f = 2; f >= 0; --f) {
+        a.w[4 + f] = off; a.nw[4 + f] = (int64_t)fin[f] * fout[f]; off += pad32(a.nw[4 + f]);
+        a.b[4 + f] = off; a.nb[4 + f] = fout[f];                    off += pad32(a.nb[4 + f]);
+    }
+    a.seg_len[0] = off;
+    for (int l = 3; l >= 0; --l) {
+        LayerGeom g = geom(l, obs);
+        a.seg_off[4 - l] = off;
+        a.w[l] = off; a.nw[l] = (int64_t)g.cout * g.cin * g.k * g.k; off += pad32(a.nw[l]);
+        a.b[l] = off; a.nb[l] = g.cout;                               off += pad32(a.nb[l]);
+        a.seg_len[4 - l] = off - a.seg_off[4 - l];
+    }
+    a.total = off;
+    return a;
+}
+
+// partial-sum workspace: per segment, NPART[seg] copies of seg_len floats, then loss partials
+constexpr int kHeadBlocks = 32;     // partial copies of the head segment
+constexpr int kWgradParts[4] = {296, 37, 9, 4};  // conv1..conv4 (grid.x of the wgrad kernels)
+struct Partials { int64_t off[5]; int nparts[5]; int64_t loss_off; int64_t total; };
+__host__ inline Partials partials_layout(const Arena& a) {
+    Partials p{};
+    int64_t off = 0;
+    p.off[0] = 0; p.nparts[0] = kHeadBlocks; off += a.seg_len[0] * kHeadBlocks;
+    for (int s = 1; s < 5; ++s) {  // s=1 -> conv4 ... s=4 -> conv1
+        int layer = 4 - s;
+        p.off[s] = off; p.nparts[s] = kWgradParts[layer]; off += a.seg_len[s] * kWgradParts[layer];
+    }
+    p.loss_off = off; off += 32 * ((kHeadBlocks + 31) / 32);
+    p.total = off;
+    return p;
+}
+
+// ---- small device helpers -----------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace bc

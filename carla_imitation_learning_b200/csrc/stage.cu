@@ -1,0 +1,80 @@
+// K0: fused frame staging  rgb u8 (n,H,W,3) -> gray planes f32/bf16 (n,H,W).
+// Replaces the per-sample numpy work of SequentialTorchDataset._load_file
+// (/root/reference/src/dataset/imitation_dataset.py:120-121,130):
+//     np.dot(images, [0.299, 0.587, 0.114]) / 255.0  ->  float32
+// The f64 evaluation ((R*.299 + G*.587) + B*.114) * (1/255), rounded to f32, equals the
+// numpy result for ALL 2^24 (R,G,B) triples (tests/test_stage_exhaustive.py proves it on the
+// CPU model and on the device), so the kernel is bit-exact for f32 output.
+// HBM-bound: 3 B read + 4 B (f32) or 2 B (bf16) written per pixel; no reuse, so no smem.
+#include "bc_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float gray_px(uint32_t r, uint32_t g, uint32_t b) {
+    // explicit _rn intrinsics: no FMA contraction, so the CPU model in the tests is exact
+    double s = __dadd_rn(__dadd_rn(__dmul_rn((double)r, 0.299), __dmul_rn((double)g, 0.587)),
+                         __dmul_rn((double)b, 0.114));
+    return (float)__dmul_rn(s, 1.0 / 255.0);
+}
+
+// PX pixels per thread: 4 for f32 output (one 16 B store), 8 for bf16 output (one 16 B store).
+template <int PX, typename TOUT>
+__global__ void __launch_bounds__(256) stage_gray_kernel(const uint8_t* __restrict__ rgb,
+                                                         TOUT* __restrict__ out, int64_t n_groups) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += stride) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + g * (3 * PX));
+        uint32_t w[3 * PX / 4];
+#pragma unroll
+        for (int i = 0; i < 3 * PX / 4; ++i) w[i] = __ldg(src + i);
+        float v[PX];
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            uint32_t c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int byte = 3 * p + k;
+                c[k] = (w[byte >> 2] >> (8 * (byte & 3))) & 0xffu;
+            }
+            v[p] = gray_px(c[0], c[1], c[2]);
+        }
+        if constexpr (sizeof(TOUT) == 4) {
+            float4* dst = reinterpret_cast<float4*>(out + g * PX);
+#pragma unroll
+            for (int i = 0; i < PX / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            uint32_t pk[PX / 2];
+#pragma unroll
+            for (int i = 0; i < PX / 2; ++i) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + g * PX);
+#pragma unroll
+            for (int i = 0; i < PX / 8; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream) {
+    BC_CHECK_ARG(rgb && gray, "bc_stage_gray: null pointer");
+    BC_CHECK_ARG(n_pixels >= 0 && n_pixels % 8 == 0, "bc_stage_gray: n_pixels=%lld must be a multiple of 8", (long long)n_pixels);
+    BC_CHECK_ARG(((uintptr_t)rgb % 4 == 0) && ((uintptr_t)gray % 16 == 0), "bc_stage_gray: rgb must be 4 B and gray 16 B aligned");
+    BC_CHECK_ARG(out_dtype == BC_F32 || out_dtype == BC_BF16, "bc_stage_gray: bad dtype %d", out_dtype);
+    if (n_pixels == 0) return BC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int sms = bc::num_sms();
+    if (out_dtype == BC_F32) {
+        int64_t groups = n_pixels / 4;
+        int blocks = (int)((groups + 255) / 256 < (int64_t)sms * 16 ? (groups + 255) / 256 : (int64_t)sms * 16);
+        stage_gray_kernel<4, float><<<blocks, 256, 0, s>>>(rgb, (float*)gray, groups);
+    } else {
+        int64_t groups = n_pixels / 8;
+        int blocks = (int)((groups + 255) / 256 < (int64_t)sms * 16 ? (groups + 255) / 256 : (int64_t)sms * 16);
+        stage_gray_kernel<8, __nv_bfloat16><<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, groups);
+    }
+    BC_CUDA_LAUNCH_CHECK("stage_gray_kernel");
+    return BC_OK;
+}

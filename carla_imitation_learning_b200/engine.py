@@ -1,0 +1,196 @@
+"""Host side of the hot path: buffer management and kernel sequencing for one device.
+
+Mirrors what torch autograd + ATen do for the reference's
+`ConvNet1.forward` (/root/reference/src/architectures/nets.py:35-39) and
+`Imitation.training_step` (/root/reference/src/models/imitation.py:38-45), but every
+numeric op is a call into libbc_b200.so. PyTorch provides device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+ACT_SHAPES = ((16, 28, 28), (32, 12, 12), (64, 4, 4), (128, 1, 1))
+H = W = 256
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA (sm_100) device: the BC hot path has no CPU fallback")
+
+
+def stage_gray(frames_u8: torch.Tensor, dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(n,H,W,3) u8 RGB on the device -> (n,H,W) gray planes, (0.299R+0.587G+0.114B)/255.
+
+    The device version of SequentialTorchDataset._load_file
+    (/root/reference/src/dataset/imitation_dataset.py:120-121,130); f32 output is bit-exact."""
+    _require_cuda(frames_u8, "frames")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3 or not frames_u8.is_contiguous():
+        raise ValueError("frames must be a contiguous (n,H,W,3) uint8 tensor")
+    n, h, w, _ = frames_u8.shape
+    if out is None:
+        out = torch.empty((n, h, w), dtype=dtype, device=frames_u8.device)
+    code = {torch.float32: _lib.BC_F32, torch.bfloat16: _lib.BC_BF16}[out.dtype]
+    _lib.check(_lib.lib().bc_stage_gray(frames_u8.data_ptr(), out.data_ptr(), n * h * w, code, _stream_ptr()), "bc_stage_gray")
+    return out
+
+
+def sliding_window(gray: torch.Tensor, frame_skip: int = 4) -> torch.Tensor:
+    """Zero-copy (n-frame_skip, frame_skip, H, W) view: sample i = planes [i, i+frame_skip).
+
+    The reference's loader is shuffle=False (imitation_dataset.py:270-274) with
+    files[index-frame_skip:index], index=i+4 (:117,:125), so consecutive samples share 3 of 4
+    planes; the view hands that overlap to the conv1 kernels without materialising it."""
+    n, h, w = gray.shape
+    if n <= frame_skip:
+        raise ValueError(f"need more than {frame_skip} frames, got {n}")
+    return gray.as_strided((n - frame_skip, frame_skip, h, w), (h * w, h * w, w, 1))
+
+
+@dataclass
+class StepBuffers:
+    """Everything one forward produces and one backward consumes."""
+    batch: int
+    x: torch.Tensor
+    y: Optional[torch.Tensor]
+    act: List[torch.Tensor]
+    amax: List[torch.Tensor]
+    hid1: torch.Tensor
+    hid2: torch.Tensor
+    logits: torch.Tensor
+    dlogits: torch.Tensor
+    loss: torch.Tensor
+    ghead: Optional[torch.Tensor] = None
+    gact: List[torch.Tensor] = field(default_factory=list)
+
+
+class BCEngine:
+    """Kernel sequencing for one parameter arena on one device."""
+
+    def __init__(self, arena: torch.Tensor, obs_size: int, n_actions: int):
+        _require_cuda(arena, "parameter arena")
+        if arena.dtype != torch.float32 or not arena.is_contiguous():
+            raise ValueError("the parameter arena is a contiguous float32 tensor")
+        self.lib = _lib.lib()
+        with torch.cuda.device(arena.device):
+            _lib.check(self.lib.bc_device_check(), "bc_device_check")
+        self.arena = arena
+        self.device = arena.device
+        self.obs_size, self.n_actions = int(obs_size), int(n_actions)
+        total, self.offsets, self.sizes = _lib.arena_layout(self.obs_size, self.n_actions)
+        if arena.numel() != total:
+            raise ValueError(f"arena has {arena.numel()} floats, layout needs {total}")
+        self.grads = torch.zeros_like(arena)
+        # partial-sum workspace: pads are never written, so it must start zeroed
+        self.partials = torch.zeros(int(self.lib.bc_partials_floats(self.obs_size, self.n_actions)),
+                                    dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ buffers
+    def alloc(self, batch: int, x: torch.Tensor, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
+        dev, f32 = self.device, torch.float32
+        e = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=dev)
+        bufs = StepBuffers(
+            batch=batch, x=x, y=y,
+            act=[e(batch, *s) for s in ACT_SHAPES],
+            amax=[e(batch, *s, dt=torch.uint8) for s in ACT_SHAPES],
+            hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
+            dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
+        if backward:
+            self._alloc_bwd(bufs)
+        return bufs
+
+    def _alloc_bwd(self, bufs: StepBuffers) -> None:
+        if bufs.ghead is None:
+            e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
+            bufs.ghead = e(bufs.batch, 128)
+            bufs.gact = [e(bufs.batch, *s) for s in ACT_SHAPES[:3]]
+
+    def check_input(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, "x")
+        if x.device != self.device:
+            raise RuntimeError(f"x is on {x.device}, parameters on {self.device}")
+        if x.dim() != 4 or x.shape[1] != self.obs_size or x.shape[2] != H or x.shape[3] != W:
+            raise ValueError(f"x must be (B,{self.obs_size},{H},{W}) like nets.py:14, got {tuple(x.shape)}")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        esz = x.element_size()
+        ok = (x.stride(3) == 1 and x.stride(2) == W and (x.stride(0) * esz) % 16 == 0 and (x.stride(1) * esz) % 16 == 0
+              and x.data_ptr() % 16 == 0)
+        return x if ok else x.contiguous()
+
+    def ctx(self, b: StepBuffers, loss_scale: Optional[float] = None) -> _lib.BcCtx:
+        c = _lib.BcCtx()
+        c.obs_size, c.n_actions, c.batch = self.obs_size, self.n_actions, b.batch
+        c.x_dtype = _lib.BC_F32 if b.x.dtype == torch.float32 else _lib.BC_BF16
+        c.x_stride_n, c.x_stride_c = (b.x.stride(0), b.x.stride(1)) if b.batch else (0, 0)
+        c.x = b.x.data_ptr()
+        c.y = b.y.data_ptr() if b.y is not None else None
+        c.params, c.grads = self.arena.data_ptr(), self.grads.data_ptr()
+        for i in range(4):
+            c.act[i], c.amax[i] = b.act[i].data_ptr(), b.amax[i].data_ptr()
+        for i in range(3):
+            c.gact[i] = b.gact[i].data_ptr() if b.gact else None
+        c.ghead = b.ghead.data_ptr() if b.ghead is not None else None
+        c.hid1, c.hid2 = b.hid1.data_ptr(), b.hid2.data_ptr()
+        c.logits, c.dlogits, c.loss = b.logits.data_ptr(), b.dlogits.data_ptr(), b.loss.data_ptr()
+        c.partials = self.partials.data_ptr()
+        c.loss_scale = (1.0 / max(b.batch, 1)) if loss_scale is None else float(loss_scale)
+        return c
+
+    # ------------------------------------------------------------------ kernels
+    def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, backward: bool = False,
+                loss_scale: Optional[float] = None) -> StepBuffers:
+        """conv1..4 (+ReLU+pool) and the head; with `y` also CE loss and dlogits, in the same head launch."""
+        x = self.check_input(x)
+        if y is not None:
+            _require_cuda(y, "y")
+            if y.dtype != torch.int64 or y.shape != (x.shape[0],):
+                raise ValueError("y must be (B,) int64 class ids (imitation_dataset.py:131)")
+            y = y.contiguous()
+        b = self.alloc(x.shape[0], x, y, backward)
+        c = self.ctx(b, loss_scale)
+        s = _stream_ptr()
+        with torch.cuda.device(self.device):
+            for layer in range(4):
+                _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
+            _lib.check(self.lib.bc_head(C.byref(c), 1 if y is not None else 0, s), "head forward")
+            if y is not None:
+                _lib.check(self.lib.bc_loss_reduce(C.byref(c), s), "loss reduce")
+        return b
+
+    def backward(self, b: StepBuffers, loss_scale: Optional[float] = None) -> torch.Tensor:
+        """Gradients of every parameter from b.dlogits (already holding d loss / d logits). Returns self.grads."""
+        self._alloc_bwd(b)
+        c = self.ctx(b, loss_scale)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bc_backward(C.byref(c), 0, _stream_ptr()), "bc_backward")
+        return self.grads
+
+    def train_forward_backward(self, x: torch.Tensor, y: torch.Tensor, loss_scale: Optional[float] = None) -> StepBuffers:
+        """Forward, CE loss and full backward in one enqueue (no autograd). grads land in self.grads."""
+        x = self.check_input(x)
+        b = self.alloc(x.shape[0], x, y.contiguous(), True)
+        self.enqueue_train(b, loss_scale)
+        return b
+
+    def enqueue_train(self, b: StepBuffers, loss_scale: Optional[float] = None) -> None:
+        c = self.ctx(b, loss_scale)
+        s = _stream_ptr()
+        with torch.cuda.device(self.device):
+            for layer in range(4):   # the head's forward is fused into bc_backward's first launch
+                _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
+            _lib.check(self.lib.bc_backward(C.byref(c), 1, s), "bc_backward")
+
+    def argmax(self, logits: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
+        _lib.check(self.lib.bc_argmax(logits.data_ptr(), out.data_ptr(), logits.shape[0], logits.shape[1], _stream_ptr()), "bc_argmax")
+        return out

@@ -1,0 +1,115 @@
+/* bc_b200.h -- C ABI of the B200-native behaviour-cloning hot path.
+ *
+ * The reference (HemuManju/carla-imitation-learning) has no FFI: its hot path is
+ * Python calling torch ATen. This header is the boundary a maintainer binds with
+ * ctypes; every entry point names the reference lines it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*
+ *   - the caller owns and allocates every buffer, including workspaces
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises,
+ *     nothing allocates, so every call is CUDA-graph capturable
+ *   - return 0 on success, negative bc_status on failure; bc_last_error_string() gives
+ *     the thread-local message. There is NO CPU fallback: a missing device is an error.
+ */
+#ifndef BC_B200_H
+#define BC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    BC_OK = 0,
+    BC_ERR_ARG = -1,      /* bad shape / null pointer / misalignment */
+    BC_ERR_DEVICE = -2,   /* no sm_100 device, or a CUDA runtime error */
+    BC_ERR_UNSUPPORTED = -3
+} bc_status;
+
+typedef enum { BC_F32 = 0, BC_BF16 = 1 } bc_dtype;
+
+/* Geometry of ConvNet1 (src/architectures/nets.py:17-33) for 256x256 inputs. */
+#define BC_H 256
+#define BC_W 256
+#define BC_NCONV 4
+#define BC_MAX_ACTIONS 16
+
+/* Flat parameter arena: tensors in reverse order of gradient completion
+ * [fc.4 fc.2 fc.0 conv4 conv3 conv2 | conv1], weight then bias, each padded to 32 floats.
+ * bc_arena_layout fills offsets (in floats) for the 14 tensors in state_dict order
+ * cnn_base.{0,3,6,9}.{weight,bias}, fc.{0,2,4}.{weight,bias}; returns the arena length. */
+int64_t bc_arena_layout(int obs_size, int n_actions, int64_t offsets[14], int64_t sizes[14]);
+
+/* All device buffers of one training/inference context. The caller fills this once. */
+typedef struct {
+    int32_t obs_size;        /* input channels (nets.py:11)            */
+    int32_t n_actions;       /* logits (nets.py:12)                    */
+    int32_t batch;           /* frames in this call                    */
+    int32_t x_dtype;         /* bc_dtype of x                          */
+    int64_t x_stride_n;      /* element stride between samples of x    */
+    int64_t x_stride_c;      /* element stride between channels of x   */
+    const void* x;           /* (batch, obs, 256, 256) planar, rows contiguous */
+    const int64_t* y;        /* (batch,) labels, may be NULL for forward-only  */
+    const float* params;     /* parameter arena                        */
+    float* grads;            /* gradient arena (same layout)           */
+    float* act[4];           /* pooled activations (B,16,28,28) (B,32,12,12) (B,64,4,4) (B,128) */
+    uint8_t* amax[4];        /* window-local argmax of each pool, same shapes  */
+    float* gact[3];          /* gradients w.r.t. act[0..2] (act[3]'s lives in ghead) */
+    float* ghead;            /* (B,128) gradient w.r.t. act[3]          */
+    float* hid1;             /* (B,64)  post-ReLU fc.0                  */
+    float* hid2;             /* (B,32)  post-ReLU fc.2                  */
+    float* logits;           /* (B,n_actions)                           */
+    float* dlogits;          /* (B,n_actions) in/out                    */
+    float* loss;             /* [1] mean CE                             */
+    float* partials;         /* workspace, bc_partials_floats() floats  */
+    float loss_scale;        /* dlogits = (softmax-onehot)*loss_scale; 1/batch for the mean */
+    int32_t reserved;
+} bc_ctx;
+
+size_t bc_partials_floats(int obs_size, int n_actions);
+
+/* ---- a1: SequentialTorchDataset._load_file/__getitem__ (src/dataset/imitation_dataset.py:115-133)
+ * rgb (n,H,W,3) u8 -> gray planes (n,H,W): (0.299R+0.587G+0.114B)/255 evaluated in f64 like
+ * numpy, rounded to f32 (or bf16). A sample is 4 consecutive planes, so the sliding window
+ * of the reference's shuffle=False loader is the strided view x_stride_n = H*W, x_stride_c = H*W. */
+int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream);
+
+/* ---- a4-a8: ConvNet1.forward (src/architectures/nets.py:35-39): conv+ReLU+pool x4, MLP.
+ * Writes act[], amax[], hid1, hid2, logits. */
+int bc_forward(const bc_ctx* c, void* stream);
+/* single stages, for unit tests: layer in 0..3 */
+int bc_conv_relu_pool_fwd(const bc_ctx* c, int layer, void* stream);
+/* head_mode bit0: compute CE loss + dlogits from y (imitation.py:43-44); bit1: backward through the
+ * MLP from dlogits (grad partials + ghead). 0 = logits only. */
+int bc_head(const bc_ctx* c, int head_mode, void* stream);
+
+/* ---- a9-a10: training_step loss + autograd backward (src/models/imitation.py:38-45).
+ * bc_backward assumes bc_forward ran on the same ctx; fills grads (and loss when with_loss). */
+int bc_backward(const bc_ctx* c, int with_loss, void* stream);
+int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream);   /* layer 1..3 -> gact[layer-1] */
+int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream);   /* layer 0..3 -> partials      */
+int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream); /* partials -> grads (, loss) */
+int bc_loss_reduce(const bc_ctx* c, void* stream);                 /* head CTAs' CE partials -> loss (forward-only / validation_step) */
+
+/* ---- a11: Adam.step (src/models/imitation.py:82-87; torch.optim.Adam defaults).
+ * state = {lr, beta1, beta2, eps, step(float), step_size, bc2_sqrt, grad_scale}; bc_adam_tick
+ * increments step and derives the bias corrections in f64 on device (graph-replayable). */
+int bc_adam_tick(float* state, void* stream);
+int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                 const float* state, int64_t n, void* stream);
+
+/* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
+int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);
+
+const char* bc_last_error_string(void);
+int bc_device_check(void);  /* BC_OK iff the current device is sm_100 */
+int bc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BC_B200_H */

@@ -1,0 +1,109 @@
+"""Imitation -- the behaviour-cloning training module, B200-native.
+
+Hook-for-hook the contract of /root/reference/src/models/imitation.py:27-91
+(`Imitation(hparams, net, data_loader)`; forward / training_step / validation_step /
+*_epoch_end / *_dataloader / configure_optimizers / scale_image), so it drops in behind
+train.py's behaviour_cloning block (train.py:93-129). What changes is underneath:
+training_step runs one fused forward+CrossEntropy through the sm_100a kernels and returns an
+autograd-connected scalar whose backward() runs the CUDA backward; configure_optimizers
+returns the fused arena Adam instead of torch.optim.Adam (same hyper-parameters, same
+state_dict keys), with the reference's MultiStepLR([20, 30], 0.1) on top.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.optim import lr_scheduler
+
+try:
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+    _HAVE_PL = True
+except Exception:  # pragma: no cover - Lightning is not installed in the build image
+    _Base = nn.Module
+    _HAVE_PL = False
+
+from carla_imitation_learning_b200.optim import FusedAdam
+
+
+class Imitation(_Base):
+    def __init__(self, hparams, net, data_loader):
+        super().__init__()
+        self.h_params = hparams
+        self.net = net
+        self.data_loader = data_loader
+        if not _HAVE_PL:
+            self._logged = {}
+            self._schedulers = None
+            self.current_epoch = 0
+            self.logger = None
+
+    # -- what Lightning would provide; only defined when it is absent ------------------------
+    if not _HAVE_PL:
+        def log(self, name, value, **_kw):
+            self._logged[name] = value
+
+        def lr_schedulers(self):
+            return self._schedulers
+
+    # -- compute -------------------------------------------------------------------------------
+    def forward(self, x):
+        return self.net.forward(x)
+
+    def _loss(self, x, y):
+        fused = getattr(self.net, "loss", None)
+        if fused is not None:
+            return fused(x, y)
+        return nn.functional.cross_entropy(self.forward(x), y)   # a foreign net: plain contract
+
+    def training_step(self, batch, batch_idx):
+        x, y = batch
+        return self._loss(x, y)
+
+    def validation_step(self, batch, batch_idx):
+        x, y = batch
+        with torch.no_grad():
+            loss = self._loss(x, y)
+        self.log('val_loss', loss)  # monitored by ModelCheckpoint (train.py:106-111)
+        return loss
+
+    # -- epoch hooks (imitation.py:57-71) -------------------------------------------------------
+    def training_epoch_end(self, outputs) -> None:
+        sch = self.lr_schedulers()
+        if sch is not None:
+            sch.step()
+        loss = torch.stack([o['loss'].detach() for o in outputs]).mean()   # stays on device until logged
+        self._add_scalars({"train_loss": loss})
+
+    def validation_epoch_end(self, outputs) -> None:
+        self._add_scalars({"val_loss": torch.stack([o.detach() for o in outputs]).mean()})
+
+    def _add_scalars(self, scalars) -> None:
+        exp = getattr(getattr(self, "logger", None), "experiment", None)
+        if exp is not None:
+            exp.add_scalars("losses", scalars, global_step=self.current_epoch)
+
+    # -- data (imitation.py:73-80) ---------------------------------------------------------------
+    def train_dataloader(self):
+        return self.data_loader['train_dataloader']
+
+    def val_dataloader(self):
+        return self.data_loader['val_dataloader']
+
+    def test_dataloader(self):
+        return self.data_loader['test_dataloader']
+
+    # -- optimiser (imitation.py:82-87) ----------------------------------------------------------
+    def configure_optimizers(self):
+        params = list(self.parameters())
+        if all(hasattr(p, "_bc_arena") for p in params):
+            optimizer = FusedAdam(params, lr=1e-3)     # LR is hard-coded in the reference (LEARNING_RATE is unused)
+        else:
+            optimizer = torch.optim.Adam(params, lr=1e-3)
+        scheduler = lr_scheduler.MultiStepLR(optimizer, milestones=[20, 30], gamma=0.1)
+        if not _HAVE_PL:
+            self._schedulers = scheduler
+        return [optimizer], [scheduler]
+
+    def scale_image(self, img):
+        return (img + 1) / 2
