@@ -45,6 +45,7 @@ EXPORTS = {
     "bc_conv_bwd_dgrad": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),
     "bc_conv_bwd_wgrad": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),
     "bc_reduce_partials": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),
+    "bc_reduce_partials_range": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "bc_loss_reduce": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_adam_tick": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

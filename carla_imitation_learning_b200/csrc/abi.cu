@@ -31,34 +31,34 @@ int num_sms() {
 namespace {
 
 // ---- K10: fused multi-tensor Adam over the flat arena ---------------------------------------
-// state: [0] lr [1] beta1 [2] beta2 [3] eps [4] step [5] step_size [6] bc2_sqrt [7] grad_scale
-__global__ void adam_tick_kernel(float* st) {
-    // torch.optim.Adam computes the bias corrections in Python doubles
-    // (torch/optim/adam.py: bias_correction1 = 1 - beta1 ** step; step_size = lr / bias_correction1;
-    //  bias_correction2_sqrt = sqrt(1 - beta2 ** step)); do the same in f64 here.
-    const double step = (double)st[4] + 1.0;
-    st[4] = (float)step;
-    const double bc1 = 1.0 - pow((double)st[1], step);
-    const double bc2 = 1.0 - pow((double)st[2], step);
-    st[5] = (float)((double)st[0] / bc1);
-    st[6] = (float)sqrt(bc2);
+// state (doubles, like the Python scalars torch.optim.Adam works with):
+//   [0] lr [1] beta1 [2] beta2 [3] eps [4] step [5] grad_scale [6] step_size (out) [7] bc2_sqrt (out)
+__global__ void adam_tick_kernel(double* st) {
+    // torch/optim/adam.py (single-tensor path): bias_correction1 = 1 - beta1 ** step;
+    // step_size = lr / bias_correction1; bias_correction2_sqrt = sqrt(1 - beta2 ** step) -- all in f64.
+    const double step = st[4] + 1.0;
+    st[4] = step;
+    st[6] = st[0] / (1.0 - pow(st[1], step));
+    st[7] = sqrt(1.0 - pow(st[2], step));
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
-                                                   const float* __restrict__ st, int64_t n4) {
-    const float b1 = st[1], b2 = st[2], eps = st[3], step_size = st[5], bc2s = st[6], gs = st[7];
+                                                   const double* __restrict__ st, int64_t n4) {
+    // the f64 scalars are rounded to f32 exactly where ATen rounds its Scalar arguments
+    const float w1 = (float)(1.0 - st[1]), b2 = (float)st[2], w2 = (float)(1.0 - st[2]), eps = (float)st[3];
+    const float gs = (float)st[5], neg_step = (float)(-st[6]), bc2s = (float)st[7];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
         float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float gk = G[k] * gs;                       // grad_scale folds the DDP 1/world mean
-            M[k] = M[k] + (gk - M[k]) * (1.f - b1);           // exp_avg.lerp_(grad, 1 - beta1)
-            V[k] = V[k] * b2 + (1.f - b2) * gk * gk;          // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-            const float denom = sqrtf(V[k]) / bc2s + eps;
-            P[k] = P[k] - step_size * (M[k] / denom);
+            const float gk = G[k] * gs;                          // grad_scale folds the DDP 1/world mean
+            M[k] = __fmaf_rn(w1, gk - M[k], M[k]);               // exp_avg.lerp_(grad, 1 - beta1), weight < 0.5 branch
+            V[k] = __fmaf_rn(w2 * gk, gk, V[k] * b2);            // exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V[k]), bc2s), eps);   // (sqrt(v) / bc2_sqrt).add_(eps)
+            P[k] = __fmaf_rn(neg_step, __fdiv_rn(M[k], denom), P[k]);                // addcdiv_(m, denom, value=-step_size)
         }
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
@@ -116,14 +116,14 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
     return bc_reduce_partials(c, with_loss, stream);
 }
 
-int bc_adam_tick(float* state, void* stream) {
+int bc_adam_tick(double* state, void* stream) {
     BC_CHECK_ARG(state, "bc_adam_tick: null state");
     adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
     BC_CUDA_LAUNCH_CHECK("adam_tick_kernel");
     return BC_OK;
 }
 
-int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* state,
+int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const double* state,
                  int64_t n, void* stream) {
     BC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "bc_adam_step: null pointer");
     BC_CHECK_ARG(n >= 0 && n % 4 == 0, "bc_adam_step: n=%lld must be a multiple of 4 (the arena is padded)", (long long)n);

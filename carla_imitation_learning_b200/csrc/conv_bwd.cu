@@ -24,9 +24,14 @@ struct WgradCfg {
     static constexpr int TILES = TILED ? HP : 1;             // tiles per frame
     static constexpr int IH = TILED ? (P - 1) * S + K : HIN; // input rows per tile
     static constexpr int IW = HIN;
+    // bank-conflict-free patch reads: lanes differ in (ci, ky) => make the row pitch = 1 and the
+    // channel-plane stride = K (mod 32), so lane t lands in bank (t + const) % 32
+    static constexpr int IWP = IW + ((1 - IW % 32) + 32) % 32;
+    static constexpr int PS_RAW = IH * IWP;
+    static constexpr int PS = PS_RAW + ((K - PS_RAW % 32) + 32) % 32;
     static constexpr int NTHR_RAW = CO_B * CIN * K;
     static constexpr int NT = (NTHR_RAW + 31) / 32 * 32;
-    static constexpr int IN_FLOATS = CIN * IH * IW;
+    static constexpr int IN_FLOATS = CIN * PS;
     static constexpr size_t SMEM_BYTES = (size_t)(IN_FLOATS + CO_B * NWIN) * 4 + (size_t)CO_B * NWIN * 4;
 };
 
@@ -36,6 +41,7 @@ conv_wgrad_kernel(const TIN* __restrict__ x, int64_t sn, int64_t sc,
                   const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
                   float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int B) {
     constexpr int HP = Cfg::HP, NWIN = Cfg::NWIN, IH = Cfg::IH, IW = Cfg::IW, NT = Cfg::NT;
+    constexpr int IWP = Cfg::IWP, PS = Cfg::PS;
     extern __shared__ __align__(16) float smem[];
     float* s_in = smem;
     float* s_g = smem + Cfg::IN_FLOATS;
@@ -68,13 +74,14 @@ conv_wgrad_kernel(const TIN* __restrict__ x, int64_t sn, int64_t sc,
                     const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
                     v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
                 }
-                *reinterpret_cast<float4*>(s_in + (c * IH + yy) * IW + 4 * xv) = v;
+                float* d = s_in + c * PS + yy * IWP + 4 * xv;   // odd pitch: scalar stores
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
             }
         } else {
             for (int i = tid; i < CIN * IH * IW; i += NT) {
                 const int xx = i % IW; int r = i / IW;
                 const int yy = r % IH, c = r / IH;
-                s_in[i] = bc::to_f32(x[(size_t)b * sn + (size_t)c * sc + (size_t)(iy0 + yy) * HIN + xx]);
+                s_in[c * PS + yy * IWP + xx] = bc::to_f32(x[(size_t)b * sn + (size_t)c * sc + (size_t)(iy0 + yy) * HIN + xx]);
             }
         }
         for (int i = tid; i < CO_B * NWIN; i += NT) {
@@ -86,11 +93,11 @@ conv_wgrad_kernel(const TIN* __restrict__ x, int64_t sn, int64_t sc,
             s_g[i] = a > 0.f ? gP[o] : 0.f;
             const int oyl = (TILED ? 0 : py * P) + pos / P;   // conv row relative to the tile
             const int ox = px * P + pos % P;
-            s_pos[i] = (oyl * S) * IW + ox * S;
+            s_pos[i] = (oyl * S) * IWP + ox * S;
         }
         __syncthreads();
         if (active) {
-            const float* base = s_in + (ci * IH + ky) * IW;
+            const float* base = s_in + ci * PS + ky * IWP;
             const float* gp = s_g + cl * NWIN;
             const int* pp = s_pos + cl * NWIN;
 #pragma unroll 4
@@ -247,12 +254,12 @@ struct ReduceArgs {
     const float* part; float* grads; float* loss;
     int64_t seg_off[5], seg_len[5], poff[5];
     int nparts[5];
-    int64_t loss_off; int n_loss; int64_t total; int with_loss;
+    int64_t loss_off; int n_loss; int64_t begin, end; int with_loss;
 };
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.total) {
+    const int64_t i = a.begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.end) {
         int s = 0;
 #pragma unroll
         for (int k = 1; k < 5; ++k) if (i >= a.seg_off[k]) s = k;
@@ -346,14 +353,21 @@ extern "C" int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream) {
 }
 
 extern "C" int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream) {
+    return bc_reduce_partials_range(c, 0, 5, with_loss, stream);
+}
+
+extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi, int with_loss, void* stream) {
     BC_CHECK_ARG(c && c->partials && c->grads, "bc_reduce_partials: null buffer");
+    BC_CHECK_ARG(0 <= seg_lo && seg_lo < seg_hi && seg_hi <= 5, "bc_reduce_partials_range: segments [%d,%d) outside [0,5)", seg_lo, seg_hi);
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
     ReduceArgs a{};
     a.part = c->partials; a.grads = c->grads; a.loss = c->loss;
     for (int k = 0; k < 5; ++k) { a.seg_off[k] = ar.seg_off[k]; a.seg_len[k] = ar.seg_len[k]; a.poff[k] = pl.off[k]; a.nparts[k] = pl.nparts[k]; }
-    a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.total = ar.total; a.with_loss = with_loss && c->loss != nullptr;
-    reduce_partials_kernel<<<(int)((ar.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
+    a.begin = ar.seg_off[seg_lo];
+    a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];
+    reduce_partials_kernel<<<(int)((a.end - a.begin + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     BC_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return BC_OK;
 }

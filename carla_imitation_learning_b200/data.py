@@ -1,0 +1,133 @@
+"""Sequential frame pipeline: pinned host frames -> H2D -> fused staging kernel -> window views.
+
+Replaces the per-sample host work of SequentialTorchDataset + DataLoader
+(/root/reference/src/dataset/imitation_dataset.py:90-136, 263-288): there every sample
+re-reads and re-converts its 4 frames in numpy (`np.dot(...)/255.0`, :121) inside worker
+processes and ships (B,4,256,256) f32 = 1 MB/sample to the trainer. Because the loader is
+`shuffle=False` and sample i = frames [i, i+4) with the label of frame i+4 (:117,:125,:131),
+a batch of B samples is B+3 distinct frames: this pipeline copies those B+frame_skip u8
+frames once (196 KB each), converts each ONCE on the device, and hands the model a
+zero-copy strided view -- 5.4x fewer PCIe bytes than f32 samples, 4x fewer conversions.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .engine import sliding_window, stage_gray
+
+
+def synthetic_sequence(seed: int, n_frames: int, h: int = 256, w: int = 256, n_actions: int = 9,
+                       label_noise: float = 0.25) -> Tuple[np.ndarray, np.ndarray]:
+    """Deterministic CARLA-shaped frames + labels (numpy PCG64): noise in [0,128) plus a +100 band
+    whose row announces the next frame's label (wrong with probability `label_noise`)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    labels = rng.integers(0, n_actions, size=n_frames + 1, dtype=np.int64)
+    shown = labels.copy()
+    flip = rng.random(n_frames + 1) < label_noise
+    shown[flip] = rng.integers(0, n_actions, size=int(flip.sum()))
+    frames = rng.integers(0, 128, size=(n_frames, h, w, 3), dtype=np.uint8)
+    band = h // n_actions
+    for i in range(n_frames):
+        r0 = int(shown[i + 1]) * band
+        frames[i, r0:r0 + band] += 100
+    return frames, labels[:n_frames]
+
+
+def continous_to_discreet(steer, throttle, brake, steer_threshold: float = 0.05) -> np.ndarray:
+    """(steer, throttle, brake) -> class id acc*3 + steer, the label contract of
+    /root/reference/src/dataset/imitation_dataset.py:317-339 (name kept, spelling included).
+    Takes the three columns as arrays instead of a DataFrame."""
+    steer = np.asarray(steer, np.float64)
+    throttle = np.asarray(throttle, np.float64)
+    brake = np.asarray(brake, np.float64)
+    right, left = steer > steer_threshold, steer < -steer_threshold
+    s = np.where(right, 2.0, np.where(left, 0.0, 1.0))
+    # inside the dead band the reference leaves raw values equal to 0.0 (or 2.0) untouched
+    s = np.where(~right & ~left & (steer == 0.0), 0.0, s)
+    acc = brake.copy()
+    acc[(brake == 0.0) & (throttle == 1.0)] = 2.0
+    acc[(brake == 0.0) & (throttle == 0.5)] = 1.0
+    acc[(brake == 1.0) & (throttle == 0.0)] = 0.0
+    return acc * 3 + s
+
+
+class SequentialFrames:
+    """Iterable of (x, y) batches over one frame sequence, staged on the device.
+
+    x is a (b, frame_skip, H, W) strided view into the staged gray planes (f32 or bf16),
+    y the (b,) int64 labels of the frames that follow each window. The last batch may be
+    short (the reference's DataLoader has no drop_last). Host frames are pinned; chunk k+1's
+    H2D copy and staging run on a side stream while the trainer consumes chunk k.
+    """
+
+    def __init__(self, frames_u8: np.ndarray, labels: np.ndarray, batch_size: int = 64, frame_skip: int = 4,
+                 device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32):
+        if frames_u8.dtype != np.uint8 or frames_u8.ndim != 4 or frames_u8.shape[-1] != 3:
+            raise ValueError("frames must be (N,H,W,3) uint8")
+        if len(labels) != len(frames_u8):
+            raise ValueError("one label per frame (state.csv rows, imitation_dataset.py:108-111)")
+        if len(frames_u8) <= frame_skip:
+            raise ValueError(f"need more than frame_skip={frame_skip} frames")
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("SequentialFrames stages on a CUDA device; there is no CPU path")
+        self.frames = torch.from_numpy(np.ascontiguousarray(frames_u8)).pin_memory()
+        self.labels = torch.from_numpy(np.asarray(labels, np.int64)).to(self.device)
+        self.batch_size, self.frame_skip, self.dtype = int(batch_size), int(frame_skip), dtype
+        self.n_samples = len(frames_u8) - frame_skip
+        self._copy_stream = torch.cuda.Stream(self.device)
+        n, h, w, _ = frames_u8.shape
+        rows = self.batch_size + frame_skip
+        self._raw = [torch.empty((rows, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self._gray = [torch.empty((rows, h, w), dtype=dtype, device=self.device) for _ in range(2)]
+
+    def __len__(self) -> int:
+        return (self.n_samples + self.batch_size - 1) // self.batch_size
+
+    def _produce(self, k: int, slot: int) -> torch.cuda.Event:
+        lo = k * self.batch_size
+        hi = min(lo + self.batch_size, self.n_samples) + self.frame_skip
+        with torch.cuda.stream(self._copy_stream):
+            self._raw[slot][:hi - lo].copy_(self.frames[lo:hi], non_blocking=True)
+            stage_gray(self._raw[slot][:hi - lo], out=self._gray[slot][:hi - lo])
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return ev
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        nb = len(self)
+        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        ev = self._produce(0, 0)
+        for k in range(nb):
+            slot = k & 1
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            if k + 1 < nb:
+                # the other slot was consumed one iteration ago on the compute stream
+                self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+                ev = self._produce(k + 1, slot ^ 1)
+            lo = k * self.batch_size
+            b = min(self.batch_size, self.n_samples - lo)
+            x = sliding_window(self._gray[slot][:b + self.frame_skip], self.frame_skip)
+            y = self.labels[lo + self.frame_skip: lo + self.frame_skip + b]
+            yield x, y
+
+
+def sequential_train_val_test_iterator(hparams, frames_by_split=None):
+    """{'train_dataloader','val_dataloader','test_dataloader'} like
+    imitation_dataset.sequential_train_val_test_iterator (imitation_dataset.py:263-288).
+    `frames_by_split` maps split -> (frames_u8, labels); without it a synthetic sequence is
+    generated (the reference ships no data, BASELINE.json asks for synthetic frames)."""
+    bs = int(hparams['BATCH_SIZE'])
+    fs = int(hparams.get('frame_skip', 4)) if hasattr(hparams, 'get') else int(hparams['frame_skip'])
+    out = {}
+    for i, split in enumerate(("train", "val", "test")):
+        if frames_by_split is not None:
+            frames, labels = frames_by_split[split]
+        else:
+            frames, labels = synthetic_sequence(i, (8 if split == "train" else 2) * bs + fs,
+                                                n_actions=int(hparams['n_actions']))
+        out[f"{split}_dataloader"] = SequentialFrames(frames, labels, bs, fs)
+    return out

@@ -40,6 +40,8 @@ def stage_gray(frames_u8: torch.Tensor, dtype: torch.dtype = torch.float32, out:
     if out is None:
         out = torch.empty((n, h, w), dtype=dtype, device=frames_u8.device)
     code = {torch.float32: _lib.BC_F32, torch.bfloat16: _lib.BC_BF16}[out.dtype]
+    if n * h * w == 0:
+        return out
     _lib.check(_lib.lib().bc_stage_gray(frames_u8.data_ptr(), out.data_ptr(), n * h * w, code, _stream_ptr()), "bc_stage_gray")
     return out
 

@@ -16,8 +16,8 @@ import torch
 from . import _lib
 from .engine import _stream_ptr
 
-# state vector layout (csrc/abi.cu): lr beta1 beta2 eps step step_size bc2_sqrt grad_scale
-_LR, _B1, _B2, _EPS, _STEP, _SS, _BC2, _GS = range(8)
+# state vector layout (csrc/abi.cu), f64: lr beta1 beta2 eps step grad_scale step_size bc2_sqrt
+_LR, _B1, _B2, _EPS, _STEP, _GS, _SS, _BC2 = range(8)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -48,7 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
         old = self._bound
         m = torch.zeros_like(arena)
         v = torch.zeros_like(arena)
-        st = torch.zeros(8, dtype=torch.float32, device=arena.device)
+        st = torch.zeros(8, dtype=torch.float64, device=arena.device)
         if old is not None:  # the arena moved: carry the moments over
             m.copy_(old[1]); v.copy_(old[2]); st.copy_(old[3])
         g = self.param_groups[0]

@@ -93,14 +93,18 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream);
 int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream);   /* layer 1..3 -> gact[layer-1] */
 int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream);   /* layer 0..3 -> partials      */
 int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream); /* partials -> grads (, loss) */
+/* gradient segments in arena order: 0 = fc head, 1 = conv4, 2 = conv3, 3 = conv2, 4 = conv1; the
+ * data-parallel exchange reduces [0,4) first so its all-reduce overlaps conv1's wgrad */
+int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi, int with_loss, void* stream);
 int bc_loss_reduce(const bc_ctx* c, void* stream);                 /* head CTAs' CE partials -> loss (forward-only / validation_step) */
 
 /* ---- a11: Adam.step (src/models/imitation.py:82-87; torch.optim.Adam defaults).
- * state = {lr, beta1, beta2, eps, step(float), step_size, bc2_sqrt, grad_scale}; bc_adam_tick
- * increments step and derives the bias corrections in f64 on device (graph-replayable). */
-int bc_adam_tick(float* state, void* stream);
+ * state = 8 DOUBLES {lr, beta1, beta2, eps, step, grad_scale, step_size(out), bc2_sqrt(out)} on the
+ * device; bc_adam_tick increments step and derives the bias corrections in f64 like torch's Python
+ * scalars do (graph-replayable: nothing about the step number lives on the host). */
+int bc_adam_tick(double* state, void* stream);
 int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                 const float* state, int64_t n, void* stream);
+                 const double* state, int64_t n, void* stream);
 
 /* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
 int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);

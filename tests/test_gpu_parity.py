@@ -280,7 +280,7 @@ def test_fused_adam_matches_oracle_formula_elementwise():
     gen = torch.Generator().manual_seed(5)
     p = torch.randn(n, generator=gen); m = torch.zeros(n); v = torch.zeros(n)
     pd, md, vd = p.to(dev), m.to(dev), v.to(dev)
-    st = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0, 0, 0, 1.0], dtype=torch.float32, device=dev)
+    st = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0, 1.0, 0, 0], dtype=torch.float64, device=dev)
     lib, s = _lib.lib(), torch.cuda.current_stream().cuda_stream
     for t in range(1, 6):
         grad = torch.randn(n, generator=gen) * (10.0 ** (t - 3))
