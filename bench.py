@@ -58,7 +58,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep only samples taken inside [t0, t1] (host clock around the timed region)."""
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.15]
+        self.rows = [(0, r) for r in (inside if inside else [r for (_t, r) in self.rows][-3:])]
 
     def stop(self):
         if self.proc is None:
@@ -68,10 +73,11 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for (_t, r) in self.rows]
+        sm = sorted(float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -163,8 +169,6 @@ def run_b200(args):
     net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
     eng = net.engine()
     opt = FusedAdam(list(net.parameters()), lr=1e-3)
-    if world > 1:
-        opt.set_grad_scale(1.0 / world)
     staged_dtype = torch.bfloat16 if args.staged == "bf16" else torch.float32
 
     # ---- data: NBUF distinct frame windows per rank (rotated so inputs are never L2-resident) ----
@@ -179,13 +183,20 @@ def run_b200(args):
     gray = torch.empty((B + 4, 256, 256), dtype=staged_dtype, device=dev)
     bufs = eng.alloc(B, sliding_window(gray), dev_labels[0], True)
 
+    from carla_imitation_learning_b200.parallel import DataParallelStep
+    dp = DataParallelStep(eng, opt) if world > 1 else None   # 2-bucket exchange overlapped with conv1 wgrad
+
+    def train(b):
+        if dp is not None:
+            dp(b)
+        else:
+            eng.enqueue_train(b)
+            opt.step_flat(eng.grads)
+
     def device_step(i):
         stage_gray(dev_frames[i % NBUF], out=gray)
         bufs.y = dev_labels[i % NBUF]
-        eng.enqueue_train(bufs)
-        if world > 1:
-            dist.all_reduce(eng.grads)
-        opt.step_flat(eng.grads)
+        train(bufs)
 
     # CUDA graphs: one per input buffer (single GPU; the NCCL exchange stays eager for N > 1)
     graphs = None
@@ -211,20 +222,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    t_host1 = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        time.sleep(0.25)       # let the 100 ms sampler emit the rows that cover the end of the region
+        sampler.window(t_host0, t_host1)
+        clocks = sampler.stop()
     loss_dev = float(bufs.loss)
 
     # ---- e2e: host buffers in, loss out, every step -------------------------------------------
@@ -237,10 +254,7 @@ def run_b200(args):
         y_in.copy_(host_labels[i % NBUF], non_blocking=True)
         stage_gray(stage_in, out=gray)
         bufs.y = y_in
-        eng.enqueue_train(bufs)
-        if world > 1:
-            dist.all_reduce(eng.grads)
-        opt.step_flat(eng.grads)
+        train(bufs)
         loss_host.copy_(bufs.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
@@ -308,8 +322,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--staged", default="f32", choices=["f32", "bf16"])

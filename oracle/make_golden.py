@@ -114,6 +114,17 @@ def golden_gray(path):
     np.savez_compressed(path, gray_f64=ref, gray_f32=ref.astype(np.float32))
 
 
+def oracle_curve_f64(B, steps, data_seed, path):
+    """The same 1k-step run with the ORACLE in f64 (~5 min): measures how far rounding alone moves the
+    curve, which bounds what 'loss curves agree' can mean for any independent implementation."""
+    frames, labels = O.synth_frames(data_seed, steps * B + 4)
+    gray = torch.from_numpy(O.gray_stack(frames)); lab = torch.from_numpy(labels)
+    tr = O.OracleTrainer(O.init_params(SEED), dtype=torch.float64)
+    out = [tr.step(torch.stack([gray[s * B + i: s * B + i + 4] for i in range(B)]), lab[s * B + 4: s * B + 4 + B])
+           for s in range(steps)]
+    np.save(path, np.asarray(out, np.float64))
+
+
 if __name__ == "__main__":
     g = os.path.join(ROOT, "tests", "golden")
     os.makedirs(g, exist_ok=True)
@@ -123,3 +134,5 @@ if __name__ == "__main__":
     golden_labels(os.path.join(g, "ref_labels.npz"))
     golden_gray(os.path.join(g, "ref_gray.npz"))
     golden_curve(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k.npz"))
+    if "--f64-curve" in sys.argv:
+        oracle_curve_f64(8, 1000, 11, os.path.join(g, "oracle_curve_b8_1k_f64.npy"))
