@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "head.cu", "conv_bwd.cu", "abi.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 
@@ -50,6 +50,7 @@ EXPORTS = {
     "bc_adam_tick": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bc_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_tc_gemm_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bc_last_error_string": (C.c_char_p, []),
     "bc_device_check": (C.c_int, []),
     "bc_abi_version": (C.c_int, []),
@@ -61,7 +62,7 @@ _lib = None
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libbc_b200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "bc_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "bc_common.cuh"), os.path.join(CSRC, "tc05.cuh"), os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")

@@ -109,6 +109,11 @@ int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 /* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
 int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);
 
+/* ---- self-test of the tcgen05/TMEM primitives the bf16 conv kernels are built from:
+ * D[M,N] f32 = A[M,K] bf16 * B[N,K]^T bf16 (K contiguous). *err_flag is set to 1 if an mbarrier
+ * wait timed out (bounded waits: a protocol bug is an error code, not a hung GPU). */
+int bc_tc_gemm_selftest(const void* A, const void* B, float* D, int M, int N, int K, int* err_flag, void* stream);
+
 const char* bc_last_error_string(void);
 int bc_device_check(void);  /* BC_OK iff the current device is sm_100 */
 int bc_abi_version(void);
