@@ -169,6 +169,8 @@ def run_b200(args):
     net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
     eng = net.engine()
     opt = FusedAdam(list(net.parameters()), lr=1e-3)
+    if args.mode == "bf16":
+        args.staged = "bf16"
     staged_dtype = torch.bfloat16 if args.staged == "bf16" else torch.float32
 
     # ---- data: NBUF distinct frame windows per rank (rotated so inputs are never L2-resident) ----
@@ -193,8 +195,13 @@ def run_b200(args):
             eng.enqueue_train(b)
             opt.step_flat(eng.grads)
 
+    if args.mode == "bf16":
+        eng.set_mode("bf16")
+
     def device_step(i):
         stage_gray(dev_frames[i % NBUF], out=gray)
+        if args.mode == "bf16":
+            eng.pack_weights()                 # f32 master weights -> bf16 MMA operand images
         bufs.y = dev_labels[i % NBUF]
         train(bufs)
 
@@ -253,6 +260,8 @@ def run_b200(args):
         stage_in.copy_(host_frames[i % NBUF], non_blocking=True)
         y_in.copy_(host_labels[i % NBUF], non_blocking=True)
         stage_gray(stage_in, out=gray)
+        if args.mode == "bf16":
+            eng.pack_weights()
         bufs.y = y_in
         train(bufs)
         loss_host.copy_(bufs.loss, non_blocking=True)
@@ -297,7 +306,7 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": ("bf16" if args.mode == "bf16" else "f32"), "data": "synthetic",
             "config": {"workload": f"ConvNet1 BC train step (BASELINE configs[1]), obs 4x256x256, 9 actions, batch {B}/GPU, "
                                    f"u8 RGB frames staged to {args.staged} gray planes, sliding 4-frame window",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graphs is not None,
@@ -305,7 +314,7 @@ def run_b200(args):
                        "final_loss": loss_dev},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (B + 4) * FRAME_BYTES + 8 * B, "d2h_bytes_per_step": 4},
-            "gpu_launches": 16 * args.steps,
+            "gpu_launches": (17 if args.mode == "bf16" else 16) * args.steps,
             "roofline": {"kernel": "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)", "bound": "tensor",
                          "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
                          "traffic": None, "peak_source": peaks["src"], "kernel_ms": k_ms,
@@ -327,6 +336,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--staged", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 
@@ -29,7 +29,8 @@ class BcCtx(C.Structure):
         ("act", C.c_void_p * 4), ("amax", C.c_void_p * 4), ("gact", C.c_void_p * 3),
         ("ghead", C.c_void_p), ("hid1", C.c_void_p), ("hid2", C.c_void_p),
         ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p),
-        ("loss_scale", C.c_float), ("reserved", C.c_int32),
+        ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
+        ("w_packed", C.c_void_p), ("err_flag", C.c_void_p),
     ]
 
 
@@ -38,6 +39,8 @@ EXPORTS = {
     "bc_arena_layout": (C.c_int64, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bc_partials_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "bc_stage_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "bc_pack_weights": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
+    "bc_packed_weight_bytes": (C.c_size_t, []),
     "bc_forward": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_conv_relu_pool_fwd": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),
     "bc_head": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),

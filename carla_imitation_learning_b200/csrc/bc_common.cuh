@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include "../../include/bc_b200.h"
 
+int bc_conv1_tc_launch(const bc_ctx* c, void* stream);   // conv1_tc.cu
+
 namespace bc {
 
 // ---- error reporting (thread-local message, C-ABI returns the code) -------------------

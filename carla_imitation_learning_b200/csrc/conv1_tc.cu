@@ -1,0 +1,279 @@
+// K1 (bf16 tensor-core variant): Conv2d(4->16, 7x7, stride 3) + bias + ReLU + MaxPool(3), tcgen05.
+// Replaces cnn_base[0:3] of /root/reference/src/architectures/nets.py:18-20 in bf16 mode.
+//
+// GEMM shape problem: N = C_out = 16 makes a plain implicit GEMM operand-bandwidth bound
+// (each 128x16 A tile read feeds only 16 columns). Stride 3 < kernel 7 means neighbouring
+// windows overlap, so FOUR horizontally adjacent outputs share one 16-pixel input segment:
+//     D[(oy, g), (j, co)] = sum_{ci, ky, p<16}  in[ci][3*oy+ky][12*g + p] * Wt[(j,co)][(ci,ky,p)]
+//     Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3*j]   (0 <= p-3j < 7, else 0)      "Toeplitz" weights
+// i.e. M = (conv row, group of 4 columns), N = 4*16 = 64, K = 28 steps of 16 pixels: 44 % of the
+// issued MACs are useful, but A traffic per output drops 4x and every MMA is M=128,N=64,K=16.
+//
+// Per CTA (persistent, one per SM), tile = 6 conv rows x 84 columns of one frame (= 2 pooled rows):
+//   warp 0      loader   : cp.async.bulk (TMA engine) of the 4 x 22 raw input rows, double buffered
+//   warp 1      MMA      : one elected thread issues 28 tcgen05.mma per tile into TMEM (2 accumulators)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue : tcgen05.ld -> +bias -> smem -> 3x3 max / first-max argmax / ReLU -> global
+//   warps 8-15  repack   : raw rows -> 128x16 bf16 A chunks in the UMMA K-major canonical layout
+// mbarrier rings: raw full/empty, A-stage full/empty (8 stages), TMEM full/empty. All waits bounded.
+#include "bc_common.cuh"
+#include "tc05.cuh"
+
+namespace c1tc {
+
+constexpr int NTHREADS = 512;
+constexpr int ROWS_IN = 22;              // input rows per tile: 3*(6-1)+7
+constexpr int NG = 21;                   // groups of 4 output columns per conv row
+constexpr int MROWS = 126;               // 6 conv rows x 21 groups (of the MMA's 128)
+constexpr int NSTEP = 28;                // (ci, ky)
+constexpr int NST = 8;                   // A stages == repack warps
+constexpr int ROW_BYTES = 512;           // 256 px bf16
+constexpr int RAW_BYTES = 4 * ROWS_IN * ROW_BYTES;       // 45056
+constexpr int A_STAGE = 128 * 32;                        // 4096
+constexpr int B_STEP = 64 * 32;                          // 2048
+constexpr int B_BYTES = NSTEP * B_STEP;                  // 57344
+constexpr int S_PITCH = 68;                              // floats; 4-bank skew per row => conflict-free STS.128
+constexpr int S_BYTES = MROWS * S_PITCH * 4;             // 34272
+constexpr int OFF_B = 0;
+constexpr int OFF_RAW = OFF_B + B_BYTES;
+constexpr int OFF_A = OFF_RAW + 2 * RAW_BYTES;
+constexpr int OFF_S = OFF_A + NST * A_STAGE;
+constexpr int OFF_BAR = (OFF_S + S_BYTES + 127) / 128 * 128;
+constexpr int NBAR = 1 + 2 + 2 + NST + NST + 2 + 2;
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+constexpr int TILES_PER_FRAME = 14;
+constexpr int TMEM_COLS = 128;
+
+// fp32 OIHW conv1 weights -> Toeplitz bf16 operand, already in the smem image the MMA reads:
+// step s=(ci,ky): 64 rows n=(j*16+co) x 16 k, chunk c=k/8 at c*1024 + n*16 bytes
+__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NSTEP * 64 * 16) return;
+    const int k = i & 15, n = (i >> 4) & 63, s = i >> 10;
+    const int ci = s / 7, ky = s % 7, j = n >> 4, co = n & 15;
+    const int kx = k - 3 * j;
+    const float v = (kx >= 0 && kx < 7) ? w[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
+    out[(size_t)s * (B_STEP / 2) + (k >> 3) * 512 + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
+                const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax, int B, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* b_full = bars;
+    uint64_t* raw_full = bars + 1;
+    uint64_t* raw_empty = bars + 3;
+    uint64_t* a_full = bars + 5;
+    uint64_t* a_empty = bars + 5 + NST;
+    uint64_t* t_full = bars + 5 + 2 * NST;
+    uint64_t* t_empty = bars + 7 + 2 * NST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = B * TILES_PER_FRAME;
+
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(b_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc05::mbar_init(raw_full + i, 1);
+            tc05::mbar_init(raw_empty + i, NST);
+            tc05::mbar_init(t_full + i, 1);
+            tc05::mbar_init(t_empty + i, 4);
+        }
+        for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 2) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
+    // rows 126,127 of every A stage are never produced: keep them zero
+    for (int i = threadIdx.x; i < NST * 2 * 2 * 4; i += NTHREADS) {
+        const int st = i / 16, rem = i % 16, c = rem / 8, r = 126 + (rem % 8) / 4, q = rem % 4;
+        reinterpret_cast<uint32_t*>(smem + OFF_A + st * A_STAGE + c * 2048 + r * 16)[q] = 0u;
+    }
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader
+        if (lane == 0) {
+            tc05::mbar_expect_tx(b_full, B_BYTES);
+            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                if (!tc05::mbar_wait(raw_empty + buf, ((it >> 1) & 1) ^ 1, err)) break;
+                const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
+                const __nv_bfloat16* src = x + (size_t)b * sn + (size_t)(ty * 18) * 256;
+                tc05::mbar_expect_tx(raw_full + buf, RAW_BYTES);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci)   // 22 rows of one plane are contiguous: one 11 KB bulk copy each
+                    tc05::bulk_g2s(smem + OFF_RAW + buf * RAW_BYTES + ci * ROWS_IN * ROW_BYTES, src + (size_t)ci * sc,
+                                   ROWS_IN * ROW_BYTES, raw_full + buf);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
+            const uint32_t a0 = tc05::smem_u32(smem + OFF_A), b0 = tc05::smem_u32(smem + OFF_B);
+            bool ok = tc05::mbar_wait(b_full, 0, err);
+            int it = 0;
+            uint32_t gs = 0;
+            for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
+                tc05::tc_fence_after();
+                for (int s = 0; ok && s < NSTEP; ++s, ++gs) {
+                    const int st = gs % NST;
+                    ok = tc05::mbar_wait(a_full + st, (gs / NST) & 1, err);
+                    tc05::tc_fence_after();
+                    const uint64_t ad = tc05::smem_desc(a0 + st * A_STAGE, 2048, 128, tc05::SW_NONE);
+                    const uint64_t bd = tc05::smem_desc(b0 + s * B_STEP, 1024, 128, tc05::SW_NONE);
+                    tc05::mma_bf16(tmem_base + acc * 64, ad, bd, idesc, s > 0);
+                    tc05::mma_commit(a_empty + st);            // stage reusable once this MMA has read it
+                }
+                if (ok) tc05::mma_commit(t_full + acc);        // accumulator complete
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ epilogue
+        const int ew = warp - 4;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
+        const int te = threadIdx.x - 128;        // 0..127
+        const int r = ew * 32 + lane;            // accumulator row
+        float* S = reinterpret_cast<float*>(smem + OFF_S);
+        float breg[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) breg[i] = bias[(te + 128 * i) & 15];
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
+            tc05::tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float v[16];
+                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 64 + c0, v);
+                tc05::tmem_ld_wait();
+                if (r < MROWS) {
+                    float4* dst = reinterpret_cast<float4*>(S + r * S_PITCH + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+            tc05::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(t_empty + acc);   // MMA may overwrite this accumulator
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // S complete (epilogue warps only)
+            const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int o = te + 128 * i;                     // 2 pooled rows x 28 x 16 = 896 outputs
+                const int co = o & 15, px = (o >> 4) % 28, pyl = o / 448;
+                // S[(oy_l*21 + ox/4) * S_PITCH + (ox%4)*16 + co], ox = 3*px + dx
+                int coff[3];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int ox = 3 * px + dx;
+                    coff[dx] = (ox >> 2) * S_PITCH + (ox & 3) * 16 + co;
+                }
+                const float* s0 = S + (3 * pyl) * NG * S_PITCH;
+                float best = s0[coff[0]];
+                int idx = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (dy == 0 && dx == 0) continue;
+                        const float v = s0[dy * NG * S_PITCH + coff[dx]];
+                        if (v > best) { best = v; idx = dy * 3 + dx; }     // strict: first maximum wins
+                    }
+                const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
+                y[g] = fmaxf(best + breg[i], 0.f);
+                amax[g] = (uint8_t)idx;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone done reading S
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ repack (A producer)
+        const int rw = warp - 8;                 // stage owned by this warp
+        int src_off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = q * 32 + lane;
+            src_off[q] = r < MROWS ? (3 * (r / NG)) * ROW_BYTES + 24 * (r % NG) : -1;
+        }
+        int it = 0;
+        uint32_t use = 0;                         // fills of this warp's stage so far
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            if (!tc05::mbar_wait(raw_full + buf, (it >> 1) & 1, err)) break;
+            const uint8_t* raw = smem + OFF_RAW + buf * RAW_BYTES;
+            const uint32_t gs0 = (uint32_t)it * NSTEP;
+            bool ok = true;
+            for (int s = (int)((rw + NST - gs0 % NST) % NST); s < NSTEP; s += NST, ++use) {
+                ok = tc05::mbar_wait(a_empty + rw, (use & 1) ^ 1, err);
+                if (!ok) break;
+                const int ci = s / 7, ky = s % 7;
+                const uint8_t* base = raw + (ci * ROWS_IN + ky) * ROW_BYTES;
+                uint8_t* dst = smem + OFF_A + rw * A_STAGE;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (src_off[q] >= 0) {
+                        const uint2* p = reinterpret_cast<const uint2*>(base + src_off[q]);
+                        const uint2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+                        uint8_t* d = dst + (q * 32 + lane) * 16;
+                        *reinterpret_cast<uint4*>(d) = make_uint4(v0.x, v0.y, v1.x, v1.y);
+                        *reinterpret_cast<uint4*>(d + 2048) = make_uint4(v2.x, v2.y, v3.x, v3.y);
+                    }
+                }
+                tc05::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(a_full + rw);
+            }
+            if (!ok) break;
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(raw_empty + buf);
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace c1tc
+
+extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c && c->params && c->w_packed, "bc_pack_weights: null buffer");
+    BC_CHECK_ARG(c->obs_size == 4, "bc_pack_weights: the tcgen05 conv1 operand exists for obs_size 4 only");
+    const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
+    c1tc::pack_conv1_weights_kernel<<<(c1tc::NSTEP * 1024 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        c->params + a.w[0], (__nv_bfloat16*)c->w_packed);
+    BC_CUDA_LAUNCH_CHECK("pack_conv1_weights_kernel");
+    return BC_OK;
+}
+
+extern "C" size_t bc_packed_weight_bytes(void) { return c1tc::B_BYTES; }
+
+int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c->x && c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05): null buffer (x, w_packed, err_flag, act, amax)");
+    BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 (tcgen05): needs bf16 gray planes and obs_size 4");
+    BC_CHECK_ARG(((uintptr_t)c->x % 16 == 0) && (c->x_stride_n * 2) % 16 == 0 && (c->x_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
+                 "conv1 (tcgen05): x, its strides and w_packed must be 16 B aligned");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(c1tc::conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tc::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05): smem opt-in %d B failed: %s", c1tc::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
+    const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
+    int grid = bc::num_sms();
+    if (grid > ntiles) grid = ntiles;
+    c1tc::conv1_tc_kernel<<<grid, c1tc::NTHREADS, c1tc::SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
+        c->act[0], c->amax[0], c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK("conv1_tc_kernel");
+    return BC_OK;
+}

@@ -30,9 +30,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as an error code, never as a hung GPU.
-// Returns false (and raises *err) after ~2^22 failed polls (each poll already sleeps in HW).
+// Returns false (and raises *err) after ~2^20 failed polls (each poll already sleeps in HW).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err) {
-    for (uint32_t it = 0; it < (1u << 22); ++it)
+    for (uint32_t it = 0; it < (1u << 20); ++it)
         if (mbar_try_wait(bar, parity)) return true;
     if (err) atomicExch(err, 1);
     return false;

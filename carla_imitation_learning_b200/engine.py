@@ -95,6 +95,10 @@ class BCEngine:
         # partial-sum workspace: pads are never written, so it must start zeroed
         self.partials = torch.zeros(int(self.lib.bc_partials_floats(self.obs_size, self.n_actions)),
                                     dtype=torch.float32, device=self.device)
+        # bf16 tensor-core mode: packed MMA operand images + the device error flag of the bounded waits
+        self.w_packed = torch.zeros(int(self.lib.bc_packed_weight_bytes()), dtype=torch.uint8, device=self.device)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.conv_mode = 0            # 0 exact f32 FFMA; 1 bf16 tcgen05 (needs bf16 gray planes, obs_size 4)
 
     # ------------------------------------------------------------------ buffers
     def alloc(self, batch: int, x: torch.Tensor, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
@@ -146,7 +150,26 @@ class BCEngine:
         c.logits, c.dlogits, c.loss = b.logits.data_ptr(), b.dlogits.data_ptr(), b.loss.data_ptr()
         c.partials = self.partials.data_ptr()
         c.loss_scale = (1.0 / max(b.batch, 1)) if loss_scale is None else float(loss_scale)
+        c.conv_mode = self.conv_mode
+        c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
         return c
+
+    def set_mode(self, mode: str) -> None:
+        """'fp32' = exact FFMA kernels (rel 1e-5); 'bf16' = tcgen05 kernels on bf16-staged frames (rel 2e-2)."""
+        self.conv_mode = {"fp32": 0, "bf16": 1}[mode]
+
+    def pack_weights(self) -> None:
+        """Refresh the bf16 operand images from the f32 master weights (after every optimiser step in bf16 mode)."""
+        c = _lib.BcCtx()
+        c.obs_size, c.n_actions = self.obs_size, self.n_actions
+        c.params, c.w_packed = self.arena.data_ptr(), self.w_packed.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bc_pack_weights(C.byref(c), _stream_ptr()), "bc_pack_weights")
+
+    def check_device_errors(self) -> None:
+        """Host-side check of the bounded-wait flag (synchronises; call outside the hot loop)."""
+        if int(self.err_flag.item()) != 0:
+            raise RuntimeError("a tcgen05 pipeline wait timed out inside a kernel (mbarrier protocol error)")
 
     # ------------------------------------------------------------------ kernels
     def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, backward: bool = False,

@@ -67,7 +67,9 @@ typedef struct {
     float* loss;             /* [1] mean CE                             */
     float* partials;         /* workspace, bc_partials_floats() floats  */
     float loss_scale;        /* dlogits = (softmax-onehot)*loss_scale; 1/batch for the mean */
-    int32_t reserved;
+    int32_t conv_mode;       /* 0 = exact f32 FFMA kernels; 1 = bf16 tcgen05 kernels where they exist */
+    void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
+    int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);
@@ -77,6 +79,11 @@ size_t bc_partials_floats(int obs_size, int n_actions);
  * numpy, rounded to f32 (or bf16). A sample is 4 consecutive planes, so the sliding window
  * of the reference's shuffle=False loader is the strided view x_stride_n = H*W, x_stride_c = H*W. */
 int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream);
+
+/* bf16 tensor-core mode: re-pack the f32 master weights into the smem images the tcgen05 kernels
+ * read (conv1: Toeplitz-expanded [64 x 448] bf16). Call after every optimiser step. */
+int bc_pack_weights(const bc_ctx* c, void* stream);
+size_t bc_packed_weight_bytes(void);
 
 /* ---- a4-a8: ConvNet1.forward (src/architectures/nets.py:35-39): conv+ReLU+pool x4, MLP.
  * Writes act[], amax[], hid1, hid2, logits. */

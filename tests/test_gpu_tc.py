@@ -26,3 +26,64 @@ def test_tc_gemm_selftest(M, N, K):
     assert torch.isfinite(got).all()
     # bf16 products are exact in f32; only the f32 accumulation order differs
     assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) * max(1, K // 64)
+
+
+@pytest.mark.parametrize("B", [1, 3, 40])
+def test_conv1_tcgen05_matches_bf16_rounded_oracle(B):
+    """conv1+ReLU+pool on tensor cores == f64 conv of the bf16-ROUNDED inputs and weights (products of
+    bf16 values are exact in f32, so only accumulation order separates the two): rel 1e-5, plus routing."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib, stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    from tests.test_gpu_parity import _check_routing
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    frames, _ = O.synth_frames(50 + B, B + 4)
+    gray = stage_gray(torch.from_numpy(frames).to(dev), dtype=torch.bfloat16)
+    x = sliding_window(gray)
+    bufs = eng.alloc(B, x, None, False)
+    c = eng.ctx(bufs)
+    _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, torch.cuda.current_stream().cuda_stream), "conv1 tc")
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    w = net.cnn_base[0].weight.detach().to(torch.bfloat16).double().cpu()
+    bias = net.cnn_base[0].bias.detach().double().cpu()
+    z = torch.nn.functional.conv2d(x.double().cpu(), w, bias, stride=3)
+    ref = torch.nn.functional.max_pool2d(torch.relu(z), 3)
+    got = bufs.act[0].cpu().double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5, err
+    _check_routing(z, bufs.amax[0].cpu(), got, 3)
+    # and against the un-rounded f32 network it is inside the bf16 tolerance of the north star
+    z32 = torch.nn.functional.conv2d(x.float().cpu().double(), net.cnn_base[0].weight.detach().double().cpu(), bias, stride=3)
+    ref32 = torch.nn.functional.max_pool2d(torch.relu(z32), 3)
+    assert float((got - ref32).abs().max() / ref32.abs().max()) <= 2e-2
+
+
+def test_bf16_mode_training_step_within_tolerance():
+    from carla_imitation_learning_b200 import stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    frames, labels = O.synth_frames(77, 36)
+    y = torch.from_numpy(labels[4:36]).to(dev)
+    fr = torch.from_numpy(frames).to(dev)
+    b32 = eng.train_forward_backward(sliding_window(stage_gray(fr)), y)
+    g32 = eng.grads.clone()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    b16 = eng.train_forward_backward(sliding_window(stage_gray(fr, dtype=torch.bfloat16)), y)
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(b16.logits, b32.logits) <= 2e-2
+    assert abs(float(b16.loss) - float(b32.loss)) <= 2e-2 * float(b32.loss)
+    assert rel(eng.grads, g32) <= 0.1      # includes pool-routing flips caused by the bf16 rounding
