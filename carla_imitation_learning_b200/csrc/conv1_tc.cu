@@ -10,42 +10,51 @@
 // issued MACs are useful, but A traffic per output drops 4x and every MMA is M=128,N=64,K=16.
 //
 // Per CTA (persistent, one per SM), tile = 6 conv rows x 84 columns of one frame (= 2 pooled rows):
-//   warp 0      loader   : cp.async.bulk (TMA engine) of the 4 x 22 raw input rows, double buffered
-//   warp 1      MMA      : one elected thread issues 28 tcgen05.mma per tile into TMEM (2 accumulators)
+//   warp 0      loader   : cp.async.bulk (TMA engine), one 11 KB copy per input plane (22 contiguous rows),
+//                          pipelined PER PLANE: plane ci of tile t+1 streams in while planes ci+1.. of tile t repack
+//   warp 1      MMA      : one thread issues 28 tcgen05.mma per tile (fully unrolled, static descriptors)
+//                          into one of two TMEM accumulators
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue : tcgen05.ld -> +bias -> smem -> 3x3 max / first-max argmax / ReLU -> global
-//   warps 8-15  repack   : raw rows -> 128x16 bf16 A chunks in the UMMA K-major canonical layout
-// mbarrier rings: raw full/empty, A-stage full/empty (8 stages), TMEM full/empty. All waits bounded.
+//   warps 4-7   epilogue : tcgen05.ld -> smem -> 3x3 max / first-max argmax / +bias / ReLU -> global
+//   warps 8-14  repack   : warp w = kernel row ky: raw rows -> 128x16 bf16 A chunk (UMMA K-major canonical layout)
+// mbarrier rings: plane full/empty (4), A-stage full/empty (14 stages), TMEM full/empty (2). All waits bounded.
 #include "bc_common.cuh"
 #include "tc05.cuh"
 
 namespace c1tc {
 
-constexpr int NTHREADS = 512;
+constexpr int NREPACK = 7;               // repack warps: warp w owns kernel row ky = w
+constexpr int NTHREADS = (8 + NREPACK) * 32;   // 480
 constexpr int ROWS_IN = 22;              // input rows per tile: 3*(6-1)+7
 constexpr int NG = 21;                   // groups of 4 output columns per conv row
 constexpr int MROWS = 126;               // 6 conv rows x 21 groups (of the MMA's 128)
-constexpr int NSTEP = 28;                // (ci, ky)
-constexpr int NST = 8;                   // A stages == repack warps
+constexpr int NSTEP = 28;                // K steps (ci, ky) of 16 pixels
+constexpr int NST = 7;                   // A stages: stage ky holds the TWO chunks (2cp, ky), (2cp+1, ky) of one fill
 constexpr int ROW_BYTES = 512;           // 256 px bf16
-constexpr int RAW_BYTES = 4 * ROWS_IN * ROW_BYTES;       // 45056
-constexpr int A_STAGE = 128 * 32;                        // 4096
+constexpr int PLANE_BYTES = ROWS_IN * ROW_BYTES;         // 11264: the tile's rows of one input plane, contiguous in HBM
+constexpr int A_CHUNK = 128 * 32;                        // 4096: one K=16 slice of the 128-row A tile
+constexpr int A_STAGE = 2 * A_CHUNK;                     // 8192
 constexpr int B_STEP = 64 * 32;                          // 2048
 constexpr int B_BYTES = NSTEP * B_STEP;                  // 57344
 constexpr int S_PITCH = 68;                              // floats; 4-bank skew per row => conflict-free STS.128
 constexpr int S_BYTES = MROWS * S_PITCH * 4;             // 34272
 constexpr int OFF_B = 0;
-constexpr int OFF_RAW = OFF_B + B_BYTES;
-constexpr int OFF_A = OFF_RAW + 2 * RAW_BYTES;
+constexpr int OFF_RAW = OFF_B + B_BYTES;                 // 4 plane buffers (pipelined per plane, not per tile)
+constexpr int OFF_A = OFF_RAW + 4 * PLANE_BYTES;
 constexpr int OFF_S = OFF_A + NST * A_STAGE;
 constexpr int OFF_BAR = (OFF_S + S_BYTES + 127) / 128 * 128;
-constexpr int NBAR = 1 + 2 + 2 + NST + NST + 2 + 2;
+constexpr int NBAR = 1 + 4 + 4 + NST + NST + 2 + 2;
 constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
 constexpr int TILES_PER_FRAME = 14;
 constexpr int TMEM_COLS = 128;
 
+// UMMA K-major no-swizzle canonical layout used for both operands: a K=16 slice of `rows` rows is
+// stored as 8-row groups of 256 B; inside a group the two 16-byte K-chunks are 128 B apart:
+//   byte(r, k) = (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2          => LBO = 128 B, SBO = 256 B
+__host__ __device__ constexpr int op_off(int r, int chunk) { return (r >> 3) * 256 + chunk * 128 + (r & 7) * 16; }
+
 // fp32 OIHW conv1 weights -> Toeplitz bf16 operand, already in the smem image the MMA reads:
-// step s=(ci,ky): 64 rows n=(j*16+co) x 16 k, chunk c=k/8 at c*1024 + n*16 bytes
+// step s=(ci,ky): 64 rows n=(j*16+co) x 16 k
 __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NSTEP * 64 * 16) return;
@@ -53,7 +62,7 @@ __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bflo
     const int ci = s / 7, ky = s % 7, j = n >> 4, co = n & 15;
     const int kx = k - 3 * j;
     const float v = (kx >= 0 && kx < 7) ? w[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
-    out[(size_t)s * (B_STEP / 2) + (k >> 3) * 512 + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    out[(size_t)s * (B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -62,32 +71,28 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* b_full = bars;
-    uint64_t* raw_full = bars + 1;
-    uint64_t* raw_empty = bars + 3;
-    uint64_t* a_full = bars + 5;
-    uint64_t* a_empty = bars + 5 + NST;
-    uint64_t* t_full = bars + 5 + 2 * NST;
-    uint64_t* t_empty = bars + 7 + 2 * NST;
+    uint64_t* raw_full = bars + 1;                 // [4] one per input plane
+    uint64_t* raw_empty = bars + 5;                // [4]
+    uint64_t* a_full = bars + 9;                   // [NST]
+    uint64_t* a_empty = bars + 9 + NST;            // [NST]
+    uint64_t* t_full = bars + 9 + 2 * NST;         // [2]
+    uint64_t* t_empty = bars + 11 + 2 * NST;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = B * TILES_PER_FRAME;
 
     if (threadIdx.x == 0) {
         tc05::mbar_init(b_full, 1);
-        for (int i = 0; i < 2; ++i) {
-            tc05::mbar_init(raw_full + i, 1);
-            tc05::mbar_init(raw_empty + i, NST);
-            tc05::mbar_init(t_full + i, 1);
-            tc05::mbar_init(t_empty + i, 4);
-        }
+        for (int i = 0; i < 4; ++i) { tc05::mbar_init(raw_full + i, 1); tc05::mbar_init(raw_empty + i, NREPACK); }
+        for (int i = 0; i < 2; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
         for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
         tc05::mbar_fence_init();
     }
     if (warp == 2) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
     // rows 126,127 of every A stage are never produced: keep them zero
-    for (int i = threadIdx.x; i < NST * 2 * 2 * 4; i += NTHREADS) {
-        const int st = i / 16, rem = i % 16, c = rem / 8, r = 126 + (rem % 8) / 4, q = rem % 4;
-        reinterpret_cast<uint32_t*>(smem + OFF_A + st * A_STAGE + c * 2048 + r * 16)[q] = 0u;
+    for (int i = threadIdx.x; i < NST * 2 * 2 * 2 * 4; i += NTHREADS) {
+        const int ch = i / 16, rem = i % 16, c = rem / 8, r = 126 + (rem % 8) / 4, q = rem % 4;   // ch = stage*2 + chunk
+        reinterpret_cast<uint32_t*>(smem + OFF_A + ch * A_CHUNK + op_off(r, c))[q] = 0u;
     }
     tc05::fence_async_smem();
     tc05::tc_fence_before();
@@ -96,45 +101,53 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ loader
+        // ------------------------------------------------------------------ loader (one lane)
         if (lane == 0) {
             tc05::mbar_expect_tx(b_full, B_BYTES);
             tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
             int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                if (!tc05::mbar_wait(raw_empty + buf, ((it >> 1) & 1) ^ 1, err)) break;
+            bool ok = true;
+            for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
                 const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
                 const __nv_bfloat16* src = x + (size_t)b * sn + (size_t)(ty * 18) * 256;
-                tc05::mbar_expect_tx(raw_full + buf, RAW_BYTES);
 #pragma unroll
-                for (int ci = 0; ci < 4; ++ci)   // 22 rows of one plane are contiguous: one 11 KB bulk copy each
-                    tc05::bulk_g2s(smem + OFF_RAW + buf * RAW_BYTES + ci * ROWS_IN * ROW_BYTES, src + (size_t)ci * sc,
-                                   ROWS_IN * ROW_BYTES, raw_full + buf);
+                for (int ci = 0; ci < 4; ++ci) {
+                    // plane buffer ci is free once all repack warps are past plane ci of the previous tile
+                    ok = ok && tc05::mbar_wait(raw_empty + ci, (it & 1) ^ 1, err);
+                    if (!ok) break;
+                    tc05::mbar_expect_tx(raw_full + ci, PLANE_BYTES);
+                    tc05::bulk_g2s(smem + OFF_RAW + ci * PLANE_BYTES, src + (size_t)ci * sc, PLANE_BYTES, raw_full + ci);
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
-            const uint32_t a0 = tc05::smem_u32(smem + OFF_A), b0 = tc05::smem_u32(smem + OFF_B);
-            bool ok = tc05::mbar_wait(b_full, 0, err);
-            int it = 0;
-            uint32_t gs = 0;
-            for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-                const int acc = it & 1;
-                ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
+        // The whole warp runs the loop (so every operand stays in uniform registers); one elected lane
+        // issues. Per tile: 14 stage visits (cp-major, ky-minor), 2 MMAs + 1 commit each.
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_A), 128, 256, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_B), 128, 256, tc05::SW_NONE);
+        bool ok = tc05::mbar_wait(b_full, 0, err);
+        int it = 0;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
+            tc05::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 64;
+#pragma unroll
+            for (int v = 0; v < 14; ++v) {
+                const int cp = v / 7, ky = v % 7;            // static after unrolling
+                if (ok) ok = tc05::mbar_wait(a_full + ky, (uint32_t)(it * 2 + cp) & 1, err);
                 tc05::tc_fence_after();
-                for (int s = 0; ok && s < NSTEP; ++s, ++gs) {
-                    const int st = gs % NST;
-                    ok = tc05::mbar_wait(a_full + st, (gs / NST) & 1, err);
-                    tc05::tc_fence_after();
-                    const uint64_t ad = tc05::smem_desc(a0 + st * A_STAGE, 2048, 128, tc05::SW_NONE);
-                    const uint64_t bd = tc05::smem_desc(b0 + s * B_STEP, 1024, 128, tc05::SW_NONE);
-                    tc05::mma_bf16(tmem_base + acc * 64, ad, bd, idesc, s > 0);
-                    tc05::mma_commit(a_empty + st);            // stage reusable once this MMA has read it
+                if (ok && tc05::elect_one()) {
+                    // descriptors differ from the base only in the 14-bit start-address field (>>4)
+                    const uint64_t a0 = ad0 + (uint64_t)(ky * (A_STAGE >> 4));
+                    tc05::mma_bf16(d_tmem, a0, bd0 + (uint64_t)(((2 * cp) * 7 + ky) * (B_STEP >> 4)), idesc, v > 0);
+                    tc05::mma_bf16(d_tmem, a0 + (A_CHUNK >> 4), bd0 + (uint64_t)(((2 * cp + 1) * 7 + ky) * (B_STEP >> 4)), idesc, 1);
+                    tc05::mma_commit(a_empty + ky);          // stage reusable once both MMAs have read it
+                    if (v == 13) tc05::mma_commit(t_full + acc);   // accumulator complete
                 }
-                if (ok) tc05::mma_commit(t_full + acc);        // accumulator complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -151,20 +164,18 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
             const int acc = it & 1;
             if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
             tc05::tc_fence_after();
+            float v[64];
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                float v[16];
-                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 64 + c0, v);
-                tc05::tmem_ld_wait();
-                if (r < MROWS) {
-                    float4* dst = reinterpret_cast<float4*>(S + r * S_PITCH + c0);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-            }
+            for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 64 + c0, v + c0);
+            tc05::tmem_ld_wait();
             tc05::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(t_empty + acc);   // MMA may overwrite this accumulator
+            if (lane == 0) tc05::mbar_arrive(t_empty + acc);   // accumulator drained: the MMA may overwrite it
+            if (r < MROWS) {
+                float4* dst = reinterpret_cast<float4*>(S + r * S_PITCH);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");      // S complete (epilogue warps only)
             const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
 #pragma unroll
@@ -186,8 +197,8 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
 #pragma unroll
                     for (int dx = 0; dx < 3; ++dx) {
                         if (dy == 0 && dx == 0) continue;
-                        const float v = s0[dy * NG * S_PITCH + coff[dx]];
-                        if (v > best) { best = v; idx = dy * 3 + dx; }     // strict: first maximum wins
+                        const float vv = s0[dy * NG * S_PITCH + coff[dx]];
+                        if (vv > best) { best = vv; idx = dy * 3 + dx; }     // strict: first maximum wins
                     }
                 const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
                 y[g] = fmaxf(best + breg[i], 0.f);
@@ -196,45 +207,51 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
             asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone done reading S
         }
     } else if (warp >= 8) {
-        // ------------------------------------------------------------------ repack (A producer)
-        const int rw = warp - 8;                 // stage owned by this warp
-        int src_off[4];
+        // ------------------------------------------------------------------ repack (A producer); warp <-> ky
+        const int ky = warp - 8;
+        int src_off[4], dst_off[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int r = q * 32 + lane;
-            src_off[q] = r < MROWS ? (3 * (r / NG)) * ROW_BYTES + 24 * (r % NG) : -1;
+            src_off[q] = r < MROWS ? (3 * (r / NG) + ky) * ROW_BYTES + 24 * (r % NG) : -1;
+            dst_off[q] = op_off(r, 0);
         }
+        uint32_t fills = 0;                       // fills of stage ky by this warp: 2 per tile (channel pairs)
+        bool ok = true;
         int it = 0;
-        uint32_t use = 0;                         // fills of this warp's stage so far
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            if (!tc05::mbar_wait(raw_full + buf, (it >> 1) & 1, err)) break;
-            const uint8_t* raw = smem + OFF_RAW + buf * RAW_BYTES;
-            const uint32_t gs0 = (uint32_t)it * NSTEP;
-            bool ok = true;
-            for (int s = (int)((rw + NST - gs0 % NST) % NST); s < NSTEP; s += NST, ++use) {
-                ok = tc05::mbar_wait(a_empty + rw, (use & 1) ^ 1, err);
-                if (!ok) break;
-                const int ci = s / 7, ky = s % 7;
-                const uint8_t* base = raw + (ci * ROWS_IN + ky) * ROW_BYTES;
-                uint8_t* dst = smem + OFF_A + rw * A_STAGE;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (src_off[q] >= 0) {
-                        const uint2* p = reinterpret_cast<const uint2*>(base + src_off[q]);
-                        const uint2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
-                        uint8_t* d = dst + (q * 32 + lane) * 16;
-                        *reinterpret_cast<uint4*>(d) = make_uint4(v0.x, v0.y, v1.x, v1.y);
-                        *reinterpret_cast<uint4*>(d + 2048) = make_uint4(v2.x, v2.y, v3.x, v3.y);
-                    }
+            for (int cp = 0; cp < 2; ++cp, ++fills) {
+                ok = ok && tc05::mbar_wait(raw_full + 2 * cp, it & 1, err) && tc05::mbar_wait(raw_full + 2 * cp + 1, it & 1, err);
+                ok = ok && tc05::mbar_wait(a_empty + ky, (fills & 1) ^ 1, err);
+                if (!ok) break;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint8_t* base = smem + OFF_RAW + (2 * cp + h) * PLANE_BYTES;
+                    uint8_t* dst = smem + OFF_A + ky * A_STAGE + h * A_CHUNK;
+                    uint2 v[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (src_off[q] >= 0) {
+                            const uint2* p = reinterpret_cast<const uint2*>(base + src_off[q]);
+                            v[q][0] = p[0]; v[q][1] = p[1]; v[q][2] = p[2]; v[q][3] = p[3];
+                        }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (src_off[q] >= 0) {
+                            uint8_t* d = dst + dst_off[q];
+                            *reinterpret_cast<uint4*>(d) = make_uint4(v[q][0].x, v[q][0].y, v[q][1].x, v[q][1].y);
+                            *reinterpret_cast<uint4*>(d + 128) = make_uint4(v[q][2].x, v[q][2].y, v[q][3].x, v[q][3].y);
+                        }
                 }
                 tc05::fence_async_smem();
                 __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(a_full + rw);
+                if (lane == 0) {
+                    tc05::mbar_arrive(a_full + ky);
+                    tc05::mbar_arrive(raw_empty + 2 * cp);       // done with both planes of this pair for this tile
+                    tc05::mbar_arrive(raw_empty + 2 * cp + 1);
+                }
             }
-            if (!ok) break;
-            __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(raw_empty + buf);
         }
     }
     tc05::tc_fence_before();

@@ -66,7 +66,77 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const __nv_bfloat
     if (warp == 0) tc05::tmem_dealloc(tmem_base, 256);
 }
 
+// Micro-benchmark: cycles per tcgen05.mma (M=128, K=16, bf16) as a function of N, operands resident
+// in shared memory, `reps` back-to-back instructions into one accumulator.
+// mode 0: same A/B every time, one commit at the end; mode 1: A cycles over 8 stages;
+// mode 2: one tcgen05.commit per MMA (nobody waits on them);
+// mode 3+: full producer/consumer ring with NS = mode-2 stages: warp 1+st "refills" stage st (waits the
+//          stage's empty barrier, fence.proxy.async, arrives on its full barrier), the MMA thread waits full,
+//          issues, commits to empty -- the synchronisation skeleton of the conv kernels without any data movement.
+__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, long long* cycles, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar, full[14], empty[14];
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NS = mode >= 3 ? mode - 2 : 0;
+    for (int i = threadIdx.x; i < (8 * 4096 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(&bar, 1);
+        for (int i = 0; i < 14; ++i) { tc05::mbar_init(full + i, 1); tc05::mbar_init(empty + i, 1); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(&tmem_base_s, 256);
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, (uint32_t)N, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, 256, tc05::SW_NONE);
+        const long long t0 = clock64();
+        bool ok = true;
+        for (int i = 0; ok && i < reps; ++i) {
+            if (NS) {
+                ok = tc05::mbar_wait(full + i % NS, (i / NS) & 1, err);
+                tc05::tc_fence_after();
+            }
+            tc05::mma_bf16(tmem_base, ad0 + (mode ? (uint64_t)((i & 7) * 256) : 0), bd0, idesc, i > 0);
+            if (NS) tc05::mma_commit(empty + i % NS);
+            else if (mode == 2) tc05::mma_commit(full + (i % 14));
+        }
+        tc05::mma_commit(&bar);
+        const long long t1 = clock64();
+        tc05::mbar_wait(&bar, 0, err);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
+    } else if (NS && warp >= 1 && warp <= NS) {
+        const int st = warp - 1;
+        bool ok = true;
+        for (int u = 0; ok && st + u * NS < reps; ++u) {
+            ok = tc05::mbar_wait(empty + st, (u & 1) ^ 1, err);
+            // stand-in for the repack: one 16-byte store per lane into the stage
+            reinterpret_cast<uint4*>(smem + (st & 7) * 4096)[lane] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(full + st);
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
+
+extern "C" int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream) {
+    BC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && cycles2 && err_flag, "bc_tc_mma_bench: bad arguments");
+    const int smem = 8 * 4096 + 8192;
+    tc_mma_bench_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(N, reps, mode, cycles2, err_flag);
+    BC_CUDA_LAUNCH_CHECK("tc_mma_bench_kernel");
+    return BC_OK;
+}
 
 extern "C" int bc_tc_gemm_selftest(const void* A, const void* B, float* D, int M, int N, int K, int* err_flag, void* stream) {
     BC_CHECK_ARG(A && B && D && err_flag, "bc_tc_gemm_selftest: null pointer");

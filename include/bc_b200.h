@@ -121,6 +121,9 @@ int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, v
  * wait timed out (bounded waits: a protocol bug is an error code, not a hung GPU). */
 int bc_tc_gemm_selftest(const void* A, const void* B, float* D, int M, int N, int K, int* err_flag, void* stream);
 
+/* cycles for `reps` back-to-back tcgen05.mma (M=128,K=16,bf16) of width N: cycles2[0] = issue, [1] = completion */
+int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream);
+
 const char* bc_last_error_string(void);
 int bc_device_check(void);  /* BC_OK iff the current device is sm_100 */
 int bc_abi_version(void);
