@@ -279,20 +279,36 @@ def run_b200(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    # ---- roofline of the dominant kernel (conv1 forward), timed live on its own stream -----------
-    c = eng.ctx(bufs)
+    # ---- per-kernel times, measured live with CUDA events on the launching stream (no profiler) -------
     import ctypes as C
+    c = eng.ctx(bufs)
+    cref = C.byref(c)
     s = torch.cuda.current_stream().cuda_stream
-    reps = 20
-    for _ in range(3):
-        _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, s))
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, s))
-    k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / reps
+    L = eng.lib
+    ops = [("stage_gray", lambda: stage_gray(dev_frames[0], out=gray))]
+    if args.mode == "bf16":
+        ops.append(("pack_weights", eng.pack_weights))
+    ops += [(f"conv{l + 1}_fwd", (lambda l=l: _lib.check(L.bc_conv_relu_pool_fwd(cref, l, s)))) for l in range(4)]
+    ops.append(("head_fwd_ce_bwd", lambda: _lib.check(L.bc_head(cref, 3, s))))
+    for l in (3, 2, 1):
+        ops.append((f"conv{l + 1}_wgrad", (lambda l=l: _lib.check(L.bc_conv_bwd_wgrad(cref, l, s)))))
+        ops.append((f"conv{l + 1}_dgrad", (lambda l=l: _lib.check(L.bc_conv_bwd_dgrad(cref, l, s)))))
+    ops.append(("conv1_wgrad", lambda: _lib.check(L.bc_conv_bwd_wgrad(cref, 0, s))))
+    ops.append(("reduce_partials", lambda: _lib.check(L.bc_reduce_partials(cref, 1, s))))
+    breakdown = {}
+    for name, fn in ops:
+        for _ in range(3):
+            fn()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(10):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        breakdown[name] = round(k0.elapsed_time(k1) / 10 * 1e3, 1)
+    k_ms = breakdown["conv1_fwd"] * 1e-3
+    stage_ms = breakdown["stage_gray"] * 1e-3
+    stage_bytes = (B + 4) * (FRAME_BYTES + 65536 * (2 if staged_dtype == torch.bfloat16 else 4))
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -315,10 +331,16 @@ def run_b200(args):
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (B + 4) * FRAME_BYTES + 8 * B, "d2h_bytes_per_step": 4},
             "gpu_launches": (17 if args.mode == "bf16" else 16) * args.steps,
-            "roofline": {"kernel": "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)", "bound": "tensor",
-                         "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-                         "traffic": None, "peak_source": peaks["src"], "kernel_ms": k_ms,
+            "roofline": {"kernel": ("conv1_tc_kernel (tcgen05 Toeplitz implicit GEMM, bf16)" if args.mode == "bf16"
+                                    else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
+                         "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tf_burst"], "traffic": None, "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
+                         "kernel_ms": k_ms, "flops_per_launch": FLOPS_FWD[0] * B,
                          "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
+            "roofline_hbm": {"kernel": "stage_gray_kernel", "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
+                             "peak": peaks["hbm"], "unit": "GB/s", "frac": stage_bytes / (stage_ms * 1e-3) / 1e9 / peaks["hbm"],
+                             "bytes_per_launch": stage_bytes, "kernel_ms": stage_ms},
+            "breakdown_us": breakdown,
             "clocks": clocks,
         }
         if not args.no_cpu:
@@ -336,7 +358,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--staged", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
+    ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
