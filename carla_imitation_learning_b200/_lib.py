@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 
@@ -30,7 +30,7 @@ class BcCtx(C.Structure):
         ("ghead", C.c_void_p), ("hid1", C.c_void_p), ("hid2", C.c_void_p),
         ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p),
         ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
-        ("w_packed", C.c_void_p), ("err_flag", C.c_void_p),
+        ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
     ]
 
 

@@ -67,7 +67,8 @@ __global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bflo
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
-                const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax, int B, int* err) {
+                const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
+                __nv_bfloat16* __restrict__ ybf, int B, int* err) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* b_full = bars;
@@ -201,8 +202,11 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                         if (vv > best) { best = vv; idx = dy * 3 + dx; }     // strict: first maximum wins
                     }
                 const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
-                y[g] = fmaxf(best + breg[i], 0.f);
+                const float out = fmaxf(best + breg[i], 0.f);
+                y[g] = out;
                 amax[g] = (uint8_t)idx;
+                // NHWC bf16 copy for the tensor-core conv2 (16 lanes = 16 channels = 32 contiguous bytes)
+                if (ybf) ybf[(((size_t)b * 28 + 2 * ty + pyl) * 28 + px) * 16 + co] = __float2bfloat16_rn(out);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone done reading S
         }
@@ -268,10 +272,10 @@ extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
     c1tc::pack_conv1_weights_kernel<<<(c1tc::NSTEP * 1024 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         c->params + a.w[0], (__nv_bfloat16*)c->w_packed);
     BC_CUDA_LAUNCH_CHECK("pack_conv1_weights_kernel");
-    return BC_OK;
+    return bc_conv_tc_pack(c, stream);     // conv2-4 operand images follow conv1's inside w_packed
 }
 
-extern "C" size_t bc_packed_weight_bytes(void) { return c1tc::B_BYTES; }
+extern "C" size_t bc_packed_weight_bytes(void) { return bc_conv_tc_pack_total(); }
 
 int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c->x && c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05): null buffer (x, w_packed, err_flag, act, amax)");
@@ -290,7 +294,7 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
     if (grid > ntiles) grid = ntiles;
     c1tc::conv1_tc_kernel<<<grid, c1tc::NTHREADS, c1tc::SMEM_BYTES, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
-        c->act[0], c->amax[0], c->batch, c->err_flag);
+        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv1_tc_kernel");
     return BC_OK;
 }

@@ -237,6 +237,7 @@ extern "C" int bc_conv_relu_pool_fwd(const bc_ctx* c, int layer, void* stream) {
     const float* b = c->params + a.b[layer];
     cudaStream_t s = (cudaStream_t)stream;
     const int B = c->batch;
+    if (c->conv_mode == 1 && layer >= 1 && c->act_bf16[layer - 1]) return bc_conv_tc_launch(c, layer, stream);
     switch (layer) {
     case 0: {
         BC_CHECK_ARG(c->x, "bc_conv_relu_pool_fwd: x is null");

@@ -73,6 +73,7 @@ class StepBuffers:
     loss: torch.Tensor
     ghead: Optional[torch.Tensor] = None
     gact: List[torch.Tensor] = field(default_factory=list)
+    act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: NHWC copies feeding the next layer's MMA
 
 
 class BCEngine:
@@ -110,6 +111,8 @@ class BCEngine:
             amax=[e(batch, *s, dt=torch.uint8) for s in ACT_SHAPES],
             hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
             dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
+        if self.conv_mode == 1:
+            bufs.act_bf16 = [torch.empty((batch, s[1], s[2], s[0]), dtype=torch.bfloat16, device=dev) for s in ACT_SHAPES[:3]]
         if backward:
             self._alloc_bwd(bufs)
         return bufs
@@ -151,6 +154,8 @@ class BCEngine:
         c.partials = self.partials.data_ptr()
         c.loss_scale = (1.0 / max(b.batch, 1)) if loss_scale is None else float(loss_scale)
         c.conv_mode = self.conv_mode
+        for i in range(3):
+            c.act_bf16[i] = b.act_bf16[i].data_ptr() if b.act_bf16 else None
         c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
         return c
 

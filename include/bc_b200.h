@@ -70,6 +70,8 @@ typedef struct {
     int32_t conv_mode;       /* 0 = exact f32 FFMA kernels; 1 = bf16 tcgen05 kernels where they exist */
     void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
     int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
+    void* act_bf16[3];       /* bf16 mode: NHWC bf16 copies of act[0..2] (B,28,28,16) (B,12,12,32) (B,4,4,64),
+                                written by the conv epilogues, read by the next layer's tcgen05 gather   */
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);

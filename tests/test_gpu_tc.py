@@ -87,3 +87,41 @@ def test_bf16_mode_training_step_within_tolerance():
     assert rel(b16.logits, b32.logits) <= 2e-2
     assert abs(float(b16.loss) - float(b32.loss)) <= 2e-2 * float(b32.loss)
     assert rel(eng.grads, g32) <= 0.1      # includes pool-routing flips caused by the bf16 rounding
+
+
+@pytest.mark.parametrize("layer,B", [(1, 3), (1, 37), (2, 5), (2, 1), (3, 33), (3, 1), (3, 70)])
+def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
+    """conv2/3/4 + ReLU + pool as tcgen05 implicit GEMMs over NHWC bf16 activations."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    from tests.test_gpu_parity import _check_routing
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    name, k, s, p = O.CONV_SPECS[layer]
+    w = net.state_dict()[f"{name}.weight"].detach().cpu()
+    bias = net.state_dict()[f"{name}.bias"].detach().cpu().double()
+    cin, hin = w.shape[1], (256, 28, 12, 4)[layer]
+    gen = torch.Generator().manual_seed(7 * layer + B)
+    xin = (torch.rand((B, cin, hin, hin), generator=gen) - 0.3).to(torch.bfloat16)
+    bufs = eng.alloc(B, torch.zeros(B, 4, 256, 256, device=dev, dtype=torch.bfloat16), None, False)
+    bufs.act_bf16[layer - 1].copy_(xin.permute(0, 2, 3, 1).contiguous().to(dev))
+    c = eng.ctx(bufs)
+    _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, torch.cuda.current_stream().cuda_stream), "conv tc")
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    z = torch.nn.functional.conv2d(xin.double(), w.to(torch.bfloat16).double(), bias, stride=1)
+    ref = torch.nn.functional.max_pool2d(torch.relu(z), 2)
+    got = bufs.act[layer].cpu().double()
+    assert got.shape == ref.shape
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5, err
+    _check_routing(z, bufs.amax[layer].cpu(), got, 2)
+    if layer < 3:   # the NHWC bf16 copy handed to the next layer
+        nhwc = bufs.act_bf16[layer].float().cpu().permute(0, 3, 1, 2)
+        assert torch.equal(nhwc, bufs.act[layer].cpu().to(torch.bfloat16).float())
