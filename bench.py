@@ -183,6 +183,8 @@ def run_b200(args):
         host_frames.append(hf); host_labels.append(hl)
         dev_frames.append(hf.to(dev)); dev_labels.append(hl.to(dev))
     gray = torch.empty((B + 4, 256, 256), dtype=staged_dtype, device=dev)
+    if args.mode == "bf16":
+        eng.set_mode("bf16")           # before alloc(): bf16 mode adds the NHWC bf16 activation copies
     bufs = eng.alloc(B, sliding_window(gray), dev_labels[0], True)
 
     from carla_imitation_learning_b200.parallel import DataParallelStep
@@ -194,9 +196,6 @@ def run_b200(args):
         else:
             eng.enqueue_train(b)
             opt.step_flat(eng.grads)
-
-    if args.mode == "bf16":
-        eng.set_mode("bf16")
 
     def device_step(i):
         stage_gray(dev_frames[i % NBUF], out=gray)

@@ -31,6 +31,7 @@ class BcCtx(C.Structure):
         ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p),
         ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
         ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
+        ("dy_bf16", C.c_void_p),
     ]
 
 

@@ -341,6 +341,7 @@ extern "C" int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream) {
     const float* w = c->params + ar.w[layer];
     const float* gP = layer == 3 ? c->ghead : c->gact[layer];
     BC_CHECK_ARG(gP, "bc_conv_bwd_dgrad: gradient buffer for layer %d is null", layer);
+    if (c->conv_mode == 1 && c->dy_bf16) return bc_dgrad_tc_launch(c, layer, stream);
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
     case 1:

@@ -225,6 +225,210 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __res
     if (warp == 2) tc05::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// dgrad on tensor cores. Through ReLU + max-pool the gradient w.r.t. the conv output ("dY") is the
+// pooled gradient routed to the saved first-max position and masked by aP > 0; unpool_kernel writes
+// it densely (NHWC bf16, zeros elsewhere) so that dgrad is the same implicit GEMM as the forward:
+//   dX[b][iy][ix][ci] = sum_{ky,kx,co} dY[b][iy-ky][ix-kx][co] * W[co][ci][ky][kx]        (zero outside dY)
+// M = 128 input pixels, N = C_in, K = taps x C_out in steps of 16 output channels.
+template <typename C>
+__global__ void unpool_kernel(const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
+                              __nv_bfloat16* __restrict__ dY, int B) {
+    constexpr int COUT = C::COUT, HP = C::HP, WPF = C::WPF, HD = 2 * HP;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (b, window, 8-channel group)
+    constexpr int CG = COUT / 8;
+    if (i >= B * WPF * CG) return;
+    const int cg = i % CG, wl = (i / CG) % WPF, b = i / (CG * WPF);
+    const int py = wl / HP, px = wl % HP;
+    float g[8]; int pos[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const size_t o = ((size_t)b * COUT + cg * 8 + k) * WPF + wl;
+        g[k] = aP[o] > 0.f ? gP[o] : 0.f;
+        pos[k] = amax[o];
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(pos[2 * k] == p ? g[2 * k] : 0.f, pos[2 * k + 1] == p ? g[2 * k + 1] : 0.f);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const size_t o = (((size_t)b * HD + 2 * py + (p >> 1)) * HD + 2 * px + (p & 1)) * COUT + cg * 8;
+        *reinterpret_cast<uint4*>(dY + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+template <typename C>
+struct DCfg {
+    static constexpr int N = C::CIN;                       // GEMM N = input channels of the layer
+    static constexpr int CK = C::COUT;                     // contraction channels
+    static constexpr int KS = C::KS, HOUT = C::HIN, HD = 2 * C::HP;
+    static constexpr int CB = CK / 16;
+    static constexpr int NSTEP = KS * KS * CB;
+    static constexpr int B_STEP = N * 32;
+    static constexpr int B_BYTES = NSTEP * B_STEP;
+    static constexpr int OFF_A = (B_BYTES + 1023) / 1024 * 1024;
+    static constexpr int OFF_BAR = OFF_A + NST * A_CHUNK;
+    static constexpr int NBAR = 1 + 2 * NST + 4;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+    static constexpr int TMEM_COLS = 2 * N < 32 ? 32 : 2 * N;
+    static constexpr int PPF = HOUT * HOUT;                // output pixels per frame
+};
+
+// B operand of dgrad: step s = (tap, cb): N = C_in rows x 16 k (k = co within the block)
+template <typename C>
+__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    using D = DCfg<C>;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D::NSTEP * D::N * 16) return;
+    const int k = i & 15, n = (i >> 4) % D::N, s = i / (16 * D::N);
+    const int tap = s / D::CB, cb = s % D::CB;
+    const float v = w[((size_t)(cb * 16 + k) * C::CIN + n) * (C::KS * C::KS) + tap];
+    out[(size_t)s * (D::B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
+}
+
+template <typename C>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ wpk, float* __restrict__ gIn, int B, int* err) {
+    using D = DCfg<C>;
+    constexpr int N = D::N, CK = D::CK, KS = D::KS, HOUT = D::HOUT, HD = D::HD, NSTEP = D::NSTEP, PPF = D::PPF;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D::OFF_BAR);
+    uint64_t* b_full = bars;
+    uint64_t* a_full = bars + 1;
+    uint64_t* a_empty = bars + 1 + NST;
+    uint64_t* t_full = bars + 1 + 2 * NST;
+    uint64_t* t_empty = bars + 3 + 2 * NST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + D::NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npix = B * PPF;
+    const int ntiles = (npix + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(b_full, 1);
+        for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 2) tc05::tmem_alloc(tmem_slot, D::TMEM_COLS);
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (tc05::elect_one()) {
+            tc05::mbar_expect_tx(b_full, D::B_BYTES);
+            tc05::bulk_g2s(smem, wpk, D::B_BYTES, b_full);
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + D::OFF_A), 128, 256, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
+        bool ok = tc05::mbar_wait(b_full, 0, err);
+        uint32_t gs = 0;
+        int it = 0;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
+            tc05::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * N;
+            for (int s = 0; ok && s < NSTEP; ++s, ++gs) {
+                const uint32_t st = gs & (NST - 1);
+                ok = tc05::mbar_wait(a_full + st, (gs / NST) & 1, err);
+                tc05::tc_fence_after();
+                if (ok && tc05::elect_one()) {
+                    tc05::mma_bf16(d_tmem, ad0 + (uint64_t)(st * (A_CHUNK >> 4)), bd0 + (uint64_t)(s * (D::B_STEP >> 4)), idesc, s > 0);
+                    tc05::mma_commit(a_empty + st);
+                    if (s == NSTEP - 1) tc05::mma_commit(t_full + acc);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // epilogue: row = input pixel, N columns = input channels -> gIn f32 NCHW
+        const int ew = warp - 4;
+        const int r = ew * 32 + lane;
+        int it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
+            tc05::tc_fence_after();
+            const int pg = t * 128 + r;
+            const bool valid = pg < npix;
+            const int b = pg / PPF, pl = pg % PPF;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N + c0, v);
+                tc05::tmem_ld_wait();
+                if (c0 + 16 >= N) {
+                    tc05::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc05::mbar_arrive(t_empty + acc);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) gIn[((size_t)b * N + c0 + j) * PPF + pl] = v[j];   // lanes = consecutive pixels: coalesced per channel
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        const int rw = warp - 8;
+        uint32_t use = 0;
+        int it = 0;
+        bool ok = true;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const __nv_bfloat16* base[4];
+            int iy[4], ix[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int pg = t * 128 + q * 32 + lane;
+                if (pg < npix) {
+                    const int b = pg / PPF, pl = pg % PPF;
+                    iy[q] = pl / HOUT; ix[q] = pl % HOUT;
+                    base[q] = dY + (size_t)b * HD * HD * CK;
+                } else {
+                    iy[q] = -1000; ix[q] = -1000; base[q] = dY;
+                }
+            }
+            const uint32_t gs0 = (uint32_t)it * NSTEP;
+            for (int s = (int)((rw + NST - gs0 % NST) % NST); s < NSTEP; s += NST, ++use) {
+                ok = tc05::mbar_wait(a_empty + rw, (use & 1) ^ 1, err);
+                if (!ok) break;
+                const int tap = s / D::CB, cb = s % D::CB;
+                const int ky = tap / KS, kx = tap % KS;
+                uint4 v[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int oy = iy[q] - ky, ox = ix[q] - kx;
+                    if ((unsigned)oy < (unsigned)HD && (unsigned)ox < (unsigned)HD) {
+                        const uint4* p = reinterpret_cast<const uint4*>(base[q] + ((size_t)oy * HD + ox) * CK + cb * 16);
+                        v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                    } else {
+                        v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
+                    }
+                }
+                uint8_t* dst = smem + D::OFF_A + rw * A_CHUNK;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint8_t* d = dst + op_off(q * 32 + lane, 0);
+                    *reinterpret_cast<uint4*>(d) = v[q][0];
+                    *reinterpret_cast<uint4*>(d + 128) = v[q][1];
+                }
+                tc05::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(a_full + rw);
+            }
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc05::tmem_dealloc(tmem_base, D::TMEM_COLS);
+}
+
 using L2 = Cfg<16, 32, 5, 28, 12>;
 using L3 = Cfg<32, 64, 4, 12, 4>;
 using L4 = Cfg<64, 128, 3, 4, 1>;
@@ -254,7 +458,9 @@ int launch(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const
 // byte offsets of the per-layer operand images inside w_packed: [conv1 | conv2 | conv3 | conv4]
 static constexpr size_t kPackOff1 = 0, kPackOff2 = 57344;
 static constexpr size_t kPackOff3 = kPackOff2 + ctc::L2::B_BYTES, kPackOff4 = kPackOff3 + ctc::L3::B_BYTES;
-static constexpr size_t kPackTotal = kPackOff4 + ctc::L4::B_BYTES;
+static constexpr size_t kPackD2 = kPackOff4 + ctc::L4::B_BYTES;            // dgrad operand images
+static constexpr size_t kPackD3 = kPackD2 + ctc::DCfg<ctc::L2>::B_BYTES, kPackD4 = kPackD3 + ctc::DCfg<ctc::L3>::B_BYTES;
+static constexpr size_t kPackTotal = kPackD4 + ctc::DCfg<ctc::L4>::B_BYTES;
 
 size_t bc_conv_tc_pack_total() { return kPackTotal; }
 
@@ -265,8 +471,48 @@ int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
     ctc::pack_weights_kernel<ctc::L2><<<(ctc::L2::NSTEP * 32 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[1], (__nv_bfloat16*)(base + kPackOff2));
     ctc::pack_weights_kernel<ctc::L3><<<(ctc::L3::NSTEP * 64 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[2], (__nv_bfloat16*)(base + kPackOff3));
     ctc::pack_weights_kernel<ctc::L4><<<(ctc::L4::NSTEP * 128 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[3], (__nv_bfloat16*)(base + kPackOff4));
+    ctc::pack_dgrad_weights_kernel<ctc::L2><<<(ctc::DCfg<ctc::L2>::NSTEP * 16 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[1], (__nv_bfloat16*)(base + kPackD2));
+    ctc::pack_dgrad_weights_kernel<ctc::L3><<<(ctc::DCfg<ctc::L3>::NSTEP * 32 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[2], (__nv_bfloat16*)(base + kPackD3));
+    ctc::pack_dgrad_weights_kernel<ctc::L4><<<(ctc::DCfg<ctc::L4>::NSTEP * 64 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[3], (__nv_bfloat16*)(base + kPackD4));
     BC_CUDA_LAUNCH_CHECK("pack_weights_kernel");
     return BC_OK;
+}
+
+namespace ctc {
+template <typename C>
+int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
+    using D = DCfg<C>;
+    auto kern = dgrad_tc_kernel<C>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, D::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const float* gP = layer == 3 ? c->ghead : c->gact[layer];
+    const int nu = c->batch * C::WPF * (C::COUT / 8);
+    // dY covers only the conv rows/cols that feed a pool window; everything the routing does not hit must be zero
+    unpool_kernel<C><<<(nu + 255) / 256, 256, 0, s>>>(gP, c->act[layer], c->amax[layer], (__nv_bfloat16*)c->dy_bf16, c->batch);
+    const int ntiles = (c->batch * D::PPF + 127) / 128;
+    int grid = bc::num_sms();
+    if (grid > ntiles) grid = ntiles;
+    kern<<<grid, NTHREADS, D::SMEM_BYTES, s>>>((const __nv_bfloat16*)c->dy_bf16, (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK(name);
+    return BC_OK;
+}
+}  // namespace ctc
+
+int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
+    BC_CHECK_ARG(layer >= 1 && layer <= 3, "dgrad (tcgen05): layer %d", layer);
+    BC_CHECK_ARG(c->w_packed && c->err_flag && c->dy_bf16 && c->gact[layer - 1] && c->act[layer] && c->amax[layer],
+                 "conv%d dgrad (tcgen05): null buffer", layer + 1);
+    const uint8_t* base = (const uint8_t*)c->w_packed;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (layer) {
+    case 1: return ctc::launch_dgrad<ctc::L2>(c, 1, base + kPackD2, s, "conv2_dgrad_tc_kernel");
+    case 2: return ctc::launch_dgrad<ctc::L3>(c, 2, base + kPackD3, s, "conv3_dgrad_tc_kernel");
+    default: return ctc::launch_dgrad<ctc::L4>(c, 3, base + kPackD4, s, "conv4_dgrad_tc_kernel");
+    }
 }
 
 int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream) {

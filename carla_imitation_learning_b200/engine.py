@@ -74,6 +74,7 @@ class StepBuffers:
     ghead: Optional[torch.Tensor] = None
     gact: List[torch.Tensor] = field(default_factory=list)
     act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: NHWC copies feeding the next layer's MMA
+    dy_bf16: Optional[torch.Tensor] = None                       # bf16 mode: un-pooled conv-output gradient scratch
 
 
 class BCEngine:
@@ -122,6 +123,8 @@ class BCEngine:
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
             bufs.ghead = e(bufs.batch, 128)
             bufs.gact = [e(bufs.batch, *s) for s in ACT_SHAPES[:3]]
+            if self.conv_mode == 1 and bufs.act_bf16:
+                bufs.dy_bf16 = torch.empty((bufs.batch, 24, 24, 32), dtype=torch.bfloat16, device=self.device)
 
     def check_input(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, "x")
@@ -156,6 +159,7 @@ class BCEngine:
         c.conv_mode = self.conv_mode
         for i in range(3):
             c.act_bf16[i] = b.act_bf16[i].data_ptr() if b.act_bf16 else None
+        c.dy_bf16 = b.dy_bf16.data_ptr() if b.dy_bf16 is not None else None
         c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
         return c
 

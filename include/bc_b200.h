@@ -72,6 +72,8 @@ typedef struct {
     int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
     void* act_bf16[3];       /* bf16 mode: NHWC bf16 copies of act[0..2] (B,28,28,16) (B,12,12,32) (B,4,4,64),
                                 written by the conv epilogues, read by the next layer's tcgen05 gather   */
+    void* dy_bf16;           /* bf16 mode: scratch for the un-pooled conv-output gradient, NHWC bf16,
+                                batch*24*24*32 elements (the largest layer); one layer at a time          */
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);

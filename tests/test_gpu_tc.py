@@ -125,3 +125,40 @@ def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
     if layer < 3:   # the NHWC bf16 copy handed to the next layer
         nhwc = bufs.act_bf16[layer].float().cpu().permute(0, 3, 1, 2)
         assert torch.equal(nhwc, bufs.act[layer].cpu().to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("B", [2, 37])
+def test_dgrad_tcgen05_matches_exact_f32_dgrad(B):
+    """Dense tensor-core dgrad (unpool -> implicit GEMM) vs the exact routing-sparse f32 kernel, same inputs."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib, stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    frames, labels = O.synth_frames(5 + B, B + 4)
+    x = sliding_window(stage_gray(torch.from_numpy(frames).to(dev), dtype=torch.bfloat16))
+    y = torch.from_numpy(labels[4:4 + B]).to(dev)
+    bufs = eng.train_forward_backward(x, y)          # fills act/amax (tensor-core forward) and allocates backward buffers
+    s = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    for layer in (3, 2, 1):
+        gP = bufs.ghead if layer == 3 else bufs.gact[layer]
+        gP.copy_(torch.randn(gP.shape, generator=gen).to(dev))
+        eng.conv_mode = 1
+        c = eng.ctx(bufs)
+        _lib.check(eng.lib.bc_conv_bwd_dgrad(C.byref(c), layer, s), "dgrad tc")
+        got = bufs.gact[layer - 1].clone()
+        eng.conv_mode = 0
+        c = eng.ctx(bufs)
+        _lib.check(eng.lib.bc_conv_bwd_dgrad(C.byref(c), layer, s), "dgrad f32")
+        torch.cuda.synchronize()
+        ref = bufs.gact[layer - 1]
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err <= 1e-2, (layer, err)             # bf16 rounding of dY and W, f32 accumulation
+    eng.conv_mode = 1
+    eng.check_device_errors()
