@@ -48,30 +48,39 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     out[(size_t)s * (C::B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
 }
 
-template <typename C>
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ bias,
-               float* __restrict__ y, uint8_t* __restrict__ amax, __nv_bfloat16* __restrict__ ybf, int B, int* err) {
-    constexpr int CIN = C::CIN, COUT = C::COUT, KS = C::KS, HIN = C::HIN, HP = C::HP, NSTEP = C::NSTEP, WPF = C::WPF;
+// ------------------------------------------------------------------------------------------------
+// One persistent warp-specialised implicit-GEMM kernel for forward and dgrad. A policy P supplies
+//   N, NSTEP, G (K-steps per stage), NSTAGE, B_STEP, the per-lane gather (setup/load) and the epilogue.
+// Why stages hold G = 4..8 K-steps: a tcgen05.mma keeps its uniform operand registers busy for ~290
+// cycles (tools/mma_bench.py: 292 cycles/MMA when a loop rewrites the same URs, 41-64 when 8 MMAs with
+// distinct registers are issued back to back), so every visit of the issuing warp must carry >= ~400
+// cycles of tensor work to hide that plus the mbarrier round trip.
+template <typename P>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_conv_kernel(const typename P::Args args) {
+    constexpr int N = P::N, NSTEP = P::NSTEP, G = P::G, NSTAGE = P::NSTAGE;
+    constexpr int NVIS = (NSTEP + G - 1) / G;
+    constexpr int STAGE_BYTES = G * A_CHUNK;
+    constexpr int NPASS = G == 8 ? 4 : 2;                    // 32-row passes of one chunk per producer warp
+    static_assert(G == 8 || G == 4, "producer mapping is written for G = 4 or 8");
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::OFF_BAR);
     uint64_t* b_full = bars;
     uint64_t* a_full = bars + 1;
-    uint64_t* a_empty = bars + 1 + NST;
-    uint64_t* t_full = bars + 1 + 2 * NST;
-    uint64_t* t_empty = bars + 3 + 2 * NST;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    uint64_t* a_empty = bars + 1 + NSTAGE;
+    uint64_t* t_full = bars + 1 + 2 * NSTAGE;
+    uint64_t* t_empty = bars + 3 + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NSTAGE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwin = B * WPF;
-    const int ntiles = (nwin + 31) / 32;
+    const int ntiles = P::num_tiles(args);
+    int* err = args.err;
 
     if (threadIdx.x == 0) {
         tc05::mbar_init(b_full, 1);
-        for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < NSTAGE; ++i) { tc05::mbar_init(a_full + i, 8); tc05::mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
         tc05::mbar_fence_init();
     }
-    if (warp == 2) tc05::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == 2) tc05::tmem_alloc(tmem_slot, P::TMEM_COLS);
     tc05::tc_fence_before();
     __syncthreads();
     tc05::tc_fence_after();
@@ -79,151 +88,199 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __res
 
     if (warp == 0) {
         if (tc05::elect_one()) {
-            tc05::mbar_expect_tx(b_full, C::B_BYTES);
-            tc05::bulk_g2s(smem + C::OFF_B, wpk, C::B_BYTES, b_full);
+            tc05::mbar_expect_tx(b_full, P::B_BYTES);
+            tc05::bulk_g2s(smem, args.wpk, P::B_BYTES, b_full);
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, COUT, 0, 0);
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_A), 128, 256, tc05::SW_NONE);
-        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_B), 128, 256, tc05::SW_NONE);
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + P::OFF_A), 128, 256, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
         bool ok = tc05::mbar_wait(b_full, 0, err);
-        uint32_t gs = 0;
+        uint32_t st = 0, ph = 0;
         int it = 0;
         for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
             tc05::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * COUT;
-            for (int s = 0; ok && s < NSTEP; ++s, ++gs) {
-                const uint32_t st = gs & (NST - 1);
-                ok = tc05::mbar_wait(a_full + st, (gs / NST) & 1, err);
+            const uint32_t d_tmem = tmem_base + acc * N;
+            for (int v = 0; ok && v < NVIS; ++v) {
+                ok = tc05::mbar_wait(a_full + st, ph, err);
                 tc05::tc_fence_after();
                 if (ok && tc05::elect_one()) {
-                    tc05::mma_bf16(d_tmem, ad0 + (uint64_t)(st * (A_CHUNK >> 4)), bd0 + (uint64_t)(s * (C::B_STEP >> 4)), idesc, s > 0);
+                    const uint64_t a_st = ad0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+                    const uint64_t b_v = bd0 + (uint64_t)(v * G * (P::B_STEP >> 4));
+#pragma unroll
+                    for (int u = 0; u < G; ++u)
+                        if (v * G + u < NSTEP)
+                            tc05::mma_bf16(d_tmem, a_st + (uint64_t)(u * (A_CHUNK >> 4)), b_v + (uint64_t)(u * (P::B_STEP >> 4)), idesc, (v | u) > 0);
                     tc05::mma_commit(a_empty + st);
-                    if (s == NSTEP - 1) tc05::mma_commit(t_full + acc);
+                    if (v == NVIS - 1) tc05::mma_commit(t_full + acc);
                 }
                 __syncwarp();
+                if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ epilogue: 4 lanes = one pool window
+        // ------------------------------------------------------------------ epilogue
         const int ew = warp - 4;
-        const int r = ew * 32 + lane;
-        const int pos = lane & 3;                               // dy*2 + dx of this row inside its window
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
             tc05::tc_fence_after();
-            const int wg = t * 32 + (r >> 2);
-            const bool valid = wg < nwin;
-            const int b = wg / WPF, wl = wg % WPF;
-#pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += 16) {
-                float v[16];
-                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * COUT + c0, v);
-                tc05::tmem_ld_wait();
-                if (c0 + 16 >= COUT) {                           // last chunk read: release the accumulator
-                    tc05::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc05::mbar_arrive(t_empty + acc);
-                }
-                float m[16];
-                int idx[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    // round 1: rows (pos, pos^1); ties go to the lower position (first maximum, torch's rule)
-                    const float o1 = __shfl_xor_sync(0xffffffffu, v[j], 1);
-                    const float lo = (pos & 1) ? o1 : v[j], hi = (pos & 1) ? v[j] : o1;      // values at even / odd position
-                    const int i1 = (pos & 2) | (hi > lo ? 1 : 0);
-                    const float m1 = hi > lo ? hi : lo;
-                    // round 2: pairs (dy=0) vs (dy=1)
-                    const float o2 = __shfl_xor_sync(0xffffffffu, m1, 2);
-                    const int oi = __shfl_xor_sync(0xffffffffu, i1, 2);
-                    const float top = (pos & 2) ? o2 : m1, bot = (pos & 2) ? m1 : o2;
-                    const int ti = (pos & 2) ? oi : i1, bi = (pos & 2) ? i1 : oi;
-                    m[j] = bot > top ? bot : top;
-                    idx[j] = bot > top ? bi : ti;
-                }
-                if (valid) {
-                    // each of the 4 lanes of a window stores 4 consecutive channels
-                    const int cb0 = c0 + 4 * pos;
-                    float o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        // select channel 4*pos+q of the chunk without dynamic register indexing
-                        float mv = 0.f; int iv = 0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j == 4 * pos + q) { mv = m[j]; iv = idx[j]; }
-                        o[q] = fmaxf(mv + bias[cb0 + q], 0.f);
-                        const size_t g = ((size_t)b * COUT + cb0 + q) * WPF + wl;
-                        y[g] = o[q];
-                        amax[g] = (uint8_t)iv;
-                    }
-                    if (ybf) {
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                        *reinterpret_cast<uint2*>(ybf + ((size_t)b * WPF + wl) * COUT + cb0) = pk;
-                    }
-                }
-            }
+            P::epilogue(args, t, ew, lane, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N, t_empty + acc);
         }
     } else if (warp >= 8) {
-        // ------------------------------------------------------------------ A gather: warp rw owns stage rw
-        const int rw = warp - 8;
-        uint32_t use = 0;
-        int it = 0;
-        bool ok = true;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const __nv_bfloat16* src[4];
+        // ------------------------------------------------------------------ A gather (8 warps fill every stage together)
+        const int pw = warp - 8;
+        const int chunk = G == 8 ? pw : (pw >> 1);
+        const int pass0 = G == 8 ? 0 : (pw & 1) * 2;
+        typename P::Gather gth;
+        uint4 v[NPASS][2];
+        uint32_t st = 0, ph = 1;                     // producer waits "empty": first pass over the ring is free
+        int t = blockIdx.x, vis = 0;
+        if (t < ntiles) {
+            gth.setup(args, t, lane, pass0);
+            if (chunk < NSTEP) gth.load(args, chunk, v);
+        }
+        while (t < ntiles) {
+            if (!tc05::mbar_wait(a_empty + st, ph, err)) break;
+            const int step = vis * G + chunk;
+            if (step < NSTEP) {
+                uint8_t* dst = smem + P::OFF_A + st * STAGE_BYTES + chunk * A_CHUNK;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int r = q * 32 + lane;
-                const int wg = t * 32 + (r >> 2), pos = r & 3;
-                if (wg < nwin) {
-                    const int b = wg / WPF, wl = wg % WPF;
-                    const int oy = 2 * (wl / HP) + (pos >> 1), ox = 2 * (wl % HP) + (pos & 1);
-                    src[q] = act + (((size_t)b * HIN + oy) * HIN + ox) * CIN;
-                } else {
-                    src[q] = nullptr;
-                }
-            }
-            const uint32_t gs0 = (uint32_t)it * NSTEP;
-            for (int s = (int)((rw + NST - gs0 % NST) % NST); s < NSTEP; s += NST, ++use) {
-                ok = tc05::mbar_wait(a_empty + rw, (use & 1) ^ 1, err);
-                if (!ok) break;
-                const int tap = s / C::CB, cb = s % C::CB;
-                const int toff = ((tap / KS) * HIN + (tap % KS)) * CIN + cb * 16;
-                uint4 v[4][2];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (src[q]) {
-                        const uint4* p = reinterpret_cast<const uint4*>(src[q] + toff);
-                        v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
-                    } else {
-                        v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
-                    }
-                }
-                uint8_t* dst = smem + C::OFF_A + rw * A_CHUNK;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint8_t* d = dst + op_off(q * 32 + lane, 0);
+                for (int q = 0; q < NPASS; ++q) {
+                    uint8_t* d = dst + op_off((pass0 + q) * 32 + lane, 0);
                     *reinterpret_cast<uint4*>(d) = v[q][0];
                     *reinterpret_cast<uint4*>(d + 128) = v[q][1];
                 }
-                tc05::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(a_full + rw);
             }
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(a_full + st);
+            if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            // next visit (possibly the next tile): prefetch its data before waiting for the stage to drain
+            if (++vis == NVIS) {
+                vis = 0;
+                t += gridDim.x;
+                if (t < ntiles) gth.setup(args, t, lane, pass0);
+            }
+            if (t < ntiles && vis * G + chunk < NSTEP) gth.load(args, vis * G + chunk, v);
         }
     }
     tc05::tc_fence_before();
     __syncthreads();
-    if (warp == 2) tc05::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == 2) tc05::tmem_dealloc(tmem_base, P::TMEM_COLS);
 }
+
+struct ConvArgs {
+    const __nv_bfloat16* in;      // forward: NHWC bf16 activations; dgrad: NHWC bf16 dY
+    const __nv_bfloat16* wpk;
+    const float* bias;
+    float* y; uint8_t* amax; __nv_bfloat16* ybf;   // forward outputs (dgrad: y = gIn)
+    int B; int* err;
+};
+
+// ---- forward policy -------------------------------------------------------------------------------
+template <typename C, int G_, int NSTAGE_>
+struct FwdP {
+    using Args = ConvArgs;
+    static constexpr int N = C::COUT, NSTEP = C::NSTEP, G = G_, NSTAGE = NSTAGE_, B_STEP = C::B_STEP, B_BYTES = C::B_BYTES;
+    static constexpr int OFF_A = (B_BYTES + 1023) / 1024 * 1024;
+    static constexpr int OFF_BAR = OFF_A + NSTAGE * G * A_CHUNK;
+    static constexpr int SMEM_BYTES = OFF_BAR + (5 + 2 * NSTAGE) * 8 + 16;
+    static constexpr int TMEM_COLS = C::TMEM_COLS;
+    __device__ static int num_tiles(const Args& a) { return (a.B * C::WPF + 31) / 32; }
+    struct Gather {
+        const __nv_bfloat16* src[4];
+        __device__ void setup(const Args& a, int tile, int lane, int pass0) {
+            const int nwin = a.B * C::WPF;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = (pass0 + q) * 32 + lane;
+                const int wg = tile * 32 + (r >> 2), pos = r & 3;
+                if (wg < nwin && pass0 + q < 4) {
+                    const int b = wg / C::WPF, wl = wg % C::WPF;
+                    const int oy = 2 * (wl / C::HP) + (pos >> 1), ox = 2 * (wl % C::HP) + (pos & 1);
+                    src[q] = a.in + (((size_t)b * C::HIN + oy) * C::HIN + ox) * C::CIN;
+                } else {
+                    src[q] = nullptr;
+                }
+            }
+        }
+        template <int NP>
+        __device__ void load(const Args&, int step, uint4 (&v)[NP][2]) {
+            const int tap = step / C::CB, cb = step % C::CB;
+            const int toff = ((tap / C::KS) * C::HIN + (tap % C::KS)) * C::CIN + cb * 16;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if (src[q]) {
+                    const uint4* p = reinterpret_cast<const uint4*>(src[q] + toff);
+                    v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                } else {
+                    v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
+                }
+            }
+        }
+    };
+    // 4 lanes = one pool window: ReLU + 2x2 max + first-max argmax by warp shuffles
+    __device__ static void epilogue(const Args& a, int tile, int ew, int lane, uint32_t taddr, uint64_t* t_empty) {
+        constexpr int COUT = C::COUT, WPF = C::WPF;
+        const int r = ew * 32 + lane, pos = lane & 3;
+        const int wg = tile * 32 + (r >> 2);
+        const bool valid = wg < a.B * WPF;
+        const int b = wg / WPF, wl = wg % WPF;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+            float v[16];
+            tc05::tmem_ld16(taddr + c0, v);
+            tc05::tmem_ld_wait();
+            if (c0 + 16 >= COUT) {                           // last chunk read: release the accumulator
+                tc05::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(t_empty);
+            }
+            float m[16];
+            int idx[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // round 1: rows (pos, pos^1); ties go to the lower position (first maximum, torch's rule)
+                const float o1 = __shfl_xor_sync(0xffffffffu, v[j], 1);
+                const float lo = (pos & 1) ? o1 : v[j], hi = (pos & 1) ? v[j] : o1;
+                const int i1 = (pos & 2) | (hi > lo ? 1 : 0);
+                const float m1 = hi > lo ? hi : lo;
+                // round 2: row pair dy=0 vs dy=1
+                const float o2 = __shfl_xor_sync(0xffffffffu, m1, 2);
+                const int oi = __shfl_xor_sync(0xffffffffu, i1, 2);
+                const float top = (pos & 2) ? o2 : m1, bot = (pos & 2) ? m1 : o2;
+                const int ti = (pos & 2) ? oi : i1, bi = (pos & 2) ? i1 : oi;
+                m[j] = bot > top ? bot : top;
+                idx[j] = bot > top ? bi : ti;
+            }
+            if (valid) {
+                const int cb0 = c0 + 4 * pos;                // each of the 4 lanes of a window stores 4 channels
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float mv = 0.f; int iv = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j == 4 * pos + q) { mv = m[j]; iv = idx[j]; }
+                    o[q] = fmaxf(mv + a.bias[cb0 + q], 0.f);
+                    const size_t g = ((size_t)b * COUT + cb0 + q) * WPF + wl;
+                    a.y[g] = o[q];
+                    a.amax[g] = (uint8_t)iv;
+                }
+                if (a.ybf) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(a.ybf + ((size_t)b * WPF + wl) * COUT + cb0) = pk;
+                }
+            }
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // dgrad on tensor cores. Through ReLU + max-pool the gradient w.r.t. the conv output ("dY") is the
@@ -289,166 +346,94 @@ __global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, __nv_bflo
     out[(size_t)s * (D::B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
 }
 
-template <typename C>
-__global__ void __launch_bounds__(NTHREADS, 1)
-dgrad_tc_kernel(const __nv_bfloat16* __restrict__ dY, const __nv_bfloat16* __restrict__ wpk, float* __restrict__ gIn, int B, int* err) {
+// ---- dgrad policy ---------------------------------------------------------------------------------
+template <typename C, int G_, int NSTAGE_>
+struct DgradP {
+    using Args = ConvArgs;
     using D = DCfg<C>;
-    constexpr int N = D::N, CK = D::CK, KS = D::KS, HOUT = D::HOUT, HD = D::HD, NSTEP = D::NSTEP, PPF = D::PPF;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D::OFF_BAR);
-    uint64_t* b_full = bars;
-    uint64_t* a_full = bars + 1;
-    uint64_t* a_empty = bars + 1 + NST;
-    uint64_t* t_full = bars + 1 + 2 * NST;
-    uint64_t* t_empty = bars + 3 + 2 * NST;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + D::NBAR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int npix = B * PPF;
-    const int ntiles = (npix + 127) / 128;
-
-    if (threadIdx.x == 0) {
-        tc05::mbar_init(b_full, 1);
-        for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
-        tc05::mbar_fence_init();
-    }
-    if (warp == 2) tc05::tmem_alloc(tmem_slot, D::TMEM_COLS);
-    tc05::tc_fence_before();
-    __syncthreads();
-    tc05::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (tc05::elect_one()) {
-            tc05::mbar_expect_tx(b_full, D::B_BYTES);
-            tc05::bulk_g2s(smem, wpk, D::B_BYTES, b_full);
-        }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + D::OFF_A), 128, 256, tc05::SW_NONE);
-        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
-        bool ok = tc05::mbar_wait(b_full, 0, err);
-        uint32_t gs = 0;
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const int acc = it & 1;
-            ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
-            tc05::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * N;
-            for (int s = 0; ok && s < NSTEP; ++s, ++gs) {
-                const uint32_t st = gs & (NST - 1);
-                ok = tc05::mbar_wait(a_full + st, (gs / NST) & 1, err);
-                tc05::tc_fence_after();
-                if (ok && tc05::elect_one()) {
-                    tc05::mma_bf16(d_tmem, ad0 + (uint64_t)(st * (A_CHUNK >> 4)), bd0 + (uint64_t)(s * (D::B_STEP >> 4)), idesc, s > 0);
-                    tc05::mma_commit(a_empty + st);
-                    if (s == NSTEP - 1) tc05::mma_commit(t_full + acc);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // epilogue: row = input pixel, N columns = input channels -> gIn f32 NCHW
-        const int ew = warp - 4;
-        const int r = ew * 32 + lane;
-        int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int acc = it & 1;
-            if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
-            tc05::tc_fence_after();
-            const int pg = t * 128 + r;
-            const bool valid = pg < npix;
-            const int b = pg / PPF, pl = pg % PPF;
-#pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                float v[16];
-                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * N + c0, v);
-                tc05::tmem_ld_wait();
-                if (c0 + 16 >= N) {
-                    tc05::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) tc05::mbar_arrive(t_empty + acc);
-                }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) gIn[((size_t)b * N + c0 + j) * PPF + pl] = v[j];   // lanes = consecutive pixels: coalesced per channel
-                }
-            }
-        }
-    } else if (warp >= 8) {
-        const int rw = warp - 8;
-        uint32_t use = 0;
-        int it = 0;
-        bool ok = true;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const __nv_bfloat16* base[4];
-            int iy[4], ix[4];
+    static constexpr int N = D::N, NSTEP = D::NSTEP, G = G_, NSTAGE = NSTAGE_, B_STEP = D::B_STEP, B_BYTES = D::B_BYTES;
+    static constexpr int OFF_A = (B_BYTES + 1023) / 1024 * 1024;
+    static constexpr int OFF_BAR = OFF_A + NSTAGE * G * A_CHUNK;
+    static constexpr int SMEM_BYTES = OFF_BAR + (5 + 2 * NSTAGE) * 8 + 16;
+    static constexpr int TMEM_COLS = D::TMEM_COLS;
+    __device__ static int num_tiles(const Args& a) { return (a.B * D::PPF + 127) / 128; }
+    struct Gather {
+        const __nv_bfloat16* base[4];
+        int iy[4], ix[4];
+        __device__ void setup(const Args& a, int tile, int lane, int pass0) {
+            const int npix = a.B * D::PPF;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int pg = t * 128 + q * 32 + lane;
-                if (pg < npix) {
-                    const int b = pg / PPF, pl = pg % PPF;
-                    iy[q] = pl / HOUT; ix[q] = pl % HOUT;
-                    base[q] = dY + (size_t)b * HD * HD * CK;
+                const int pg = tile * 128 + (pass0 + q) * 32 + lane;
+                if (pg < npix && pass0 + q < 4) {
+                    const int b = pg / D::PPF, pl = pg % D::PPF;
+                    iy[q] = pl / D::HOUT; ix[q] = pl % D::HOUT;
+                    base[q] = a.in + (size_t)b * D::HD * D::HD * D::CK;
                 } else {
-                    iy[q] = -1000; ix[q] = -1000; base[q] = dY;
+                    iy[q] = -1000; ix[q] = -1000; base[q] = a.in;
                 }
             }
-            const uint32_t gs0 = (uint32_t)it * NSTEP;
-            for (int s = (int)((rw + NST - gs0 % NST) % NST); s < NSTEP; s += NST, ++use) {
-                ok = tc05::mbar_wait(a_empty + rw, (use & 1) ^ 1, err);
-                if (!ok) break;
-                const int tap = s / D::CB, cb = s % D::CB;
-                const int ky = tap / KS, kx = tap % KS;
-                uint4 v[4][2];
+        }
+        template <int NP>
+        __device__ void load(const Args&, int step, uint4 (&v)[NP][2]) {
+            const int tap = step / D::CB, cb = step % D::CB;
+            const int ky = tap / D::KS, kx = tap % D::KS;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int oy = iy[q] - ky, ox = ix[q] - kx;
-                    if ((unsigned)oy < (unsigned)HD && (unsigned)ox < (unsigned)HD) {
-                        const uint4* p = reinterpret_cast<const uint4*>(base[q] + ((size_t)oy * HD + ox) * CK + cb * 16);
-                        v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
-                    } else {
-                        v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
-                    }
+            for (int q = 0; q < NP; ++q) {
+                const int oy = iy[q] - ky, ox = ix[q] - kx;
+                if ((unsigned)oy < (unsigned)D::HD && (unsigned)ox < (unsigned)D::HD) {
+                    const uint4* p = reinterpret_cast<const uint4*>(base[q] + ((size_t)oy * D::HD + ox) * D::CK + cb * 16);
+                    v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                } else {
+                    v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
                 }
-                uint8_t* dst = smem + D::OFF_A + rw * A_CHUNK;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint8_t* d = dst + op_off(q * 32 + lane, 0);
-                    *reinterpret_cast<uint4*>(d) = v[q][0];
-                    *reinterpret_cast<uint4*>(d + 128) = v[q][1];
-                }
-                tc05::fence_async_smem();
+            }
+        }
+    };
+    // row = input pixel, N columns = input channels -> gIn f32 NCHW (lanes = consecutive pixels: coalesced per channel)
+    __device__ static void epilogue(const Args& a, int tile, int ew, int lane, uint32_t taddr, uint64_t* t_empty) {
+        const int pg = tile * 128 + ew * 32 + lane;
+        const bool valid = pg < a.B * D::PPF;
+        const int b = pg / D::PPF, pl = pg % D::PPF;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            float v[16];
+            tc05::tmem_ld16(taddr + c0, v);
+            tc05::tmem_ld_wait();
+            if (c0 + 16 >= N) {
+                tc05::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(a_full + rw);
+                if (lane == 0) tc05::mbar_arrive(t_empty);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a.y[((size_t)b * N + c0 + j) * D::PPF + pl] = v[j];
             }
         }
     }
-    tc05::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tc05::tmem_dealloc(tmem_base, D::TMEM_COLS);
-}
+};
 
 using L2 = Cfg<16, 32, 5, 28, 12>;
 using L3 = Cfg<32, 64, 4, 12, 4>;
 using L4 = Cfg<64, 128, 3, 4, 1>;
 
-template <typename C>
+template <typename C, int G, int NSTAGE>
 int launch(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
-    auto kern = conv_tc_kernel<C>;
+    using P = FwdP<C, G, NSTAGE>;
+    auto kern = gemm_conv_kernel<P>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, P::SMEM_BYTES, cudaGetErrorString(e));
         configured = true;
     }
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
     const int ntiles = (c->batch * C::WPF + 31) / 32;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, NTHREADS, C::SMEM_BYTES, s>>>((const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)wpk,
-                                              c->params + a.b[layer], c->act[layer], c->amax[layer],
-                                              layer < 3 ? (__nv_bfloat16*)c->act_bf16[layer] : nullptr, c->batch, c->err_flag);
+    ConvArgs args{(const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)wpk, c->params + a.b[layer],
+                  c->act[layer], c->amax[layer], layer < 3 ? (__nv_bfloat16*)c->act_bf16[layer] : nullptr, c->batch, c->err_flag};
+    kern<<<grid, NTHREADS, P::SMEM_BYTES, s>>>(args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;
 }
@@ -479,14 +464,15 @@ int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
 }
 
 namespace ctc {
-template <typename C>
+template <typename C, int G, int NSTAGE>
 int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
     using D = DCfg<C>;
-    auto kern = dgrad_tc_kernel<C>;
+    using P = DgradP<C, G, NSTAGE>;
+    auto kern = gemm_conv_kernel<P>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D::SMEM_BYTES);
-        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, D::SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, P::SMEM_BYTES, cudaGetErrorString(e));
         configured = true;
     }
     const float* gP = layer == 3 ? c->ghead : c->gact[layer];
@@ -496,7 +482,8 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
     const int ntiles = (c->batch * D::PPF + 127) / 128;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, NTHREADS, D::SMEM_BYTES, s>>>((const __nv_bfloat16*)c->dy_bf16, (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag);
+    ConvArgs args{(const __nv_bfloat16*)c->dy_bf16, (const __nv_bfloat16*)wpk, nullptr, c->gact[layer - 1], nullptr, nullptr, c->batch, c->err_flag};
+    kern<<<grid, NTHREADS, P::SMEM_BYTES, s>>>(args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;
 }
@@ -509,9 +496,9 @@ int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
     const uint8_t* base = (const uint8_t*)c->w_packed;
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch_dgrad<ctc::L2>(c, 1, base + kPackD2, s, "conv2_dgrad_tc_kernel");
-    case 2: return ctc::launch_dgrad<ctc::L3>(c, 2, base + kPackD3, s, "conv3_dgrad_tc_kernel");
-    default: return ctc::launch_dgrad<ctc::L4>(c, 3, base + kPackD4, s, "conv4_dgrad_tc_kernel");
+    case 1: return ctc::launch_dgrad<ctc::L2, 8, 3>(c, 1, base + kPackD2, s, "conv2_dgrad_tc_kernel");
+    case 2: return ctc::launch_dgrad<ctc::L3, 8, 3>(c, 2, base + kPackD3, s, "conv3_dgrad_tc_kernel");
+    default: return ctc::launch_dgrad<ctc::L4, 4, 4>(c, 3, base + kPackD4, s, "conv4_dgrad_tc_kernel");
     }
 }
 
@@ -523,8 +510,8 @@ int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream) {
     const uint8_t* base = (const uint8_t*)c->w_packed;
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch<ctc::L2>(c, 1, base + kPackOff2, s, "conv2_tc_kernel");
-    case 2: return ctc::launch<ctc::L3>(c, 2, base + kPackOff3, s, "conv3_tc_kernel");
-    default: return ctc::launch<ctc::L4>(c, 3, base + kPackOff4, s, "conv4_tc_kernel");
+    case 1: return ctc::launch<ctc::L2, 8, 3>(c, 1, base + kPackOff2, s, "conv2_tc_kernel");
+    case 2: return ctc::launch<ctc::L3, 8, 3>(c, 2, base + kPackOff3, s, "conv3_tc_kernel");
+    default: return ctc::launch<ctc::L4, 4, 4>(c, 3, base + kPackOff4, s, "conv4_tc_kernel");
     }
 }

@@ -91,28 +91,46 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // whole warp runs the loop, one elected lane issues (the pattern of the conv kernels)
         const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, (uint32_t)N, 0, 0);
         const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, 256, tc05::SW_NONE);
         const long long t0 = clock64();
         bool ok = true;
+        uint32_t st = 0, ph = 0;
+        if (mode == 1) {
+            // unrolled x8: every MMA of a group has its own uniform operand registers
+            for (int i = 0; i < reps; i += 8) {
+                if (tc05::elect_one()) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        tc05::mma_bf16(tmem_base, ad0 + (uint64_t)(u * 256), bd0 + (uint64_t)(u * 16), idesc, (i | u) > 0);
+                }
+                __syncwarp();
+            }
+        } else
         for (int i = 0; ok && i < reps; ++i) {
             if (NS) {
-                ok = tc05::mbar_wait(full + i % NS, (i / NS) & 1, err);
+                ok = tc05::mbar_wait(full + st, ph, err);
                 tc05::tc_fence_after();
             }
-            tc05::mma_bf16(tmem_base, ad0 + (mode ? (uint64_t)((i & 7) * 256) : 0), bd0, idesc, i > 0);
-            if (NS) tc05::mma_commit(empty + i % NS);
-            else if (mode == 2) tc05::mma_commit(full + (i % 14));
+            if (tc05::elect_one()) {
+                tc05::mma_bf16(tmem_base, ad0 + (mode ? (uint64_t)((i & 7) * 256) : 0), bd0, idesc, i > 0);
+                if (NS) tc05::mma_commit(empty + st);
+                else if (mode == 2) tc05::mma_commit(full + (i % 14));
+            }
+            __syncwarp();
+            if (NS && ++st == (uint32_t)NS) { st = 0; ph ^= 1; }
         }
-        tc05::mma_commit(&bar);
+        if (tc05::elect_one()) tc05::mma_commit(&bar);
+        __syncwarp();
         const long long t1 = clock64();
         tc05::mbar_wait(&bar, 0, err);
         const long long t2 = clock64();
-        if (blockIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t0; }
     } else if (NS && warp >= 1 && warp <= NS) {
-        const int st = warp - 1;
+        const int st = warp - 1;   // warp 0 issues; warps 1..NS are the stand-in producers
         bool ok = true;
         for (int u = 0; ok && st + u * NS < reps; ++u) {
             ok = tc05::mbar_wait(empty + st, (u & 1) ^ 1, err);
@@ -131,9 +149,11 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
 }  // namespace
 
 extern "C" int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream) {
+    const int threads = (mode >> 8) ? (mode >> 8) : 512;   // bits 8.. of mode: CTA size override
+    mode &= 0xff;
     BC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && cycles2 && err_flag, "bc_tc_mma_bench: bad arguments");
     const int smem = 8 * 4096 + 8192;
-    tc_mma_bench_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(N, reps, mode, cycles2, err_flag);
+    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, cycles2, err_flag);
     BC_CUDA_LAUNCH_CHECK("tc_mma_bench_kernel");
     return BC_OK;
 }

@@ -17,3 +17,7 @@ for N in (16, 64, 128, 256):
 print("N  64 commit after every MMA          : issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, 2))
 for ns in (1, 2, 4, 7, 8, 14):
     print(f"N  64 ring of {ns:2d} stages (wait/commit per MMA): issue %.1f complete %.1f cyc/mma err %d" % run(64, 448, 2 + ns))
+for N in (16, 64, 128, 256):
+    print(f"N {N:3d} unrolled x8 groups, one commit   : issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1))
+for th in (512, 64, 128, 256, 512):
+    print(f"N  64 back-to-back, CTA of {th:3d} threads: issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, (th << 8) | 0))
