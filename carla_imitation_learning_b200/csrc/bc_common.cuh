@@ -11,6 +11,7 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream);            // conv1_tc.cu
 int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream);  // conv_tc.cu (layers 1..3)
 int bc_conv_tc_pack(const bc_ctx* c, void* stream);
 int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
+int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 size_t bc_conv_tc_pack_total();
 
 namespace bc {

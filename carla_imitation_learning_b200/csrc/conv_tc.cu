@@ -413,6 +413,180 @@ struct DgradP {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// wgrad on tensor cores:  dW[(tap,ci)][co] = sum_pixels patch[pixel][(tap,ci)] * dY[pixel][co]
+// GEMM with M = taps*C_in (one 128-row M-tile = 8 im2col chunks of 16 channels), N = C_out,
+// K = pixels of the pooled conv region, 128 per visit. Both operands are "MN-major": the gathered
+// chunks keep the pixel (=K) index at 16-byte stride and 8 channels contiguous, which is exactly the
+// canonical MN-major core matrix, so the SAME gather as the forward feeds the transposed product:
+//   chunk image: byte(r = pixel, c = channel half) = c*2048 + (r/8)*128 + (r%8)*16
+//   A descriptor over 8 chunks: M-blocks (8 channels) every 2048 B (SBO), K-blocks (8 pixels) every 128 B (LBO)
+//   B = dY tile [pixel][co] stored as [co/8][pixel][16 B]: same strides.
+// One CTA = one M-tile (blockIdx.y) x a strided set of pixel tiles (blockIdx.x = partial-sum slot);
+// the accumulator lives in TMEM for the whole kernel and leaves once, as that slot's partial dW in
+// arena (OIHW) order. An extra all-ones chunk makes the bias gradient one more row of the same GEMM.
+template <typename C>
+struct WCfg {
+    static constexpr int N = C::COUT, CIN = C::CIN, KS = C::KS, HIN = C::HIN, HD = 2 * C::HP;
+    static constexpr int NSTEP = C::NSTEP;                  // im2col chunks (tap, 16-channel block)
+    static constexpr int NCH = NSTEP + 1;                   // + the ones chunk (bias gradient)
+    static constexpr int NMT = (NCH + 7) / 8;               // M-tiles = gridDim.y
+    static constexpr int PPF = HD * HD;                     // conv pixels per frame that feed a pool window
+    static constexpr int DY_BYTES = N * 256;                // [N/8][128 pixels][16 B]
+    static constexpr int STAGE_BYTES = 8 * A_CHUNK + DY_BYTES;
+    static constexpr int NSTAGE = 3;
+    static constexpr int OFF_BAR = NSTAGE * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSTAGE + 1) * 8 + 16;
+    static constexpr int TMEM_COLS = N < 32 ? 32 : N;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(NTHREADS, 1)
+wgrad_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ dY, float* __restrict__ part,
+                int64_t seg_len, int64_t w_off, int64_t b_off, int B, int* err) {
+    using W = WCfg<C>;
+    constexpr int N = W::N, CIN = W::CIN, KS = W::KS, HIN = W::HIN, HD = W::HD, NSTEP = W::NSTEP, PPF = W::PPF, NSTAGE = W::NSTAGE;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W::OFF_BAR);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + NSTAGE;
+    uint64_t* done = bars + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.y;
+    const int npix = B * PPF;
+    const int nkt = (npix + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { tc05::mbar_init(a_full + i, 8); tc05::mbar_init(a_empty + i, 1); }
+        tc05::mbar_init(done, 1);
+        tc05::mbar_fence_init();
+    }
+    if (warp == 2) tc05::tmem_alloc(tmem_slot, W::TMEM_COLS);
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool any = (int)blockIdx.x < nkt;
+
+    if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer: 8 K-steps (16 pixels each) per visit
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 1, 1);     // both operands MN-major
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 2048, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * A_CHUNK), 128, 2048, tc05::SW_NONE);
+        uint32_t st = 0, ph = 0;
+        bool ok = true, first = true;
+        for (int kt = blockIdx.x; ok && kt < nkt; kt += gridDim.x) {
+            ok = tc05::mbar_wait(a_full + st, ph, err);
+            tc05::tc_fence_after();
+            if (ok && tc05::elect_one()) {
+                const uint64_t so = (uint64_t)(st * (W::STAGE_BYTES >> 4));
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    tc05::mma_bf16(tmem_base, ad0 + so + (uint64_t)(u * 16), bd0 + so + (uint64_t)(u * 16), idesc, (first && u == 0) ? 0u : 1u);
+                tc05::mma_commit(a_empty + st);
+            }
+            __syncwarp();
+            first = false;
+            if (++st == NSTAGE) { st = 0; ph ^= 1; }
+        }
+        if (tc05::elect_one()) tc05::mma_commit(done);
+        __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ epilogue: this slot's partial dW (and db)
+        const int ew = warp - 4;
+        const int i = ew * 32 + lane;                          // accumulator row = (chunk in tile, channel in block)
+        const int ch = mt * 8 + (i >> 4), ci16 = i & 15;
+        float* dst = part + (size_t)blockIdx.x * seg_len;
+        const bool okw = tc05::mbar_wait(done, 0, err);
+        tc05::tc_fence_after();
+        if (okw) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                if (any) {
+                    tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + c0, v);
+                    tc05::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;   // a slot without pixel tiles contributes zeros
+                }
+                if (ch < NSTEP) {
+                    const int tap = ch / C::CB, ci = (ch % C::CB) * 16 + ci16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        dst[w_off + ((size_t)(c0 + j) * CIN + ci) * (KS * KS) + tap] = v[j];
+                } else if (ch == NSTEP && ci16 == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[b_off + c0 + j] = v[j];
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ producers: warp pw gathers chunk pw of this M-tile
+        const int pw = warp - 8;
+        const int step = mt * 8 + pw;                          // (tap, channel block); == NSTEP: the ones chunk
+        const int tap = step < NSTEP ? step / C::CB : 0, cb = step < NSTEP ? step % C::CB : 0;
+        const int toff = ((tap / KS) * HIN + (tap % KS)) * CIN + cb * 16;
+        constexpr int DYV = W::DY_BYTES / 16 / 256;            // dY uint4s per producer lane
+        uint32_t st = 0, ph = 1;
+        uint4 v[4][2];
+        uint4 dv[DYV];
+        auto load = [&](int kt) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int pg = kt * 128 + q * 32 + lane;
+                v[q][0] = make_uint4(0, 0, 0, 0); v[q][1] = make_uint4(0, 0, 0, 0);
+                if (pg < npix) {
+                    if (step < NSTEP) {
+                        const int b = pg / PPF, pl = pg % PPF;
+                        const uint4* p = reinterpret_cast<const uint4*>(act + (((size_t)b * HIN + pl / HD) * HIN + pl % HD) * CIN + toff);
+                        v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                    } else if (step == NSTEP) {
+                        v[q][0] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0 x8
+                        v[q][1] = v[q][0];
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < DYV; ++d) {
+                const int e = (d * 8 + pw) * 32 + lane;          // uint4 index: (n-block, pixel)
+                const int nb = e >> 7, r = e & 127;
+                const int pg = kt * 128 + r;
+                dv[d] = pg < npix ? __ldg(reinterpret_cast<const uint4*>(dY + (size_t)pg * N + nb * 8)) : make_uint4(0, 0, 0, 0);
+            }
+        };
+        int kt = blockIdx.x;
+        if (kt < nkt) load(kt);
+        while (kt < nkt) {
+            if (!tc05::mbar_wait(a_empty + st, ph, err)) break;
+            uint8_t* sa = smem + st * W::STAGE_BYTES + pw * A_CHUNK;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q * 32 + lane;
+                uint8_t* d = sa + (r >> 3) * 128 + (r & 7) * 16;
+                *reinterpret_cast<uint4*>(d) = v[q][0];
+                *reinterpret_cast<uint4*>(d + 2048) = v[q][1];
+            }
+            uint8_t* sd = smem + st * W::STAGE_BYTES + 8 * A_CHUNK;
+#pragma unroll
+            for (int d = 0; d < DYV; ++d) {
+                const int e = (d * 8 + pw) * 32 + lane;
+                *reinterpret_cast<uint4*>(sd + (e >> 7) * 2048 + (e & 127) * 16) = dv[d];
+            }
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(a_full + st);
+            if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            kt += gridDim.x;
+            if (kt < nkt) load(kt);
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc05::tmem_dealloc(tmem_base, W::TMEM_COLS);
+}
+
 using L2 = Cfg<16, 32, 5, 28, 12>;
 using L3 = Cfg<32, 64, 4, 12, 4>;
 using L4 = Cfg<64, 128, 3, 4, 1>;
@@ -488,6 +662,43 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
     return BC_OK;
 }
 }  // namespace ctc
+
+namespace ctc {
+template <typename C>
+int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
+    using W = WCfg<C>;
+    auto kern = wgrad_tc_kernel<C>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, W::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
+    const bc::Partials pl = bc::partials_layout(ar);
+    const int seg = 4 - layer;
+    const float* gP = layer == 3 ? c->ghead : c->gact[layer];
+    const int nu = c->batch * C::WPF * (C::COUT / 8);
+    unpool_kernel<C><<<(nu + 255) / 256, 256, 0, s>>>(gP, c->act[layer], c->amax[layer], (__nv_bfloat16*)c->dy_bf16, c->batch);
+    kern<<<dim3(bc::kWgradParts[layer], W::NMT), NTHREADS, W::SMEM_BYTES, s>>>(
+        (const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)c->dy_bf16, c->partials + pl.off[seg], ar.seg_len[seg],
+        ar.w[layer] - ar.seg_off[seg], ar.b[layer] - ar.seg_off[seg], c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK(name);
+    return BC_OK;
+}
+}  // namespace ctc
+
+int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
+    BC_CHECK_ARG(layer >= 1 && layer <= 3, "wgrad (tcgen05): layer %d", layer);
+    BC_CHECK_ARG(c->err_flag && c->dy_bf16 && c->act_bf16[layer - 1] && c->partials && c->act[layer] && c->amax[layer],
+                 "conv%d wgrad (tcgen05): null buffer", layer + 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (layer) {
+    case 1: return ctc::launch_wgrad<ctc::L2>(c, 1, s, "conv2_wgrad_tc_kernel");
+    case 2: return ctc::launch_wgrad<ctc::L3>(c, 2, s, "conv3_wgrad_tc_kernel");
+    default: return ctc::launch_wgrad<ctc::L4>(c, 3, s, "conv4_wgrad_tc_kernel");
+    }
+}
 
 int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
     BC_CHECK_ARG(layer >= 1 && layer <= 3, "dgrad (tcgen05): layer %d", layer);

@@ -162,3 +162,43 @@ def test_dgrad_tcgen05_matches_exact_f32_dgrad(B):
         assert err <= 1e-2, (layer, err)             # bf16 rounding of dY and W, f32 accumulation
     eng.conv_mode = 1
     eng.check_device_errors()
+
+
+@pytest.mark.parametrize("B", [2, 37])
+def test_wgrad_tcgen05_matches_exact_f32_wgrad(B):
+    """Tensor-core wgrad (MN-major operands, ones-chunk bias row) vs the exact routing-sparse f32 kernel."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib, stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    frames, labels = O.synth_frames(9 + B, B + 4)
+    x = sliding_window(stage_gray(torch.from_numpy(frames).to(dev), dtype=torch.bfloat16))
+    y = torch.from_numpy(labels[4:4 + B]).to(dev)
+    bufs = eng.train_forward_backward(x, y)
+    s = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    params = dict(net.named_parameters())
+    names = ["cnn_base.0", "cnn_base.3", "cnn_base.6", "cnn_base.9"]
+    for layer in (3, 2, 1):
+        gP = bufs.ghead if layer == 3 else bufs.gact[layer]
+        gP.copy_(torch.randn(gP.shape, generator=gen).to(dev))
+        res = {}
+        for mode in (1, 0):
+            eng.conv_mode = mode
+            c = eng.ctx(bufs)
+            _lib.check(eng.lib.bc_conv_bwd_wgrad(C.byref(c), layer, s), "wgrad")
+            _lib.check(eng.lib.bc_reduce_partials_range(C.byref(c), 4 - layer, 5 - layer, 0, s), "reduce")
+            torch.cuda.synchronize()
+            res[mode] = {k: eng.grads[params[f"{names[layer]}.{k}"]._bc_offset:][:params[f"{names[layer]}.{k}"].numel()].clone()
+                         for k in ("weight", "bias")}
+        for k in ("weight", "bias"):
+            err = float((res[1][k] - res[0][k]).abs().max() / res[0][k].abs().max())
+            assert err <= 1e-2, (layer, k, err)
+    eng.conv_mode = 1
+    eng.check_device_errors()
