@@ -12,6 +12,8 @@ int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream);  // conv_tc.cu 
 int bc_conv_tc_pack(const bc_ctx* c, void* stream);
 int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
+int bc_unpool_launch(const bc_ctx* c, int layer, void* stream);
+void bc_tc_set_dy_ready(bool v);
 size_t bc_conv_tc_pack_total();
 
 namespace bc {
@@ -66,7 +68,7 @@ __host__ inline Arena arena_layout(int obs, int na) {
 }
 
 // partial-sum workspace: per segment, NPART[seg] copies of seg_len floats, then loss partials
-constexpr int kHeadBlocks = 32;     // partial copies of the head segment
+constexpr int kHeadBlocks = 128;    // partial copies of the head segment (= head CTAs: 2 samples each at B=256)
 constexpr int kWgradParts[4] = {296, 37, 9, 4};  // conv1..conv4 (grid.x of the wgrad kernels)
 struct Partials { int64_t off[5]; int nparts[5]; int64_t loss_off; int64_t total; };
 __host__ inline Partials partials_layout(const Arena& a) {

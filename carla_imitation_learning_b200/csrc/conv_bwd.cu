@@ -257,8 +257,14 @@ struct ReduceArgs {
     int64_t loss_off; int n_loss; int64_t begin, end; int with_loss;
 };
 
+// 32 consecutive arena elements per CTA x 8 part-groups: thread (e, g) sums copies p = g, g+8, ... in
+// order, the 8 group sums are then added in fixed order => deterministic, with 8x the loads in flight of
+// a one-thread-per-element walk over up to 296 copies.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
-    const int64_t i = a.begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red[8][33];
+    const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t i = a.begin + (int64_t)blockIdx.x * 32 + e;
+    float acc = 0.f;
     if (i < a.end) {
         int s = 0;
 #pragma unroll
@@ -266,14 +272,19 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
         const float* p = a.part + a.poff[s] + (i - a.seg_off[s]);
         const int64_t stride = a.seg_len[s];
         const int n = a.nparts[s];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int q = 0;
-        for (; q + 4 <= n; q += 4) {
-            s0 += p[(int64_t)q * stride]; s1 += p[(int64_t)(q + 1) * stride];
-            s2 += p[(int64_t)(q + 2) * stride]; s3 += p[(int64_t)(q + 3) * stride];
-        }
-        for (; q < n; ++q) s0 += p[(int64_t)q * stride];
-        a.grads[i] = (s0 + s1) + (s2 + s3);
+        float s0 = 0.f, s1 = 0.f;
+        int q = g;
+        for (; q + 8 < n; q += 16) { s0 += p[(int64_t)q * stride]; s1 += p[(int64_t)(q + 8) * stride]; }
+        if (q < n) s0 += p[(int64_t)q * stride];
+        acc = s0 + s1;
+    }
+    red[g][e] = acc;
+    __syncthreads();
+    if (g == 0 && i < a.end) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][e];
+        a.grads[i] = t;
     }
     if (a.with_loss && blockIdx.x == 0 && threadIdx.x < 32) {
         float v = 0.f;
@@ -369,7 +380,7 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
     a.begin = ar.seg_off[seg_lo];
     a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];
-    reduce_partials_kernel<<<(int)((a.end - a.begin + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    reduce_partials_kernel<<<(int)((a.end - a.begin + 31) / 32), 256, 0, (cudaStream_t)stream>>>(a);
     BC_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return BC_OK;
 }

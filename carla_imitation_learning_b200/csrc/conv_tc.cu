@@ -39,9 +39,7 @@ struct Cfg {
 
 // f32 OIHW -> bf16 operand image: step s = (tap, cb): COUT rows x 16 k (k = ci within the block)
 template <typename C>
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C::NSTEP * C::COUT * 16) return;
+__device__ __forceinline__ void pack_fwd_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int i) {
     const int k = i & 15, n = (i >> 4) % C::COUT, s = i / (16 * C::COUT);
     const int tap = s / C::CB, cb = s % C::CB;
     const float v = w[((size_t)n * C::CIN + cb * 16 + k) * (C::KS * C::KS) + tap];
@@ -336,10 +334,8 @@ struct DCfg {
 
 // B operand of dgrad: step s = (tap, cb): N = C_in rows x 16 k (k = co within the block)
 template <typename C>
-__global__ void pack_dgrad_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+__device__ __forceinline__ void pack_dgrad_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int i) {
     using D = DCfg<C>;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= D::NSTEP * D::N * 16) return;
     const int k = i & 15, n = (i >> 4) % D::N, s = i / (16 * D::N);
     const int tap = s / D::CB, cb = s % D::CB;
     const float v = w[((size_t)(cb * 16 + k) * C::CIN + n) * (C::KS * C::KS) + tap];
@@ -591,6 +587,17 @@ using L2 = Cfg<16, 32, 5, 28, 12>;
 using L3 = Cfg<32, 64, 4, 12, 4>;
 using L4 = Cfg<64, 128, 3, 4, 1>;
 
+// bc_backward runs unpool once per layer and tells the wgrad/dgrad launchers to reuse its output
+static thread_local bool g_dy_ready = false;
+
+template <typename C>
+void run_unpool(const bc_ctx* c, int layer, cudaStream_t s) {
+    if (g_dy_ready) return;
+    const float* gP = layer == 3 ? c->ghead : c->gact[layer];
+    const int nu = c->batch * C::WPF * (C::COUT / 8);
+    unpool_kernel<C><<<(nu + 255) / 256, 256, 0, s>>>(gP, c->act[layer], c->amax[layer], (__nv_bfloat16*)c->dy_bf16, c->batch);
+}
+
 template <typename C, int G, int NSTAGE>
 int launch(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
     using P = FwdP<C, G, NSTAGE>;
@@ -622,18 +629,43 @@ static constexpr size_t kPackD3 = kPackD2 + ctc::DCfg<ctc::L2>::B_BYTES, kPackD4
 static constexpr size_t kPackTotal = kPackD4 + ctc::DCfg<ctc::L4>::B_BYTES;
 
 size_t bc_conv_tc_pack_total() { return kPackTotal; }
+void bc_tc_set_dy_ready(bool v) { ctc::g_dy_ready = v; }
+
+int bc_unpool_launch(const bc_ctx* c, int layer, void* stream) {
+    BC_CHECK_ARG(layer >= 1 && layer <= 3 && c->dy_bf16, "unpool: bad layer / null dy_bf16");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool keep = ctc::g_dy_ready;
+    ctc::g_dy_ready = false;
+    if (layer == 1) ctc::run_unpool<ctc::L2>(c, 1, s);
+    else if (layer == 2) ctc::run_unpool<ctc::L3>(c, 2, s);
+    else ctc::run_unpool<ctc::L4>(c, 3, s);
+    ctc::g_dy_ready = keep;
+    BC_CUDA_LAUNCH_CHECK("unpool_kernel");
+    return BC_OK;
+}
+
+namespace ctc {
+struct PackArgs { const float* w2; const float* w3; const float* w4; uint8_t* base; };
+constexpr int kNF2 = L2::NSTEP * L2::COUT * 16, kNF3 = L3::NSTEP * L3::COUT * 16, kNF4 = L4::NSTEP * L4::COUT * 16;
+constexpr int kND2 = DCfg<L2>::NSTEP * DCfg<L2>::N * 16, kND3 = DCfg<L3>::NSTEP * DCfg<L3>::N * 16, kND4 = DCfg<L4>::NSTEP * DCfg<L4>::N * 16;
+constexpr int kPackElems = kNF2 + kNF3 + kNF4 + kND2 + kND3 + kND4;
+// all six conv2-4 operand images (forward + dgrad) in one launch
+__global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kNF2) { pack_fwd_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + o2), i); return; } i -= kNF2;
+    if (i < kNF3) { pack_fwd_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + o3), i); return; } i -= kNF3;
+    if (i < kNF4) { pack_fwd_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + o4), i); return; } i -= kNF4;
+    if (i < kND2) { pack_dgrad_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + d2), i); return; } i -= kND2;
+    if (i < kND3) { pack_dgrad_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + d3), i); return; } i -= kND3;
+    if (i < kND4) pack_dgrad_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + d4), i);
+}
+}  // namespace ctc
 
 int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
-    uint8_t* base = (uint8_t*)c->w_packed;
-    cudaStream_t s = (cudaStream_t)stream;
-    ctc::pack_weights_kernel<ctc::L2><<<(ctc::L2::NSTEP * 32 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[1], (__nv_bfloat16*)(base + kPackOff2));
-    ctc::pack_weights_kernel<ctc::L3><<<(ctc::L3::NSTEP * 64 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[2], (__nv_bfloat16*)(base + kPackOff3));
-    ctc::pack_weights_kernel<ctc::L4><<<(ctc::L4::NSTEP * 128 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[3], (__nv_bfloat16*)(base + kPackOff4));
-    ctc::pack_dgrad_weights_kernel<ctc::L2><<<(ctc::DCfg<ctc::L2>::NSTEP * 16 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[1], (__nv_bfloat16*)(base + kPackD2));
-    ctc::pack_dgrad_weights_kernel<ctc::L3><<<(ctc::DCfg<ctc::L3>::NSTEP * 32 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[2], (__nv_bfloat16*)(base + kPackD3));
-    ctc::pack_dgrad_weights_kernel<ctc::L4><<<(ctc::DCfg<ctc::L4>::NSTEP * 64 * 16 + 255) / 256, 256, 0, s>>>(c->params + a.w[3], (__nv_bfloat16*)(base + kPackD4));
-    BC_CUDA_LAUNCH_CHECK("pack_weights_kernel");
+    ctc::PackArgs pa{c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed};
+    ctc::pack_all_kernel<<<(ctc::kPackElems + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
+    BC_CUDA_LAUNCH_CHECK("pack_all_kernel");
     return BC_OK;
 }
 
@@ -649,10 +681,7 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, P::SMEM_BYTES, cudaGetErrorString(e));
         configured = true;
     }
-    const float* gP = layer == 3 ? c->ghead : c->gact[layer];
-    const int nu = c->batch * C::WPF * (C::COUT / 8);
-    // dY covers only the conv rows/cols that feed a pool window; everything the routing does not hit must be zero
-    unpool_kernel<C><<<(nu + 255) / 256, 256, 0, s>>>(gP, c->act[layer], c->amax[layer], (__nv_bfloat16*)c->dy_bf16, c->batch);
+    run_unpool<C>(c, layer, s);   // dY covers only the conv rows/cols that feed a pool window; unrouted positions are zero
     const int ntiles = (c->batch * D::PPF + 127) / 128;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
@@ -677,9 +706,7 @@ int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
     const int seg = 4 - layer;
-    const float* gP = layer == 3 ? c->ghead : c->gact[layer];
-    const int nu = c->batch * C::WPF * (C::COUT / 8);
-    unpool_kernel<C><<<(nu + 255) / 256, 256, 0, s>>>(gP, c->act[layer], c->amax[layer], (__nv_bfloat16*)c->dy_bf16, c->batch);
+    run_unpool<C>(c, layer, s);
     kern<<<dim3(bc::kWgradParts[layer], W::NMT), NTHREADS, W::SMEM_BYTES, s>>>(
         (const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)c->dy_bf16, c->partials + pl.off[seg], ar.seg_len[seg],
         ar.w[layer] - ar.seg_off[seg], ar.b[layer] - ar.seg_off[seg], c->batch, c->err_flag);
