@@ -204,24 +204,39 @@ def run_b200(args):
         bufs.y = dev_labels[i % NBUF]
         train(bufs)
 
-    # CUDA graphs: one per input buffer (single GPU; the NCCL exchange stays eager for N > 1)
+    # CUDA graphs: one per input buffer. For N > 1 the step is captured as three graph segments with the
+    # two NCCL all-reduces launched eagerly between them (capturing NCCL inside one graph hung on this
+    # torch/NCCL build): [stage..reduce fc-conv2] -> allreduce b0 || [conv1 wgrad, reduce] -> allreduce b1 -> [Adam].
     graphs = None
-    if world == 1 and not args.no_graph:
-        for i in range(3):
-            device_step(i)
+    if not args.no_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                device_step(i)
+        torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graphs = []
         for i in range(NBUF):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                device_step(i)
-            graphs.append(g)
-
+            if dp is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    device_step(i)
+                graphs.append(g)
+            else:
+                def pre(i=i):
+                    stage_gray(dev_frames[i % NBUF], out=gray)
+                    if args.mode == "bf16":
+                        eng.pack_weights()
+                    bufs.y = dev_labels[i % NBUF]
+                graphs.append(dp.capture(bufs, pre))
     def step(i):
-        if graphs is not None:
+        if graphs is None:
+            device_step(i)
+        elif dp is None:
             graphs[i % NBUF].replay()
         else:
-            device_step(i)
+            dp.replay(graphs[i % NBUF])
 
     def barrier():
         if world > 1:
@@ -274,7 +289,7 @@ def run_b200(args):
         train(bufs)
 
     slot_graphs = None
-    if graphs is not None:
+    if graphs is not None and world == 1:
         upload(0); upload(1)
         torch.cuda.synchronize()
         slot_graphs = []

@@ -263,6 +263,246 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     if (warp == 2) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ================================================================================================
+// conv1 wgrad on tcgen05 (bf16 mode). Same Toeplitz view as the forward, transposed:
+//   dWt[(ci,ky,p)][(j,co)] = sum_{rows r=(oy,g)}  in[ci][3oy+ky][12g+p] * dY[r][(j,co)]        (GEMM, K = rows)
+//   dW[co][ci][ky][kx]     = sum_{j=0..3} dWt[(ci,ky,3j+kx)][(j,co)]                          (fold, epilogue)
+// dY = pooled gradient routed to the saved first-max position, masked by ReLU; built per tile in smem
+// from (gact0, act1, amax1). Both operands are MN-major: the repacked A chunks keep the row (=K) index at
+// 16 B stride with 8 pixels contiguous, so 8 chunks form one M=128 operand (SBO 2048 / LBO 128).
+// M = 448 -> 4 M-tiles of 8 chunks ordered (ky, ci): tile mt holds kernel rows 2mt, 2mt+1 (tile 3: row 6,
+// plus an all-ones chunk whose accumulator row is the bias gradient). 4 accumulators x 64 columns stay
+// in TMEM for the whole kernel; one partial dW per CTA leaves at the end, already folded to OIHW.
+namespace wg {
+constexpr int NTHREADS = 512;
+constexpr int RAW_BYTES = 4 * PLANE_BYTES;               // 45056, whole tile (all 4 planes), double buffered
+constexpr int STAGE_BYTES = 8 * A_CHUNK;                 // 32768: one M-tile of chunks
+constexpr int NSTAGE = 3;
+constexpr int DY_BYTES = 64 * 256;                       // [8 n-blocks][128 rows][16 B]
+constexpr int OFF_RAW = 0;
+constexpr int OFF_A = OFF_RAW + 2 * RAW_BYTES;           // 90112
+constexpr int OFF_DY = OFF_A + NSTAGE * STAGE_BYTES;     // 188416
+constexpr int OFF_BAR = OFF_DY + 2 * DY_BYTES;           // 221184
+constexpr int NBAR = 2 + 2 + NSTAGE + NSTAGE + 2 + 2 + 1;
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+constexpr int TMEM_COLS = 256;
+}  // namespace wg
+
+__global__ void __launch_bounds__(wg::NTHREADS, 1)
+conv1_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
+                      const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
+                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + wg::OFF_BAR);
+    uint64_t* raw_full = bars;            // [2]
+    uint64_t* raw_empty = bars + 2;       // [2]
+    uint64_t* a_full = bars + 4;          // [wg::NSTAGE]
+    uint64_t* a_empty = bars + 4 + wg::NSTAGE;
+    uint64_t* dy_full = bars + 4 + 2 * wg::NSTAGE;   // [2]
+    uint64_t* dy_empty = bars + 6 + 2 * wg::NSTAGE;  // [2]
+    uint64_t* done = bars + 8 + 2 * wg::NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + wg::NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = B * TILES_PER_FRAME;
+    const bool any = (int)blockIdx.x < ntiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc05::mbar_init(raw_full + i, 1); tc05::mbar_init(raw_empty + i, 8);
+            tc05::mbar_init(dy_full + i, 4); tc05::mbar_init(dy_empty + i, 1);
+        }
+        for (int i = 0; i < wg::NSTAGE; ++i) { tc05::mbar_init(a_full + i, 8); tc05::mbar_init(a_empty + i, 1); }
+        tc05::mbar_init(done, 1);
+        tc05::mbar_fence_init();
+    }
+    if (warp == 2) tc05::tmem_alloc(tmem_slot, wg::TMEM_COLS);
+    // zero the A stages once: rows 126,127 and the unused chunks of M-tile 3 must never hold NaN patterns
+    for (int i = threadIdx.x; i < wg::NSTAGE * wg::STAGE_BYTES / 16; i += wg::NTHREADS) reinterpret_cast<uint4*>(smem + wg::OFF_A)[i] = make_uint4(0, 0, 0, 0);
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader: whole tile (4 planes), double buffered
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                if (!tc05::mbar_wait(raw_empty + buf, ((it >> 1) & 1) ^ 1, err)) break;
+                const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
+                const __nv_bfloat16* src = x + (size_t)b * sn + (size_t)(ty * 18) * 256;
+                tc05::mbar_expect_tx(raw_full + buf, wg::RAW_BYTES);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci)
+                    tc05::bulk_g2s(smem + wg::OFF_RAW + buf * wg::RAW_BYTES + ci * PLANE_BYTES, src + (size_t)ci * sc, PLANE_BYTES, raw_full + buf);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer: per tile 4 visits (M-tiles) x 8 K-steps
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 1, 1);      // MN-major A and B
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + wg::OFF_A), 128, 2048, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + wg::OFF_DY), 128, 2048, tc05::SW_NONE);
+        uint32_t st = 0, ph = 0;
+        bool ok = true;
+        int it = 0;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ok = tc05::mbar_wait(dy_full + buf, (it >> 1) & 1, err);
+#pragma unroll 1
+            for (int mt = 0; ok && mt < 4; ++mt) {
+                ok = tc05::mbar_wait(a_full + st, ph, err);
+                tc05::tc_fence_after();
+                if (ok && tc05::elect_one()) {
+                    const uint64_t a_st = ad0 + (uint64_t)(st * (wg::STAGE_BYTES >> 4));
+                    const uint64_t b_t = bd0 + (uint64_t)(buf * (wg::DY_BYTES >> 4));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        tc05::mma_bf16(tmem_base + mt * 64, a_st + (uint64_t)(u * 16), b_t + (uint64_t)(u * 16), idesc, (it > 0 || u > 0) ? 1u : 0u);
+                    tc05::mma_commit(a_empty + st);
+                    if (mt == 3) tc05::mma_commit(dy_empty + buf);
+                }
+                __syncwarp();
+                if (++st == wg::NSTAGE) { st = 0; ph ^= 1; }
+            }
+        }
+        if (tc05::elect_one()) tc05::mma_commit(done);
+        __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ dY builder, then the folding epilogue
+        const int ew = warp - 4;
+        const int te = threadIdx.x - 128;
+        bool ok = true;
+        int it = 0;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ok = tc05::mbar_wait(dy_empty + buf, ((it >> 1) & 1) ^ 1, err);
+            if (!ok) break;
+            uint8_t* dy = smem + wg::OFF_DY + buf * wg::DY_BYTES;
+#pragma unroll
+            for (int q = 0; q < wg::DY_BYTES / 16 / 128; ++q) reinterpret_cast<uint4*>(dy)[te + 128 * q] = make_uint4(0, 0, 0, 0);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const int o = te + 128 * q;                      // 2 pooled rows x 16 channels x 28 columns
+                const int px = o % 28, co = (o / 28) & 15, pyl = o / 448;
+                const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
+                const float gv = aP[g] > 0.f ? gP[g] : 0.f;
+                const int pos = amax[g];
+                const int oyl = 3 * pyl + pos / 3, ox = 3 * px + pos % 3;
+                const int r = oyl * NG + (ox >> 2), n = (ox & 3) * 16 + co;
+                *reinterpret_cast<__nv_bfloat16*>(dy + (n >> 3) * 2048 + r * 16 + (n & 7) * 2) = __float2bfloat16_rn(gv);
+            }
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(dy_full + buf);
+        }
+        // ---- epilogue: fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
+        float* dst = part + (size_t)blockIdx.x * seg_len;
+        if ((int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
+            for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
+                for (int i = te; i < 3136 + 16; i += 128) part[(size_t)s2 * seg_len + (i < 3136 ? w_off + i : b_off + i - 3136)] = 0.f;
+        }
+        if (ok && tc05::mbar_wait(done, 0, err)) {
+            tc05::tc_fence_after();
+            const int i = ew * 32 + lane;                            // accumulator row: chunk = i/16 (ky half, ci), p = i%16
+            const int chunk = i >> 4, p = i & 15;
+#pragma unroll 1
+            for (int mt = 0; mt < 4; ++mt) {
+                float v[64];
+                if (any) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + mt * 64 + c0, v + c0);
+                    tc05::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) v[c] = 0.f;
+                }
+                const int ky = 2 * mt + (chunk >> 2), ci = chunk & 3;
+                const bool wrow = ky < 7 && p < 7;                  // this lane writes tap kx = p
+                const bool brow = mt == 3 && chunk == 4 && p == 0;  // ones chunk: bias gradient
+#pragma unroll
+                for (int co = 0; co < 16; ++co) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // dW[.., kx] += dWt[p = 3j + kx][(j, co)]: fetch column j*16+co from the lane holding row 3j+kx
+                        const int srcl = (lane & 16) + ((3 * j + p) & 15);
+                        const float o = __shfl_sync(0xffffffffu, v[j * 16 + co], srcl);
+                        acc += brow ? v[j * 16 + co] : o;
+                    }
+                    if (wrow) dst[w_off + ((size_t)(co * 4 + ci) * 7 + ky) * 7 + p] = acc;
+                    else if (brow) dst[b_off + co] = acc;
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ repack: warp w fills chunk w of every M-tile stage
+        const int pw = warp - 8;
+        const int ci = pw & 3;
+        int src_off[4], dst_off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = q * 32 + lane;
+            src_off[q] = r < MROWS ? (3 * (r / NG)) * ROW_BYTES + 24 * (r % NG) : -1;
+            dst_off[q] = (r >> 3) * 128 + (r & 7) * 16;            // wgrad image: chunk half c at +2048
+        }
+        uint32_t st = 0, ph = 1;
+        bool ok = true;
+        int it = 0;
+        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ok = tc05::mbar_wait(raw_full + buf, (it >> 1) & 1, err);
+#pragma unroll 1
+            for (int mt = 0; ok && mt < 4; ++mt) {
+                ok = tc05::mbar_wait(a_empty + st, ph, err);
+                if (!ok) break;
+                const int ky = 2 * mt + (pw >> 2);
+                uint8_t* dst = smem + wg::OFF_A + st * wg::STAGE_BYTES + pw * A_CHUNK;
+                if (ky < 7) {
+                    const uint8_t* base = smem + wg::OFF_RAW + buf * wg::RAW_BYTES + ci * PLANE_BYTES + ky * ROW_BYTES;
+                    uint2 v[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (src_off[q] >= 0) {
+                            const uint2* pp = reinterpret_cast<const uint2*>(base + src_off[q]);
+                            v[q][0] = pp[0]; v[q][1] = pp[1]; v[q][2] = pp[2]; v[q][3] = pp[3];
+                        }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (src_off[q] >= 0) {
+                            uint8_t* d = dst + dst_off[q];
+                            *reinterpret_cast<uint4*>(d) = make_uint4(v[q][0].x, v[q][0].y, v[q][1].x, v[q][1].y);
+                            *reinterpret_cast<uint4*>(d + 2048) = make_uint4(v[q][2].x, v[q][2].y, v[q][3].x, v[q][3].y);
+                        }
+                } else if (mt == 3 && pw == 4) {
+                    // the ones chunk: accumulator row 64 of M-tile 3 becomes sum_r dY[r][n]
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint8_t* d = dst + dst_off[q];
+                        const uint4 one = (q * 32 + lane) < MROWS ? make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u) : make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(d) = one;
+                        *reinterpret_cast<uint4*>(d + 2048) = one;
+                    }
+                }
+                tc05::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(a_full + st);
+                if (++st == wg::NSTAGE) { st = 0; ph ^= 1; }
+            }
+            if (!ok) break;
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(raw_empty + buf);
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc05::tmem_dealloc(tmem_base, wg::TMEM_COLS);
+}
+
 }  // namespace c1tc
 
 extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
@@ -296,5 +536,26 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
         (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
         c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv1_tc_kernel");
+    return BC_OK;
+}
+
+int bc_conv1_wgrad_tc_launch(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c->x && c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05): null buffer");
+    BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 wgrad (tcgen05): needs bf16 gray planes and obs_size 4");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(c1tc::conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tc::wg::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05): smem opt-in %d B failed: %s", c1tc::wg::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
+    const bc::Partials pl = bc::partials_layout(ar);
+    const int nparts = bc::kWgradParts[0];
+    int grid = bc::num_sms();
+    if (grid > nparts) grid = nparts;
+    c1tc::conv1_wgrad_tc_kernel<<<grid, c1tc::wg::NTHREADS, c1tc::wg::SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, c->gact[0], c->act[0], c->amax[0],
+        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], nparts, c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tc_kernel");
     return BC_OK;
 }

@@ -81,11 +81,12 @@ class DataParallelStep:
         self.xchg = GradExchange(engine.obs_size, engine.n_actions, group)
         optimizer.set_grad_scale(self.xchg.grad_scale)
 
-    def __call__(self, bufs, loss_scale: Optional[float] = None) -> None:
+    # the step as three kernel segments; the exchange is launched between them
+    def _seg_a(self, bufs, loss_scale=None) -> None:
         from .engine import _stream_ptr
         eng, lib = self.eng, self.eng.lib
         c = eng.ctx(bufs, loss_scale)
-        s = _stream_ptr()
+        s, ref = _stream_ptr(), None
         ref = C.byref(c)
         with torch.cuda.device(eng.device):
             for layer in range(4):
@@ -95,9 +96,42 @@ class DataParallelStep:
                 _lib.check(lib.bc_conv_bwd_wgrad(ref, layer, s), "wgrad")
                 _lib.check(lib.bc_conv_bwd_dgrad(ref, layer, s), "dgrad")
             _lib.check(lib.bc_reduce_partials_range(ref, 0, 4, 1, s), "reduce [fc..conv2]")
-            self.xchg.start(eng.grads, 0)                  # overlaps with conv1's wgrad below
-            _lib.check(lib.bc_conv_bwd_wgrad(ref, 0, s), "conv1 wgrad")
-            _lib.check(lib.bc_reduce_partials_range(ref, 4, 5, 0, s), "reduce [conv1]")
-            self.xchg.start(eng.grads, 1)
-            self.xchg.finish()
-            self.opt.step_flat(eng.grads)
+
+    def _seg_b(self, bufs, loss_scale=None) -> None:
+        from .engine import _stream_ptr
+        eng, lib = self.eng, self.eng.lib
+        c = eng.ctx(bufs, loss_scale)
+        with torch.cuda.device(eng.device):
+            _lib.check(lib.bc_conv_bwd_wgrad(C.byref(c), 0, _stream_ptr()), "conv1 wgrad")
+            _lib.check(lib.bc_reduce_partials_range(C.byref(c), 4, 5, 0, _stream_ptr()), "reduce [conv1]")
+
+    def __call__(self, bufs, loss_scale: Optional[float] = None) -> None:
+        self._seg_a(bufs, loss_scale)
+        self.xchg.start(self.eng.grads, 0)                 # overlaps with conv1's wgrad below
+        self._seg_b(bufs, loss_scale)
+        self.xchg.start(self.eng.grads, 1)
+        self.xchg.finish()
+        self.opt.step_flat(self.eng.grads)
+
+    def capture(self, bufs, pre=None):
+        """Capture the three kernel segments as CUDA graphs (NCCL stays outside). `pre` = optional callable
+        enqueuing work that precedes the step (staging, weight packing) into the first segment."""
+        ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            if pre is not None:
+                pre()
+            self._seg_a(bufs)
+        with torch.cuda.graph(gb):
+            self._seg_b(bufs)
+        with torch.cuda.graph(gc):
+            self.opt.step_flat(self.eng.grads)
+        return ga, gb, gc
+
+    def replay(self, graphs) -> None:
+        ga, gb, gc = graphs
+        ga.replay()
+        self.xchg.start(self.eng.grads, 0)
+        gb.replay()
+        self.xchg.start(self.eng.grads, 1)
+        self.xchg.finish()
+        gc.replay()

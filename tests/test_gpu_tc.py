@@ -185,7 +185,7 @@ def test_wgrad_tcgen05_matches_exact_f32_wgrad(B):
     gen = torch.Generator(device="cpu").manual_seed(4)
     params = dict(net.named_parameters())
     names = ["cnn_base.0", "cnn_base.3", "cnn_base.6", "cnn_base.9"]
-    for layer in (3, 2, 1):
+    for layer in (3, 2, 1, 0):          # layer 0 = conv1: Toeplitz wgrad with the fold in the epilogue
         gP = bufs.ghead if layer == 3 else bufs.gact[layer]
         gP.copy_(torch.randn(gP.shape, generator=gen).to(dev))
         res = {}
