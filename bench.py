@@ -377,7 +377,9 @@ def run_b200(args):
             "roofline": {"kernel": ("conv1_tc_kernel (tcgen05 Toeplitz implicit GEMM, bf16)" if args.mode == "bf16"
                                     else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_burst"], "traffic": None, "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
+                         "frac": achieved / peaks["tf_burst"],
+                         "traffic": (35465472 if (args.mode == "bf16" and B == 256) else None),   # ncu dram read+write of this kernel, profiles/r1d
+                         "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
                          "kernel_ms": k_ms, "flops_per_launch": FLOPS_FWD[0] * B,
                          "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
             "roofline_hbm": {"kernel": "stage_gray_kernel", "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
