@@ -126,6 +126,13 @@ class BCEngine:
             if self.conv_mode == 1 and bufs.act_bf16:
                 bufs.dy_bf16 = torch.empty((bufs.batch, 24, 24, 32), dtype=torch.bfloat16, device=self.device)
 
+    def cast_bf16(self, x: torch.Tensor) -> torch.Tensor:
+        """Contiguous f32 -> bf16 copy with our own kernel (bf16 mode fed with the reference's f32 batches)."""
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        _lib.check(self.lib.bc_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream_ptr()), "bc_cast_bf16")
+        return out
+
     def check_input(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, "x")
         if x.device != self.device:
@@ -134,6 +141,8 @@ class BCEngine:
             raise ValueError(f"x must be (B,{self.obs_size},{H},{W}) like nets.py:14, got {tuple(x.shape)}")
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
+        if self.conv_mode == 1 and x.dtype == torch.float32 and self.obs_size == 4:
+            x = self.cast_bf16(x)           # tensor-core conv1 reads bf16 planes
         esz = x.element_size()
         ok = (x.stride(3) == 1 and x.stride(2) == W and (x.stride(0) * esz) % 16 == 0 and (x.stride(1) * esz) % 16 == 0
               and x.data_ptr() % 16 == 0)

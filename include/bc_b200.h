@@ -84,6 +84,9 @@ size_t bc_partials_floats(int obs_size, int n_actions);
  * of the reference's shuffle=False loader is the strided view x_stride_n = H*W, x_stride_c = H*W. */
 int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream);
 
+/* bf16 mode fed with f32 samples (the reference's batch format): contiguous f32 -> bf16 cast, n % 4 == 0 */
+int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream);
+
 /* bf16 tensor-core mode: re-pack the f32 master weights into the smem images the tcgen05 kernels
  * read (conv1: Toeplitz-expanded [64 x 448] bf16). Call after every optimiser step. */
 int bc_pack_weights(const bc_ctx* c, void* stream);

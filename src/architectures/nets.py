@@ -59,6 +59,14 @@ class ConvNet1(_Base):
         obs_size = int(hparams['obs_size'])
         n_actions = int(hparams['n_actions'])
         self.obs_size, self.n_actions = obs_size, n_actions
+        # B200 addition (configs/model/imitation.yaml `precision`): 'fp32' = exact FFMA kernels,
+        # 'bf16' = tcgen05 kernels. The reference has no such key; absent means fp32.
+        try:
+            self.precision = str(hparams['precision']) if 'precision' in hparams else 'fp32'
+        except TypeError:
+            self.precision = 'fp32'
+        if self.precision not in ('fp32', 'bf16'):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
 
         # same RNG consumption order as the reference: example input first (nets.py:14) ...
         self.example_input_array = torch.randn((1, obs_size, 256, 256))
@@ -147,6 +155,10 @@ class ConvNet1(_Base):
                     "ConvNet1 runs only on a CUDA sm_100 (B200) device: move it with .to('cuda'). "
                     "There is deliberately no CPU / PyTorch fallback for the hot path.")
             self._engine = BCEngine(self._arena, self.obs_size, self.n_actions)
+            if self.precision == 'bf16' and self.obs_size == 4:
+                self._engine.set_mode('bf16')
+        if self._engine.conv_mode == 1:
+            self._engine.pack_weights()     # bf16 operand images follow the f32 master weights (cheap: 2 launches)
         return self._engine
 
     def _to_device(self, t: torch.Tensor) -> torch.Tensor:

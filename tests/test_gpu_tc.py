@@ -202,3 +202,40 @@ def test_wgrad_tcgen05_matches_exact_f32_wgrad(B):
             assert err <= 1e-2, (layer, k, err)
     eng.conv_mode = 1
     eng.check_device_errors()
+
+
+def test_bf16_module_path_trains_like_the_reference(golden_dir):
+    """precision='bf16' through the Lightning-contract shells: the 1k-step curve of the reference."""
+    import os
+    from carla_imitation_learning_b200 import stage_gray
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    from src.models.imitation import Imitation
+    dev = torch.device("cuda", 0)
+    g = np.load(os.path.join(golden_dir, "ref_curve_b8_1k.npz"))
+    B, steps = int(g["B"]), int(g["steps"])
+    frames, labels = O.synth_frames(int(g["data_seed"]), steps * B + 4)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
+    model = Imitation({"obs_size": 4, "n_actions": 9}, net, {})
+    opt = model.configure_optimizers()[0][0]
+    lab = torch.from_numpy(labels).to(dev)
+    losses = []
+    for s0 in range(0, steps, 50):
+        gray = stage_gray(torch.from_numpy(frames[s0 * B: s0 * B + 50 * B + 4]).to(dev), dtype=torch.bfloat16)
+        for s in range(s0, s0 + 50):
+            o = (s - s0) * B
+            x = gray.as_strided((B, 4, 256, 256), (65536, 65536, 256, 1), gray.storage_offset() + o * 65536)
+            loss = model.training_step((x, lab[s * B + 4: s * B + 4 + B]), s)
+            opt.zero_grad(); loss.backward(); opt.step()
+            losses.append(loss.detach())
+    net.engine().check_device_errors()
+    got = torch.stack(losses).cpu().double().numpy()
+    ref = g["losses"]
+    np.save(os.path.join(os.environ.get("BC_TEST_OUT", "/tmp"), "curve_b8_1k_device_bf16.npy"), got)
+    assert np.abs(got[:30] - ref[:30]).max() <= 2e-2 * ref[:30].max()          # same trajectory within the bf16 tolerance
+    assert abs(got.mean() - ref.mean()) <= 3e-2 * ref.mean(), (got.mean(), ref.mean())
+    assert abs(got[750:].mean() - ref[750:].mean()) <= 6e-2 * ref[750:].mean(), (got[750:].mean(), ref[750:].mean())
+    # f32 reference-style batches are accepted too (cast kernel) and give the same logits as bf16 planes
+    x32 = x.float()
+    assert torch.equal(net(x32), net(x))
