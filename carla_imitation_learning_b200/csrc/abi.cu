@@ -108,7 +108,7 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
     // head: (CE from labels when with_loss, else the caller's dlogits) + MLP backward -> ghead
     int rc = bc_head(c, with_loss ? 3 : 2, stream);
     if (rc) return rc;
-    const bool tc = c->conv_mode == 1 && c->dy_bf16 && c->act_bf16[0];
+    const bool tc = (c->conv_mode & 6) && c->dy_bf16 && c->act_bf16[0];
     for (int l = 3; l >= 1; --l) {
         if (tc) {   // one unpool feeds both the tensor-core wgrad and dgrad of the layer
             if ((rc = bc_unpool_launch(c, l, stream))) return rc;

@@ -100,7 +100,7 @@ class BCEngine:
         # bf16 tensor-core mode: packed MMA operand images + the device error flag of the bounded waits
         self.w_packed = torch.zeros(int(self.lib.bc_packed_weight_bytes()), dtype=torch.uint8, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.conv_mode = 0            # 0 exact f32 FFMA; 1 bf16 tcgen05 (needs bf16 gray planes, obs_size 4)
+        self.conv_mode = 0            # bit mask, see bc_ctx.conv_mode: 0 = exact f32 FFMA kernels, 15 = all tcgen05 kernels
 
     # ------------------------------------------------------------------ buffers
     def alloc(self, batch: int, x: torch.Tensor, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
@@ -112,7 +112,7 @@ class BCEngine:
             amax=[e(batch, *s, dt=torch.uint8) for s in ACT_SHAPES],
             hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
             dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
-        if self.conv_mode == 1:
+        if self.conv_mode & 1:
             bufs.act_bf16 = [torch.empty((batch, s[1], s[2], s[0]), dtype=torch.bfloat16, device=dev) for s in ACT_SHAPES[:3]]
         if backward:
             self._alloc_bwd(bufs)
@@ -123,7 +123,7 @@ class BCEngine:
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
             bufs.ghead = e(bufs.batch, 128)
             bufs.gact = [e(bufs.batch, *s) for s in ACT_SHAPES[:3]]
-            if self.conv_mode == 1 and bufs.act_bf16:
+            if self.conv_mode and bufs.act_bf16:
                 bufs.dy_bf16 = torch.empty((bufs.batch, 24, 24, 32), dtype=torch.bfloat16, device=self.device)
 
     def cast_bf16(self, x: torch.Tensor) -> torch.Tensor:
@@ -141,7 +141,7 @@ class BCEngine:
             raise ValueError(f"x must be (B,{self.obs_size},{H},{W}) like nets.py:14, got {tuple(x.shape)}")
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
-        if self.conv_mode == 1 and x.dtype == torch.float32 and self.obs_size == 4:
+        if (self.conv_mode & 1) and x.dtype == torch.float32 and self.obs_size == 4:
             x = self.cast_bf16(x)           # tensor-core conv1 reads bf16 planes
         esz = x.element_size()
         ok = (x.stride(3) == 1 and x.stride(2) == W and (x.stride(0) * esz) % 16 == 0 and (x.stride(1) * esz) % 16 == 0
@@ -174,7 +174,7 @@ class BCEngine:
 
     def set_mode(self, mode: str) -> None:
         """'fp32' = exact FFMA kernels (rel 1e-5); 'bf16' = tcgen05 kernels on bf16-staged frames (rel 2e-2)."""
-        self.conv_mode = {"fp32": 0, "bf16": 1}[mode]
+        self.conv_mode = {"fp32": 0, "bf16": 15}[mode]
 
     def pack_weights(self) -> None:
         """Refresh the bf16 operand images from the f32 master weights (after every optimiser step in bf16 mode)."""

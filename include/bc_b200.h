@@ -67,7 +67,7 @@ typedef struct {
     float* loss;             /* [1] mean CE                             */
     float* partials;         /* workspace, bc_partials_floats() floats  */
     float loss_scale;        /* dlogits = (softmax-onehot)*loss_scale; 1/batch for the mean */
-    int32_t conv_mode;       /* 0 = exact f32 FFMA kernels; 1 = bf16 tcgen05 kernels where they exist */
+    int32_t conv_mode;       /* bit mask of tcgen05 (bf16) kernels: 1 forward, 2 dgrad, 4 wgrad conv2-4, 8 wgrad conv1; 0 = exact f32 */
     void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
     int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
     void* act_bf16[3];       /* bf16 mode: NHWC bf16 copies of act[0..2] (B,28,28,16) (B,12,12,32) (B,4,4,64),

@@ -157,7 +157,7 @@ class ConvNet1(_Base):
             self._engine = BCEngine(self._arena, self.obs_size, self.n_actions)
             if self.precision == 'bf16' and self.obs_size == 4:
                 self._engine.set_mode('bf16')
-        if self._engine.conv_mode == 1:
+        if self._engine.conv_mode:
             self._engine.pack_weights()     # bf16 operand images follow the f32 master weights (cheap: 2 launches)
         return self._engine
 
