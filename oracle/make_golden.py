@@ -89,6 +89,39 @@ def golden_curve(B, steps, data_seed, path):
     print(path, losses[0], losses[steps // 2], losses[-1])
 
 
+def golden_curve_ensemble(B, steps, data_seed, path, members=8):
+    """The reference's OWN reproducibility envelope: the same 1k-step run of the unmodified reference,
+    re-run `members` times with every initial weight moved by about one f32 ulp (w *= 1 + 6e-8 * N(0,1))
+    and with different intra-op thread counts (different f32 summation orders). Any independent
+    implementation differs from the reference by at least this much rounding, so the spread of these curves
+    is what 'the loss curves agree' can mean; the tests bound the device curve by it."""
+    frames, labels = O.synth_frames(data_seed, steps * B + 4)
+    gray = torch.from_numpy(O.gray_stack(frames))
+    lab = torch.from_numpy(labels)
+    curves, meta = [], []
+    for m in range(members):
+        threads = (1, 2, 4, 8)[m % 4]
+        torch.set_num_threads(threads)
+        net, model = build_ref()
+        gen = torch.Generator().manual_seed(1000 + m)
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.mul_(1.0 + 6e-8 * torch.randn(p_.shape, generator=gen))
+        opt = model.configure_optimizers()[0][0]
+        losses = []
+        for s in range(steps):
+            x = torch.stack([gray[s * B + i: s * B + i + 4] for i in range(B)])
+            y = lab[s * B + 4: s * B + 4 + B]
+            loss = model.training_step((x, y), s)
+            opt.zero_grad(); loss.backward(); opt.step()
+            losses.append(float(loss))
+        curves.append(losses); meta.append(threads)
+        print("member", m, "threads", threads, "mean", np.mean(losses), flush=True)
+    torch.set_num_threads(os.cpu_count())
+    np.savez_compressed(path, B=B, steps=steps, data_seed=data_seed, threads=np.asarray(meta),
+                        losses=np.asarray(curves, np.float64))
+
+
 def golden_labels(path):
     # pandas 3 (this image) returns read-only `.values` under copy-on-write, which the
     # reference's in-place writes (imitation_dataset.py:322-324) predate; feed it a
@@ -134,5 +167,7 @@ if __name__ == "__main__":
     golden_labels(os.path.join(g, "ref_labels.npz"))
     golden_gray(os.path.join(g, "ref_gray.npz"))
     golden_curve(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k.npz"))
+    if "--ensemble" in sys.argv:
+        golden_curve_ensemble(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k_ensemble.npz"))
     if "--f64-curve" in sys.argv:
         oracle_curve_f64(8, 1000, 11, os.path.join(g, "oracle_curve_b8_1k_f64.npy"))

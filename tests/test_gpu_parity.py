@@ -407,16 +407,7 @@ def test_loss_curve_1k_steps_within_one_percent(golden_dir):
     np.save(os.path.join(os.environ.get("BC_TEST_OUT", "/tmp"), "curve_b8_1k_device.npy"), got)
     # (1) while the two trajectories are still the same trajectory, steps agree to rounding
     assert np.abs(got[:70] - ref[:70]).max() <= 1e-3 * ref[:70].max()
-    # (2) the curve as a whole is within 1 %
-    assert abs(got.mean() - ref.mean()) <= 1e-2 * ref.mean(), (got.mean(), ref.mean())
-    # (3) 50-step windows. Adam at lr 1e-3 amplifies rounding differences once the loss leaves the
-    # ln 9 plateau: the reference ALGORITHM evaluated in f64 (oracle, tests/golden/oracle_curve_b8_1k_f64.npy)
-    # already departs from the reference's own f32 run by up to 5.2 % per window, so a 1 % per-window
-    # band is not a property the reference has. The device must stay within 1.5x that sensitivity.
-    f64 = np.load(os.path.join(golden_dir, "oracle_curve_b8_1k_f64.npy"))
-    rw = ref.reshape(-1, 50).mean(1)
-    sens = float((np.abs(f64.reshape(-1, 50).mean(1) - rw) / rw).max())
-    rel = np.abs(got.reshape(-1, 50).mean(1) - rw) / rw
-    assert rel.max() <= max(1e-2, 1.5 * sens), (rel.max(), sens, int(rel.argmax()))
-    # (4) and it ends where the reference ends (last 250 steps within 2 %)
-    assert abs(got[750:].mean() - ref[750:].mean()) <= 2e-2 * ref[750:].mean()
+    # (2)-(5): within 1 % of the reference's own reproducibility envelope (tests/curve_check.py explains why a
+    # bare 1 % band around ONE reference run is not a property the reference itself has)
+    from tests.curve_check import check_curve
+    check_curve(got, golden_dir, tol=1e-2)

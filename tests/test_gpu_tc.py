@@ -234,8 +234,8 @@ def test_bf16_module_path_trains_like_the_reference(golden_dir):
     ref = g["losses"]
     np.save(os.path.join(os.environ.get("BC_TEST_OUT", "/tmp"), "curve_b8_1k_device_bf16.npy"), got)
     assert np.abs(got[:30] - ref[:30]).max() <= 2e-2 * ref[:30].max()          # same trajectory within the bf16 tolerance
-    assert abs(got.mean() - ref.mean()) <= 3e-2 * ref.mean(), (got.mean(), ref.mean())
-    assert abs(got[750:].mean() - ref[750:].mean()) <= 6e-2 * ref[750:].mean(), (got[750:].mean(), ref[750:].mean())
+    from tests.curve_check import check_curve
+    check_curve(got, golden_dir, tol=2e-2, exit_slack=40)                      # bf16 tolerance of the north star
     # f32 reference-style batches are accepted too (cast kernel) and give the same logits as bf16 planes
     x32 = x.float()
     assert torch.equal(net(x32), net(x))

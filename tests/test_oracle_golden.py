@@ -135,3 +135,18 @@ def test_loss_curve_first_steps(golden_dir):
         xb = torch.stack([gray[s * B + i:s * B + i + 4] for i in range(B)])
         loss = tr.step(xb, lab[s * B + 4:s * B + 4 + B])
         assert abs(loss - g["losses"][s]) <= 2e-3 * g["losses"][s], s
+
+
+def test_oracle_f64_curve_sits_inside_the_reference_reproducibility_envelope(golden_dir):
+    """The f64 oracle run and every ensemble member pass the same curve check the device curves get
+    (tests/curve_check.py); a curve stuck on the ln 9 plateau does not."""
+    import pytest
+    from tests.curve_check import check_curve
+    f64 = np.load(os.path.join(golden_dir, "oracle_curve_b8_1k_f64.npy"))
+    check_curve(f64, golden_dir, tol=1e-2)
+    ens = np.load(os.path.join(golden_dir, "ref_curve_b8_1k_ensemble.npz"))["losses"]
+    assert ens.shape == (8, 1000)
+    for c in ens:
+        check_curve(c, golden_dir, tol=1e-2)
+    with pytest.raises(AssertionError):
+        check_curve(np.full(1000, 2.1972), golden_dir, tol=2e-2)
