@@ -199,6 +199,8 @@ def run_b200(args):
 
     def device_step(i):
         stage_gray(dev_frames[i % NBUF], out=gray)
+        if bufs.x_tp is not None:
+            eng.to_tp(bufs.x, out=bufs.x_tp)
         if args.mode == "bf16":
             eng.pack_weights()                 # f32 master weights -> bf16 MMA operand images
         bufs.y = dev_labels[i % NBUF]
@@ -226,6 +228,8 @@ def run_b200(args):
             else:
                 def pre(i=i):
                     stage_gray(dev_frames[i % NBUF], out=gray)
+                    if bufs.x_tp is not None:
+                        eng.to_tp(bufs.x, out=bufs.x_tp)
                     if args.mode == "bf16":
                         eng.pack_weights()
                     bufs.y = dev_labels[i % NBUF]
@@ -283,6 +287,8 @@ def run_b200(args):
 
     def slot_step(k):
         stage_gray(slots[k][0], out=gray)
+        if bufs.x_tp is not None:
+            eng.to_tp(bufs.x, out=bufs.x_tp)
         if args.mode == "bf16":
             eng.pack_weights()
         bufs.y = slots[k][1]
@@ -330,6 +336,7 @@ def run_b200(args):
     L = eng.lib
     ops = [("stage_gray", lambda: stage_gray(dev_frames[0], out=gray))]
     if args.mode == "bf16":
+        ops.append(("planes_to_tp", lambda: eng.to_tp(bufs.x, out=bufs.x_tp)))
         ops.append(("pack_weights", eng.pack_weights))
     ops += [(f"conv{l + 1}_fwd", (lambda l=l: _lib.check(L.bc_conv_relu_pool_fwd(cref, l, s)))) for l in range(4)]
     ops.append(("head_fwd_ce_bwd", lambda: _lib.check(L.bc_head(cref, 3, s))))

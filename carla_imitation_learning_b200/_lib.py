@@ -17,7 +17,8 @@ SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "head.cu", "c
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 
-BC_F32, BC_BF16 = 0, 1
+BC_F32, BC_BF16, BC_BF16_TP = 0, 1, 2
+TP_PLANE_ELEMS = 86688
 
 
 class BcCtx(C.Structure):
@@ -32,6 +33,7 @@ class BcCtx(C.Structure):
         ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
         ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
         ("dy_bf16", C.c_void_p),
+        ("x_tp", C.c_void_p), ("x_tp_stride_n", C.c_int64), ("x_tp_stride_c", C.c_int64),
     ]
 
 
@@ -42,6 +44,7 @@ EXPORTS = {
     "bc_stage_gray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "bc_pack_weights": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_packed_weight_bytes": (C.c_size_t, []),
+    "bc_planes_to_tp": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bc_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bc_forward": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_conv_relu_pool_fwd": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),

@@ -264,6 +264,260 @@ conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
 }
 
 
+}  // namespace c1tc
+
+// ================================================================================================
+// conv1 forward, second generation: the A operand comes straight from "Toeplitz-ready" (TP) planes
+// (stage.cu): no repack warps, no LDS/STS between the bulk copy and the MMA.
+//   * a plane slot in shared memory holds, for one tile (6 conv rows), the 6 pieces (c = row class, h = K half)
+//     of one input plane exactly as they lie in HBM: piece (c,h) = rows q0..q0+nq(c)-1, 336 B each. The A
+//     operand of kernel row ky = 3d + c is the 126 x 16 slice starting d rows into pieces (c,0) / (c,1):
+//     start = P(c,0) + 336 d, SBO = 128 B (8 rows), LBO = P(c,1) - P(c,0). Rows 126, 127 of the M=128
+//     instruction read 32 B past the slice: they only feed accumulator rows that are never read.
+//   * with the sliding-window batch (x_tp_stride_n == x_tp_stride_c) samples b..b+3 share planes: a super-tile
+//     is (tile row ty, up to 4 consecutive samples); its S+3 planes are loaded ONCE and plane j feeds sample s
+//     as channel ci = j - s. L2->smem traffic per sample drops from 4 to 7/4 planes.
+//   * 8 accumulators of 64 columns (2 sets x 4 samples) fill the 512 TMEM columns; two epilogue groups of
+//     4 warps take alternate sample tiles.
+//   * every CTA owns a contiguous, balanced range of the (ty, b) sample-tile list (no wave quantisation).
+namespace c1tp {
+using c1tc::B_BYTES; using c1tc::B_STEP; using c1tc::MROWS; using c1tc::NG; using c1tc::S_PITCH; using c1tc::S_BYTES;
+using c1tc::TILES_PER_FRAME;
+constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, 1-3 and 12 MMA issuers, 4-7 / 8-11 epilogue groups
+constexpr int ROWB = 336;                    // 21 groups x 16 B
+constexpr int PIECE0 = 8 * ROWB, PIECE12 = 7 * ROWB;      // class 0 feeds ky 0,3,6 (8 rows), classes 1,2 feed two ky (7 rows)
+constexpr int SLOT_BYTES = 2 * PIECE0 + 4 * PIECE12;      // 14784
+constexpr int TP_PIECE_BYTES = 86 * ROWB;                 // piece stride inside a TP plane in HBM
+__host__ __device__ constexpr int piece_off(int c, int h) { return c == 0 ? h * PIECE0 : 2 * PIECE0 + (c - 1) * 2 * PIECE12 + h * PIECE12; }
+__host__ __device__ constexpr int a_off(int ky) { return piece_off(ky % 3, 0) + (ky / 3) * ROWB; }
+constexpr int NSLOT = 6;
+constexpr int SMAX = 4;
+constexpr int OFF_B = 0;
+constexpr int OFF_RING = OFF_B + B_BYTES;
+constexpr int OFF_S = (OFF_RING + NSLOT * SLOT_BYTES + 64 + 127) / 128 * 128;   // 64 B: the over-read of the last slice
+constexpr int P_BYTES = 2 * 28 * 16 * 2;                  // one tile's pooled outputs as NHWC bf16
+constexpr int OFF_P = OFF_S + 2 * S_BYTES;
+constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = (OFF_BIAS + 64 + 127) / 128 * 128;
+constexpr int NBAR = 1 + 2 * NSLOT + 8 + 8;
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+constexpr int TMEM_COLS = 512;
+static_assert(SMEM_BYTES <= 227 * 1024, "conv1 (TP) shared memory");
+
+// contiguous balanced range of the (ty, b) sample-tile list, cut into runs of <= smax samples of one tile row
+struct TileIter {
+    int i, hi, B, smax;
+    __device__ TileIter(int B_, int smax_) : B(B_), smax(smax_) {
+        const long long T = (long long)B_ * TILES_PER_FRAME;
+        i = (int)(T * blockIdx.x / gridDim.x);
+        hi = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    }
+    __device__ bool next(int& ty, int& b0, int& S) {
+        if (i >= hi) return false;
+        ty = i / B; b0 = i - ty * B;
+        S = min(smax, min(B - b0, hi - i));
+        i += S;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
+                const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
+                __nv_bfloat16* __restrict__ ybf, int B, int* err) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* b_full = bars;
+    uint64_t* slot_full = bars + 1;                  // [NSLOT]
+    uint64_t* slot_empty = bars + 1 + NSLOT;         // [NSLOT]
+    uint64_t* t_full = bars + 1 + 2 * NSLOT;         // [8] accumulator (set, s)
+    uint64_t* t_empty = bars + 9 + 2 * NSLOT;        // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int smax = (sn == sc) ? SMAX : 1;          // plane sharing needs the sliding window
+
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(b_full, 1);
+        for (int i = 0; i < NSLOT; ++i) { tc05::mbar_init(slot_full + i, 1); tc05::mbar_init(slot_empty + i, 4); }
+        for (int i = 0; i < 8; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(smem + OFF_RING + NSLOT * SLOT_BYTES)[threadIdx.x] = 0u;   // over-read pad
+    if (threadIdx.x < 16) reinterpret_cast<float*>(smem + OFF_BIAS)[threadIdx.x] = bias[threadIdx.x];
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader (one lane): 6 bulk copies per plane
+        if (lane == 0) {
+            tc05::mbar_expect_tx(b_full, B_BYTES);
+            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+            TileIter it(B, smax);
+            int ty, b0, S;
+            uint32_t k = 0;
+            bool ok = true;
+            while (ok && it.next(ty, b0, S)) {
+                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(x + (int64_t)b0 * sn) + (size_t)(6 * ty) * ROWB;
+                for (int j = 0; j < S + 3; ++j, ++k) {
+                    const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
+                    ok = tc05::mbar_wait(slot_empty + slot, ph ^ 1, err);
+                    if (!ok) break;
+                    tc05::mbar_expect_tx(slot_full + slot, SLOT_BYTES);
+                    const uint8_t* src = src0 + (int64_t)j * sc * 2;
+                    uint8_t* dst = smem + OFF_RING + slot * SLOT_BYTES;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            tc05::bulk_g2s(dst + piece_off(c, h), src + (c * 2 + h) * TP_PIECE_BYTES, c == 0 ? PIECE0 : PIECE12, slot_full + slot);
+                }
+            }
+        }
+    } else if (warp <= 3 || warp == 12) {
+        // ------------------------------------------------------------------ 4 MMA issuers (whole warp loops, one elected lane issues)
+        // Sample tile number c (running count over the CTA's list) belongs to issuer c % 4, accumulator c % 8 and
+        // epilogue group c % 2. One issuer alone leaves the tensor pipe idle between groups of MMAs: a queued
+        // tcgen05.mma holds its uniform registers until it is dispatched, so the warp cannot set up the next group
+        // before the previous one has drained (measured: 470 cycles per 7-MMA group, 224 of them busy). With four
+        // issuers, each with its own uniform register file and its own accumulators, the queue never runs dry.
+        const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
+        const uint32_t ring = tc05::smem_u32(smem + OFF_RING);
+        const uint64_t ad_c0 = tc05::smem_desc(ring, PIECE0, 128, tc05::SW_NONE);     // LBO = distance between the K halves
+        const uint64_t ad_c12 = tc05::smem_desc(ring, PIECE12, 128, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_B), 128, 256, tc05::SW_NONE);
+        bool ok = tc05::mbar_wait(b_full, 0, err);
+        TileIter it(B, smax);
+        int ty, b0, S;
+        uint32_t k = 0, use = 0, cnt = 0;
+        while (ok && it.next(ty, b0, S)) {
+            const int s = (int)((w - cnt) & 3);          // the sample of this super-tile this issuer owns (if s < S)
+            const uint32_t idx = (cnt + (uint32_t)s) & 7;
+            for (int j = 0; ok && j < S + 3; ++j, ++k) {
+                const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
+                ok = tc05::mbar_wait(slot_full + slot, ph, err);
+                tc05::tc_fence_after();
+                const int ci = j - s;
+                if (s < S && ci >= 0 && ci <= 3) {
+                    if (ci == 0) {
+                        ok = ok && tc05::mbar_wait(t_empty + idx, ((use >> idx) & 1) ^ 1, err);
+                        tc05::tc_fence_after();
+                    }
+                    if (ok && tc05::elect_one()) {
+                        const uint64_t so = (uint64_t)((slot * SLOT_BYTES) >> 4);
+                        const uint32_t d_tmem = tmem_base + idx * 64;
+                        const uint64_t bb = bd0 + (uint64_t)(ci * 7 * (B_STEP >> 4));
+#pragma unroll
+                        for (int ky = 0; ky < 7; ++ky)
+                            tc05::mma_bf16(d_tmem, (ky % 3 == 0 ? ad_c0 : ad_c12) + so + (uint64_t)(a_off(ky) >> 4),
+                                           bb + (uint64_t)(ky * (B_STEP >> 4)), idesc, (ci | ky) > 0);
+                        tc05::mma_commit(slot_empty + slot);
+                        if (ci == 3) tc05::mma_commit(t_full + idx);
+                    }
+                    __syncwarp();
+                    if (ci == 3) use ^= 1u << idx;
+                } else if (lane == 0) {
+                    tc05::mbar_arrive(slot_empty + slot);   // nothing of this plane is ours: release our share of the slot
+                }
+            }
+            cnt += (uint32_t)S;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 4-11): two groups take alternate sample tiles
+        const int eg = (warp - 4) >> 2;          // group
+        const int ew = warp & 3;                 // TMEM lane quadrant of this warp
+        const int te = (warp - 4 - 4 * eg) * 32 + lane;   // 0..127 inside the group
+        const int r = ew * 32 + lane;            // accumulator row
+        float* S_ = reinterpret_cast<float*>(smem + OFF_S + eg * S_BYTES);
+        __nv_bfloat16* P_ = reinterpret_cast<__nv_bfloat16*>(smem + OFF_P + eg * P_BYTES);
+        const float* bias_s = reinterpret_cast<const float*>(smem + OFF_BIAS);
+        TileIter it(B, smax);
+        int ty, b0, S;
+        uint32_t use = 0, cnt = 0;
+        bool ok = true;
+        while (ok && it.next(ty, b0, S)) {
+            for (int s = 0; ok && s < S; ++s, ++cnt) {
+                const uint32_t idx = cnt & 7;
+                const uint32_t par = (use >> idx) & 1;
+                use ^= 1u << idx;
+                if ((int)(cnt & 1) != eg) continue;
+                ok = tc05::mbar_wait(t_full + idx, par, err);
+                if (!ok) break;
+                tc05::tc_fence_after();
+                float v[64];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + idx * 64 + c0, v + c0);
+                tc05::tmem_ld_wait();
+                tc05::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(t_empty + idx);   // accumulator drained
+                if (r < MROWS) {
+                    float4* dst = reinterpret_cast<float4*>(S_ + r * S_PITCH);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int b = b0 + s;
+                // pass A: one work item = (pooled row, 4 channels, column); lanes run along the column so the f32 NCHW
+                // activation and the argmax leave as 28-element runs; 9 LDS.128 feed 4 outputs
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int o = te + 128 * i;                     // 2 pooled rows x 4 channel quads x 28 columns = 224 items
+                    if (o < 224) {
+                        const int px = o % 28, cq = (o / 28) & 3, pyl = o / 112;
+                        const float* s0 = S_ + (3 * pyl) * NG * S_PITCH + 4 * cq;
+                        float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const int ox = 3 * px + dx;
+                                const float4 vv = *reinterpret_cast<const float4*>(s0 + dy * NG * S_PITCH + (ox >> 2) * S_PITCH + (ox & 3) * 16);
+                                if (dy == 0 && dx == 0) { best = vv; continue; }
+                                // strict: first maximum wins (torch's max_pool2d routing)
+                                if (vv.x > best.x) { best.x = vv.x; bi[0] = dy * 3 + dx; }
+                                if (vv.y > best.y) { best.y = vv.y; bi[1] = dy * 3 + dx; }
+                                if (vv.z > best.z) { best.z = vv.z; bi[2] = dy * 3 + dx; }
+                                if (vv.w > best.w) { best.w = vv.w; bi[3] = dy * 3 + dx; }
+                            }
+                        const float bv[4] = {best.x, best.y, best.z, best.w};
+                        float outv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int co = 4 * cq + q;
+                            const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
+                            outv[q] = fmaxf(bv[q] + bias_s[co], 0.f);
+                            y[g] = outv[q];
+                            amax[g] = (uint8_t)bi[q];
+                        }
+                        __nv_bfloat162 p01 = __floats2bfloat162_rn(outv[0], outv[1]), p23 = __floats2bfloat162_rn(outv[2], outv[3]);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&p01); pk.y = *reinterpret_cast<uint32_t*>(&p23);
+                        *reinterpret_cast<uint2*>(P_ + (pyl * 28 + px) * 16 + 4 * cq) = pk;   // NHWC bf16 tile, stored in pass B
+                    }
+                }
+                if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+                // pass B: the tile's NHWC bf16 copy for the tensor-core conv2 is one contiguous 1792 B block
+                if (ybf && te < 112)
+                    reinterpret_cast<uint4*>(ybf + (((size_t)b * 28 + 2 * ty) * 28) * 16)[te] = reinterpret_cast<const uint4*>(P_)[te];
+                // S_ and P_ are rewritten only after the next tile's first barrier, which every thread reaches after this store
+            }
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace c1tp
+
+namespace c1tc {
+
 // ================================================================================================
 // conv1 wgrad on tcgen05 (bf16 mode). Same Toeplitz view as the forward, transposed:
 //   dWt[(ci,ky,p)][(j,co)] = sum_{rows r=(oy,g)}  in[ci][3oy+ky][12g+p] * dY[r][(j,co)]        (GEMM, K = rows)
@@ -517,7 +771,30 @@ extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
 
 extern "C" size_t bc_packed_weight_bytes(void) { return bc_conv_tc_pack_total(); }
 
+static int conv1_tp_launch(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05, TP): null buffer (w_packed, err_flag, act, amax)");
+    BC_CHECK_ARG(c->obs_size == 4, "conv1 (tcgen05, TP): obs_size 4 only");
+    BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
+                 "conv1 (tcgen05, TP): x_tp, its strides and w_packed must be 16 B aligned");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(c1tp::conv1_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tp::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05, TP): smem opt-in %d B failed: %s", c1tp::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
+    const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
+    int grid = bc::num_sms();
+    if (grid > ntiles) grid = ntiles;
+    c1tp::conv1_tp_kernel<<<grid, c1tp::NTHREADS, c1tp::SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
+        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
+    return BC_OK;
+}
+
 int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
+    if (c->x_tp) return conv1_tp_launch(c, stream);
     BC_CHECK_ARG(c->x && c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05): null buffer (x, w_packed, err_flag, act, amax)");
     BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 (tcgen05): needs bf16 gray planes and obs_size 4");
     BC_CHECK_ARG(((uintptr_t)c->x % 16 == 0) && (c->x_stride_n * 2) % 16 == 0 && (c->x_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),

@@ -240,8 +240,9 @@ extern "C" int bc_conv_relu_pool_fwd(const bc_ctx* c, int layer, void* stream) {
     if ((c->conv_mode & 1) && layer >= 1 && c->act_bf16[layer - 1]) return bc_conv_tc_launch(c, layer, stream);
     switch (layer) {
     case 0: {
-        BC_CHECK_ARG(c->x, "bc_conv_relu_pool_fwd: x is null");
-        if ((c->conv_mode & 1) && c->x_dtype == BC_BF16 && c->obs_size == 4) return bc_conv1_tc_launch(c, stream);
+        BC_CHECK_ARG(c->x || c->x_tp, "bc_conv_relu_pool_fwd: x is null");
+        if ((c->conv_mode & 1) && (c->x_tp || c->x_dtype == BC_BF16) && c->obs_size == 4) return bc_conv1_tc_launch(c, stream);
+        BC_CHECK_ARG(c->x, "bc_conv_relu_pool_fwd: the exact-f32 conv1 reads plain planes (x), only x_tp was given");
         const int esz = c->x_dtype == BC_F32 ? 4 : 2;
         BC_CHECK_ARG(c->x_dtype == BC_F32 || c->x_dtype == BC_BF16, "bad x_dtype %d", c->x_dtype);
         BC_CHECK_ARG(((uintptr_t)c->x % 16 == 0) && (c->x_stride_n * esz) % 16 == 0 && (c->x_stride_c * esz) % 16 == 0,

@@ -68,7 +68,99 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
     }
 }
 
+// ---- "Toeplitz-ready" (TP) bf16 planes: the layout conv1's tcgen05 kernels consume without any repack.
+// conv1 is a 7x7 stride-3 convolution evaluated as D[(oy,g),(j,co)] = sum A[(oy,g),(ci,ky,p)] * Wt (conv1_tc.cu):
+// row (oy,g) of the A operand for kernel row ky is the 16-pixel segment [12g, 12g+16) of image row 3*oy+ky.
+// A plane is therefore stored as  TP[c = R%3][h = half of the segment][q = R/3][g = 0..20][8 px]  (R = image
+// row): for a fixed (c,h) consecutive (q,g) are 16 B apart, which IS the UMMA no-swizzle canonical layout
+// (8 rows x 16 B core matrices, SBO 128 B; the two K halves of a row are one piece stride apart = LBO), both
+// K-major (forward) and MN-major (wgrad). 1.32x the bytes of the plain plane (segments overlap by 4 px);
+// rows R = 256, 257 (q = 85 of classes 1, 2) are zero.
+constexpr int TP_NG = 21, TP_NQ = 86;
+
+template <typename LOADER>
+__device__ __forceinline__ void tp_write(LOADER&& load16, __nv_bfloat16* __restrict__ out, int64_t u) {
+    const int g = (int)(u % TP_NG), q = (int)((u / TP_NG) % TP_NQ), c = (int)((u / (TP_NG * TP_NQ)) % 3);
+    const int64_t plane = u / (TP_NG * TP_NQ * 3);
+    const int R = 3 * q + c;
+    uint32_t pk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (R < BC_H) load16(plane, R, 12 * g, pk);
+    __nv_bfloat16* dst = out + plane * BC_TP_PLANE_ELEMS + ((int64_t)(c * 2) * TP_NQ + q) * (TP_NG * 8) + g * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(dst + TP_NQ * TP_NG * 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out, int64_t n_units) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride)
+        tp_write([&](int64_t plane, int R, int px0, uint32_t (&pk)[8]) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + ((plane * BC_H + R) * BC_W + px0) * 3);
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) w[i] = __ldg(src + i);
+            float v[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                uint32_t ch[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int byte = 3 * p + k;
+                    ch[k] = (w[byte >> 2] >> (8 * (byte & 3))) & 0xffu;
+                }
+                v[p] = gray_px(ch[0], ch[1], ch[2]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        }, out, u);
+}
+
+// plain planes (f32 or bf16, rows contiguous, `plane_stride` elements apart) -> TP planes
+template <typename TIN>
+__global__ void __launch_bounds__(256) planes_to_tp_kernel(const TIN* __restrict__ in, int64_t plane_stride, __nv_bfloat16* __restrict__ out, int64_t n_units) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride)
+        tp_write([&](int64_t plane, int R, int px0, uint32_t (&pk)[8]) {
+            const TIN* src = in + plane * plane_stride + R * BC_W + px0;
+            if constexpr (sizeof(TIN) == 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(src) + i);
+                    pk[2 * i] = pack_bf16(f.x, f.y); pk[2 * i + 1] = pack_bf16(f.z, f.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(src) + i);
+                    pk[2 * i] = w.x; pk[2 * i + 1] = w.y;
+                }
+            }
+        }, out, u);
+}
+
 }  // namespace
+
+extern "C" int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream) {
+    BC_CHECK_ARG(planes && out_tp && n_planes >= 0, "bc_planes_to_tp: null pointer");
+    BC_CHECK_ARG(in_dtype == BC_F32 || in_dtype == BC_BF16, "bc_planes_to_tp: planes are f32 or bf16, got dtype %d", in_dtype);
+    const int esz = in_dtype == BC_F32 ? 4 : 2;
+    BC_CHECK_ARG((uintptr_t)planes % 16 == 0 && (plane_stride * esz) % 16 == 0 && (uintptr_t)out_tp % 16 == 0, "bc_planes_to_tp: 16 B alignment");
+    if (n_planes == 0) return BC_OK;
+    const int64_t units = n_planes * 3 * TP_NQ * TP_NG;
+    int64_t blocks = (units + 255) / 256;
+    const int64_t cap = (int64_t)bc::num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (in_dtype == BC_F32)
+        planes_to_tp_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)planes, plane_stride, (__nv_bfloat16*)out_tp, units);
+    else
+        planes_to_tp_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)planes, plane_stride, (__nv_bfloat16*)out_tp, units);
+    BC_CUDA_LAUNCH_CHECK("planes_to_tp_kernel");
+    return BC_OK;
+}
 
 extern "C" int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
     BC_CHECK_ARG(in && out && n >= 0 && n % 4 == 0, "bc_cast_bf16: null pointer or n %% 4 != 0");
@@ -87,11 +179,16 @@ extern "C" int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, i
     BC_CHECK_ARG(rgb && gray, "bc_stage_gray: null pointer");
     BC_CHECK_ARG(n_pixels >= 0 && n_pixels % 8 == 0, "bc_stage_gray: n_pixels=%lld must be a multiple of 8", (long long)n_pixels);
     BC_CHECK_ARG(((uintptr_t)rgb % 4 == 0) && ((uintptr_t)gray % 16 == 0), "bc_stage_gray: rgb must be 4 B and gray 16 B aligned");
-    BC_CHECK_ARG(out_dtype == BC_F32 || out_dtype == BC_BF16, "bc_stage_gray: bad dtype %d", out_dtype);
+    BC_CHECK_ARG(out_dtype == BC_F32 || out_dtype == BC_BF16 || out_dtype == BC_BF16_TP, "bc_stage_gray: bad dtype %d", out_dtype);
     if (n_pixels == 0) return BC_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int sms = bc::num_sms();
-    if (out_dtype == BC_F32) {
+    if (out_dtype == BC_BF16_TP) {
+        BC_CHECK_ARG(n_pixels % (BC_H * BC_W) == 0, "bc_stage_gray: the TP layout is defined for whole 256x256 frames");
+        const int64_t units = n_pixels / (BC_H * BC_W) * 3 * TP_NQ * TP_NG;
+        int blocks = (int)((units + 255) / 256 < (int64_t)sms * 16 ? (units + 255) / 256 : (int64_t)sms * 16);
+        stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, units);
+    } else if (out_dtype == BC_F32) {
         int64_t groups = n_pixels / 4;
         int blocks = (int)((groups + 255) / 256 < (int64_t)sms * 16 ? (groups + 255) / 256 : (int64_t)sms * 16);
         stage_gray_kernel<4, float><<<blocks, 256, 0, s>>>(rgb, (float*)gray, groups);

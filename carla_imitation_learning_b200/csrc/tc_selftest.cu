@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const __nv_bfloat
 // mode 3+: full producer/consumer ring with NS = mode-2 stages: warp 1+st "refills" stage st (waits the
 //          stage's empty barrier, fence.proxy.async, arrives on its full barrier), the MMA thread waits full,
 //          issues, commits to empty -- the synchronisation skeleton of the conv kernels without any data movement.
-__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, long long* cycles, int* err) {
+__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, int M, long long* cycles, int* err) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar, full[14], empty[14];
     __shared__ uint32_t tmem_base_s;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
     const uint32_t tmem_base = tmem_base_s;
     if (warp == 0) {
         // whole warp runs the loop, one elected lane issues (the pattern of the conv kernels)
-        const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, (uint32_t)N, 0, 0);
+        const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, (uint32_t)M, (uint32_t)N, 0, 0);
         const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, 256, tc05::SW_NONE);
         const long long t0 = clock64();
@@ -149,11 +149,13 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
 }  // namespace
 
 extern "C" int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream) {
+    const int M = (mode & (1 << 20)) ? 64 : 128;          // bit 20: M=64 instructions
+    mode &= ~(1 << 20);
     const int threads = (mode >> 8) ? (mode >> 8) : 512;   // bits 8.. of mode: CTA size override
     mode &= 0xff;
     BC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && cycles2 && err_flag, "bc_tc_mma_bench: bad arguments");
     const int smem = 8 * 4096 + 8192;
-    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, cycles2, err_flag);
+    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, M, cycles2, err_flag);
     BC_CUDA_LAUNCH_CHECK("tc_mma_bench_kernel");
     return BC_OK;
 }

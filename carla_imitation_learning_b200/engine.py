@@ -75,6 +75,8 @@ class StepBuffers:
     gact: List[torch.Tensor] = field(default_factory=list)
     act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: NHWC copies feeding the next layer's MMA
     dy_bf16: Optional[torch.Tensor] = None                       # bf16 mode: un-pooled conv-output gradient scratch
+    x_tp: Optional[torch.Tensor] = None                          # bf16 mode: the input as Toeplitz-ready planes
+    x_tp_strides: tuple = (0, 0)                                 # (sample, channel) element strides into x_tp
 
 
 class BCEngine:
@@ -112,6 +114,8 @@ class BCEngine:
             amax=[e(batch, *s, dt=torch.uint8) for s in ACT_SHAPES],
             hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
             dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
+        if (self.conv_mode & 1) and self.obs_size == 4 and batch:
+            bufs.x_tp, bufs.x_tp_strides = self.to_tp(x)
         if self.conv_mode & 1:
             bufs.act_bf16 = [torch.empty((batch, s[1], s[2], s[0]), dtype=torch.bfloat16, device=dev) for s in ACT_SHAPES[:3]]
         if backward:
@@ -132,6 +136,21 @@ class BCEngine:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         _lib.check(self.lib.bc_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream_ptr()), "bc_cast_bf16")
         return out
+
+    def to_tp(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """(B,4,256,256) f32/bf16 batch -> Toeplitz-ready bf16 planes (include/bc_b200.h BC_BF16_TP) + strides.
+        A sliding-window view (sliding_window()) is converted once per PLANE, not per sample."""
+        B = x.shape[0]
+        P = H * W
+        sliding = x.stride(0) == P and x.stride(1) == P
+        if not sliding and not (x.stride(1) == P and x.stride(0) == self.obs_size * P):
+            x = x.contiguous()
+        n_planes = B + self.obs_size - 1 if sliding else B * self.obs_size
+        tp = out if out is not None else torch.empty((n_planes, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=x.device)
+        code = _lib.BC_F32 if x.dtype == torch.float32 else _lib.BC_BF16
+        _lib.check(self.lib.bc_planes_to_tp(x.data_ptr(), code, n_planes, P, tp.data_ptr(), _stream_ptr()), "bc_planes_to_tp")
+        e = _lib.TP_PLANE_ELEMS
+        return tp, ((e, e) if sliding else (self.obs_size * e, e))
 
     def check_input(self, x: torch.Tensor) -> torch.Tensor:
         _require_cuda(x, "x")
@@ -170,6 +189,8 @@ class BCEngine:
             c.act_bf16[i] = b.act_bf16[i].data_ptr() if b.act_bf16 else None
         c.dy_bf16 = b.dy_bf16.data_ptr() if b.dy_bf16 is not None else None
         c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
+        if b.x_tp is not None:
+            c.x_tp, (c.x_tp_stride_n, c.x_tp_stride_c) = b.x_tp.data_ptr(), b.x_tp_strides
         return c
 
     def set_mode(self, mode: str) -> None:

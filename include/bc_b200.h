@@ -30,7 +30,11 @@ typedef enum {
     BC_ERR_UNSUPPORTED = -3
 } bc_status;
 
-typedef enum { BC_F32 = 0, BC_BF16 = 1 } bc_dtype;
+/* BC_BF16_TP: bf16 gray planes in the "Toeplitz-ready" layout conv1's tcgen05 kernels consume without a repack:
+ * plane[c = R%3][h][q = R/3][g = 0..20][8 px] holds pixels [12g + 8h, 12g + 8h + 8) of image row R (zero for R >= 256);
+ * BC_TP_PLANE_ELEMS bf16 per 256x256 plane (1.32x the plain plane: the 16-pixel segments overlap by 4). */
+typedef enum { BC_F32 = 0, BC_BF16 = 1, BC_BF16_TP = 2 } bc_dtype;
+#define BC_TP_PLANE_ELEMS 86688   /* 3 classes x 2 halves x 86 rows x 21 groups x 8 px */
 
 /* Geometry of ConvNet1 (src/architectures/nets.py:17-33) for 256x256 inputs. */
 #define BC_H 256
@@ -74,6 +78,11 @@ typedef struct {
                                 written by the conv epilogues, read by the next layer's tcgen05 gather   */
     void* dy_bf16;           /* bf16 mode: scratch for the un-pooled conv-output gradient, NHWC bf16,
                                 batch*24*24*32 elements (the largest layer); one layer at a time          */
+    const void* x_tp;        /* bf16 mode: the input as BC_BF16_TP planes (bc_stage_gray / bc_planes_to_tp); sample n,
+                                channel c is the plane at x_tp + n*x_tp_stride_n + c*x_tp_stride_c (elements).
+                                stride_n == stride_c is the sliding window: consecutive samples share 3 of 4 planes
+                                and conv1 then loads every plane once for 4 samples                              */
+    int64_t x_tp_stride_n, x_tp_stride_c;
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);
@@ -83,6 +92,10 @@ size_t bc_partials_floats(int obs_size, int n_actions);
  * numpy, rounded to f32 (or bf16). A sample is 4 consecutive planes, so the sliding window
  * of the reference's shuffle=False loader is the strided view x_stride_n = H*W, x_stride_c = H*W. */
 int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream);
+
+/* plain planes (f32 or bf16; 256x256, rows contiguous, `plane_stride` elements apart) -> BC_BF16_TP planes:
+ * how a reference-style (B,4,256,256) batch enters the tcgen05 conv1 (bf16 mode) */
+int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream);
 
 /* bf16 mode fed with f32 samples (the reference's batch format): contiguous f32 -> bf16 cast, n % 4 == 0 */
 int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream);

@@ -122,6 +122,30 @@ def golden_curve_ensemble(B, steps, data_seed, path, members=8):
                         losses=np.asarray(curves, np.float64))
 
 
+def golden_resume_state(B, at_step, data_seed, path):
+    """Parameters and Adam state of the canonical reference run (golden_curve) after `at_step` steps, i.e. past the
+    ln 9 plateau. The plateau exit is a saddle escape whose timing amplifies bf16-sized (4e-3) gradient rounding into
+    +-100 steps or no exit at all (measured on the unmodified reference with that noise injected), so
+    the bf16 mode's 1k-step curve is compared from this common state, where the dynamics are contractive again."""
+    net, model = build_ref()
+    opt = model.configure_optimizers()[0][0]
+    frames, labels = O.synth_frames(data_seed, 1000 * B + 4)
+    gray = torch.from_numpy(O.gray_stack(frames[:at_step * B + 4]))
+    lab = torch.from_numpy(labels)
+    for s in range(at_step):
+        x = torch.stack([gray[s * B + i: s * B + i + 4] for i in range(B)])
+        loss = model.training_step((x, lab[s * B + 4: s * B + 4 + B]), s)
+        opt.zero_grad(); loss.backward(); opt.step()
+    named = dict(net.named_parameters())
+    st = opt.state
+    np.savez_compressed(
+        path, B=B, at_step=at_step, data_seed=data_seed, params=flat(named),
+        exp_avg=np.concatenate([st[named[k]]["exp_avg"].reshape(-1).numpy() for k in O.PARAM_ORDER]),
+        exp_avg_sq=np.concatenate([st[named[k]]["exp_avg_sq"].reshape(-1).numpy() for k in O.PARAM_ORDER]),
+        last_loss=float(loss.detach()))
+    print(path, "loss at resume", float(loss.detach()))
+
+
 def golden_labels(path):
     # pandas 3 (this image) returns read-only `.values` under copy-on-write, which the
     # reference's in-place writes (imitation_dataset.py:322-324) predate; feed it a
@@ -167,6 +191,8 @@ if __name__ == "__main__":
     golden_labels(os.path.join(g, "ref_labels.npz"))
     golden_gray(os.path.join(g, "ref_gray.npz"))
     golden_curve(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k.npz"))
+    if "--resume-state" in sys.argv:
+        golden_resume_state(8, 200, 11, os.path.join(g, "ref_state_b8_step200.npz"))
     if "--ensemble" in sys.argv:
         golden_curve_ensemble(8, 1000, 11, os.path.join(g, "ref_curve_b8_1k_ensemble.npz"))
     if "--f64-curve" in sys.argv:

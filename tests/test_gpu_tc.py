@@ -310,3 +310,65 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
             ed = float((got_d - ref_d).abs().max() / ref_d.abs().max())
             assert ed <= 2e-5, (layer, "dgrad", ed)
     eng.check_device_errors()
+
+
+def _tp_reference(planes):
+    """(n,256,256) -> (n, 3, 2, 86, 21, 8): TP[c][h][q][g][i] = plane[3q+c][12g+8h+i], zero rows beyond 255
+    (the layout include/bc_b200.h documents for BC_BF16_TP)."""
+    n = planes.shape[0]
+    pad = torch.zeros((n, 258, 256), dtype=planes.dtype, device=planes.device)
+    pad[:, :256] = planes
+    R = (3 * torch.arange(86)[None, :] + torch.arange(3)[:, None]).to(planes.device)                     # (3,86)
+    px = (12 * torch.arange(21)[None, :, None] + 8 * torch.arange(2)[:, None, None] + torch.arange(8)[None, None, :]).to(planes.device)  # (2,21,8)
+    return pad[:, R[:, None, :, None, None], px[None, :, None, :, :]]
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_toeplitz_ready_planes_are_a_pure_rearrangement(n):
+    """bc_planes_to_tp (f32 and bf16 input) and bc_stage_gray(..., BC_BF16_TP) == the plain bf16 planes re-indexed."""
+    from carla_imitation_learning_b200 import _lib, stage_gray
+    from oracle import bc_oracle as O
+    dev = torch.device("cuda", 0)
+    frames, _ = O.synth_frames(90 + n, n)
+    fr = torch.from_numpy(frames).to(dev)
+    plain16 = stage_gray(fr, dtype=torch.bfloat16)
+    plain32 = stage_gray(fr)
+    ref = _tp_reference(plain16).reshape(n, -1)
+    assert ref.shape[1] == _lib.TP_PLANE_ELEMS
+    s = torch.cuda.current_stream().cuda_stream
+    for src, code in ((plain16, _lib.BC_BF16), (plain32, _lib.BC_F32)):
+        out = torch.full((n, _lib.TP_PLANE_ELEMS), float("nan"), dtype=torch.bfloat16, device=dev)
+        _lib.check(_lib.lib().bc_planes_to_tp(src.data_ptr(), code, n, 65536, out.data_ptr(), s), "bc_planes_to_tp")
+        assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+    out = torch.full((n, _lib.TP_PLANE_ELEMS), float("nan"), dtype=torch.bfloat16, device=dev)
+    _lib.check(_lib.lib().bc_stage_gray(fr.data_ptr(), out.data_ptr(), n * 65536, _lib.BC_BF16_TP, s), "bc_stage_gray TP")
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 37])
+def test_conv1_tcgen05_materialised_batch_equals_sliding_view(B):
+    """The plane-sharing path (sliding view: one load feeds 4 samples) and the per-sample path (contiguous batch)
+    of conv1_tp_kernel produce identical bits, for batch sizes that leave partial sample groups."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib, stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    eng.set_mode("bf16")
+    eng.pack_weights()
+    frames, _ = O.synth_frames(150 + B, B + 4)
+    x = sliding_window(stage_gray(torch.from_numpy(frames).to(dev), dtype=torch.bfloat16))[:B]
+    outs = []
+    for xx in (x, x.contiguous()):
+        bufs = eng.alloc(B, xx, None, False)
+        assert (bufs.x_tp_strides[0] == bufs.x_tp_strides[1]) == (xx is x)
+        c = eng.ctx(bufs)
+        _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, torch.cuda.current_stream().cuda_stream), "conv1 tc")
+        torch.cuda.synchronize()
+        outs.append((bufs.act[0].clone(), bufs.amax[0].clone(), bufs.act_bf16[0].clone()))
+    eng.check_device_errors()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

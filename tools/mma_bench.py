@@ -21,3 +21,5 @@ for N in (16, 64, 128, 256):
     print(f"N {N:3d} unrolled x8 groups, one commit   : issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1))
 for th in (512, 64, 128, 256, 512):
     print(f"N  64 back-to-back, CTA of {th:3d} threads: issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, (th << 8) | 0))
+for N in (32, 64, 128):
+    print(f"M=64 N {N:3d} unrolled x8 groups, one commit: issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1 | (1 << 20)))
