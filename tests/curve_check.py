@@ -14,7 +14,13 @@ The device curve is therefore held to:
       widened by `tol` + the ensemble's own leave-one-out excess;
   (4) plateau exit (first step whose 20-step running mean is < 2.0) within `exit_slack` steps of the ensemble's;
   (5) the last 250 steps' mean inside the ensemble's range widened by `tol`.
-`tol` is the north star's 1 % (fp32 mode) / 2 % (bf16 mode)."""
+`tol` is the north star's 1 % (fp32 mode) / 2 % (bf16 mode).
+
+bf16 mode: the saddle escape amplifies bf16-sized rounding (4e-3 relative on the gradients) into +-100 steps of exit
+time, or no exit within 1000 steps -- measured on the UNMODIFIED reference with that noise injected into its f32
+gradients (2 of 6 runs never left the plateau). So the bf16 curve is checked (a) per step on the
+plateau from the common initial state and (b) for steps 200..999 from the reference's own parameters and Adam state
+at step 200, where the dynamics are contractive again and "the curves agree within 2 %" is a meaningful statement."""
 import os
 
 import numpy as np
@@ -25,12 +31,14 @@ def _exit_step(curve):
     return int(np.argmax(m < 2.0))
 
 
-def check_curve(got, golden_dir, tol, exit_slack=25):
+def check_curve(got, golden_dir, tol, exit_slack=25, start=0):
+    """`got` = losses of steps [start, 1000). start > 0 is a run resumed from the reference's own state at that step
+    (tests/golden/ref_state_b8_step200.npz): checks (2) and (4), which are about the plateau, do not apply to it."""
     ref = np.load(os.path.join(golden_dir, "ref_curve_b8_1k.npz"))["losses"]
     ens = np.load(os.path.join(golden_dir, "ref_curve_b8_1k_ensemble.npz"))["losses"]
     members = np.vstack([ens, ref[None]])                      # 9 runs of the unmodified reference
-    means = members.mean(1)
-    assert means.min() - tol * ref.mean() <= got.mean() <= means.max() + tol * ref.mean(), (got.mean(), means)
+    assert start % 50 == 0 and len(got) == 1000 - start
+    got = np.concatenate([np.full(start, np.nan), got])
     w = members.reshape(len(members), -1, 50).mean(2)
     excess = 0.0                                               # how far a member falls outside the OTHER members' envelope
     for m in range(len(w)):
@@ -39,7 +47,13 @@ def check_curve(got, golden_dir, tol, exit_slack=25):
     gw = got.reshape(-1, 50).mean(1)
     out = np.maximum(w.min(0) - gw, gw - w.max(0)).clip(0) / gw
     assert out[6:].max() <= tol + excess, (float(out[6:].max()), excess, int(out[6:].argmax()) + 6)
-    exits = [_exit_step(c) for c in members]
-    assert min(exits) - exit_slack <= _exit_step(got) <= max(exits) + exit_slack, (_exit_step(got), exits)
-    tails = members[:, 750:].mean(1)
-    assert tails.min() * (1 - tol) <= got[750:].mean() <= tails.max() * (1 + tol), (got[750:].mean(), tails)
+    for lo_step in (750, 300):                                 # (5) and the whole post-plateau part
+        stat = np.sort(members[:, lo_step:].mean(1))
+        loo = max(stat[1] / stat[0], stat[-1] / stat[-2]) - 1.0   # leave-one-out excess of this statistic
+        g = got[lo_step:].mean()
+        assert stat[0] * (1 - tol - loo) <= g <= stat[-1] * (1 + tol + loo), (lo_step, g, stat, loo)
+    if start == 0:
+        means = members.mean(1)
+        assert means.min() - tol * ref.mean() <= got.mean() <= means.max() + tol * ref.mean(), (got.mean(), means)
+        exits = [_exit_step(c) for c in members]
+        assert min(exits) - exit_slack <= _exit_step(got) <= max(exits) + exit_slack, (_exit_step(got), exits)
