@@ -148,7 +148,7 @@ def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from carla_imitation_learning_b200 import FusedAdam, sliding_window, stage_gray
+    from carla_imitation_learning_b200 import FusedAdam, sliding_window, stage_frames, stage_gray
     from carla_imitation_learning_b200 import _lib
     from src.architectures.nets import ConvNet1
 
@@ -182,10 +182,19 @@ def run_b200(args):
         hl = torch.from_numpy(l[4:4 + B].copy()).pin_memory()
         host_frames.append(hf); host_labels.append(hl)
         dev_frames.append(hf.to(dev)); dev_labels.append(hl.to(dev))
-    gray = torch.empty((B + 4, 256, 256), dtype=staged_dtype, device=dev)
     if args.mode == "bf16":
         eng.set_mode("bf16")           # before alloc(): bf16 mode adds the NHWC bf16 activation copies
-    bufs = eng.alloc(B, sliding_window(gray), dev_labels[0], True)
+        staged = stage_frames(dev_frames[0])          # Toeplitz-ready + plain bf16 planes, rewritten in place every step
+        bufs = eng.alloc(B, staged, dev_labels[0], True)
+
+        def stage(frames_u8):
+            stage_frames(frames_u8, out=staged)
+    else:
+        gray = torch.empty((B + 4, 256, 256), dtype=staged_dtype, device=dev)
+        bufs = eng.alloc(B, sliding_window(gray), dev_labels[0], True)
+
+        def stage(frames_u8):
+            stage_gray(frames_u8, out=gray)
 
     from carla_imitation_learning_b200.parallel import DataParallelStep
     dp = DataParallelStep(eng, opt) if world > 1 else None   # 2-bucket exchange overlapped with conv1 wgrad
@@ -198,9 +207,7 @@ def run_b200(args):
             opt.step_flat(eng.grads)
 
     def device_step(i):
-        stage_gray(dev_frames[i % NBUF], out=gray)
-        if bufs.x_tp is not None:
-            eng.to_tp(bufs.x, out=bufs.x_tp)
+        stage(dev_frames[i % NBUF])
         if args.mode == "bf16":
             eng.pack_weights()                 # f32 master weights -> bf16 MMA operand images
         bufs.y = dev_labels[i % NBUF]
@@ -227,9 +234,7 @@ def run_b200(args):
                 graphs.append(g)
             else:
                 def pre(i=i):
-                    stage_gray(dev_frames[i % NBUF], out=gray)
-                    if bufs.x_tp is not None:
-                        eng.to_tp(bufs.x, out=bufs.x_tp)
+                    stage(dev_frames[i % NBUF])
                     if args.mode == "bf16":
                         eng.pack_weights()
                     bufs.y = dev_labels[i % NBUF]
@@ -286,9 +291,7 @@ def run_b200(args):
             up_done[i & 1].record(copy_stream)
 
     def slot_step(k):
-        stage_gray(slots[k][0], out=gray)
-        if bufs.x_tp is not None:
-            eng.to_tp(bufs.x, out=bufs.x_tp)
+        stage(slots[k][0])
         if args.mode == "bf16":
             eng.pack_weights()
         bufs.y = slots[k][1]
@@ -334,9 +337,8 @@ def run_b200(args):
     cref = C.byref(c)
     s = torch.cuda.current_stream().cuda_stream
     L = eng.lib
-    ops = [("stage_gray", lambda: stage_gray(dev_frames[0], out=gray))]
+    ops = [("stage_gray", lambda: stage(dev_frames[0]))]
     if args.mode == "bf16":
-        ops.append(("planes_to_tp", lambda: eng.to_tp(bufs.x, out=bufs.x_tp)))
         ops.append(("pack_weights", eng.pack_weights))
     ops += [(f"conv{l + 1}_fwd", (lambda l=l: _lib.check(L.bc_conv_relu_pool_fwd(cref, l, s)))) for l in range(4)]
     ops.append(("head_fwd_ce_bwd", lambda: _lib.check(L.bc_head(cref, 3, s))))
@@ -358,7 +360,8 @@ def run_b200(args):
         breakdown[name] = round(k0.elapsed_time(k1) / 10 * 1e3, 1)
     k_ms = breakdown["conv1_fwd"] * 1e-3
     stage_ms = breakdown["stage_gray"] * 1e-3
-    stage_bytes = (B + 4) * (FRAME_BYTES + 65536 * (2 if staged_dtype == torch.bfloat16 else 4))
+    # algorithmic bytes of the staging kernel: u8 RGB in; gray planes out (bf16 mode: Toeplitz-ready + plain bf16 planes)
+    stage_bytes = (B + 4) * (FRAME_BYTES + (2 * _lib.TP_PLANE_ELEMS + 2 * 65536 if args.mode == "bf16" else 65536 * 4))
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -380,8 +383,9 @@ def run_b200(args):
                        "final_loss": loss_dev},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (B + 4) * FRAME_BYTES + 8 * B, "d2h_bytes_per_step": 4},
-            "gpu_launches": (17 if args.mode == "bf16" else 16) * args.steps,
-            "roofline": {"kernel": ("conv1_tc_kernel (tcgen05 Toeplitz implicit GEMM, bf16)" if args.mode == "bf16"
+            # per step: stage, [pack], 4 conv fwd, head, 3 x ([unpool,] wgrad, dgrad), conv1 wgrad, reduce, adam tick, adam
+            "gpu_launches": (20 if args.mode == "bf16" else 16) * args.steps,
+            "roofline": {"kernel": ("conv1_tp_kernel (tcgen05 Toeplitz implicit GEMM on Toeplitz-ready planes, bf16)" if args.mode == "bf16"
                                     else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_burst"],
@@ -389,7 +393,7 @@ def run_b200(args):
                          "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
                          "kernel_ms": k_ms, "flops_per_launch": FLOPS_FWD[0] * B,
                          "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
-            "roofline_hbm": {"kernel": "stage_gray_kernel", "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
+            "roofline_hbm": {"kernel": ("stage_gray_tp_kernel" if args.mode == "bf16" else "stage_gray_kernel"), "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": stage_bytes / (stage_ms * 1e-3) / 1e9 / peaks["hbm"],
                              "bytes_per_launch": stage_bytes, "kernel_ms": stage_ms},
             "breakdown_us": breakdown,

@@ -53,17 +53,7 @@ constexpr int TMEM_COLS = 128;
 //   byte(r, k) = (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2          => LBO = 128 B, SBO = 256 B
 __host__ __device__ constexpr int op_off(int r, int chunk) { return (r >> 3) * 256 + chunk * 128 + (r & 7) * 16; }
 
-// fp32 OIHW conv1 weights -> Toeplitz bf16 operand, already in the smem image the MMA reads:
-// step s=(ci,ky): 64 rows n=(j*16+co) x 16 k
-__global__ void pack_conv1_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NSTEP * 64 * 16) return;
-    const int k = i & 15, n = (i >> 4) & 63, s = i >> 10;
-    const int ci = s / 7, ky = s % 7, j = n >> 4, co = n & 15;
-    const int kx = k - 3 * j;
-    const float v = (kx >= 0 && kx < 7) ? w[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
-    out[(size_t)s * (B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
-}
+// The Toeplitz bf16 weight operand (step s=(ci,ky): 64 rows n=(j*16+co) x 16 k) is written by pack_all_kernel (conv_tc.cu).
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
@@ -763,10 +753,7 @@ extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c && c->params && c->w_packed, "bc_pack_weights: null buffer");
     BC_CHECK_ARG(c->obs_size == 4, "bc_pack_weights: the tcgen05 conv1 operand exists for obs_size 4 only");
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
-    c1tc::pack_conv1_weights_kernel<<<(c1tc::NSTEP * 1024 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        c->params + a.w[0], (__nv_bfloat16*)c->w_packed);
-    BC_CUDA_LAUNCH_CHECK("pack_conv1_weights_kernel");
-    return bc_conv_tc_pack(c, stream);     // conv2-4 operand images follow conv1's inside w_packed
+    return bc_conv_tc_pack(c, stream);     // one launch: conv1's Toeplitz image, then conv2-4's forward and dgrad images
 }
 
 extern "C" size_t bc_packed_weight_bytes(void) { return bc_conv_tc_pack_total(); }

@@ -37,14 +37,7 @@ struct Cfg {
     static constexpr int WPF = HP * HP;                    // pool windows per frame
 };
 
-// f32 OIHW -> bf16 operand image: step s = (tap, cb): COUT rows x 16 k (k = ci within the block)
-template <typename C>
-__device__ __forceinline__ void pack_fwd_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int i) {
-    const int k = i & 15, n = (i >> 4) % C::COUT, s = i / (16 * C::COUT);
-    const int tap = s / C::CB, cb = s % C::CB;
-    const float v = w[((size_t)n * C::CIN + cb * 16 + k) * (C::KS * C::KS) + tap];
-    out[(size_t)s * (C::B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
-}
+// Weight operand images (pack_all_kernel, below): forward step s = (tap, ci/16): COUT rows x 16 k (k = ci%16).
 
 // ------------------------------------------------------------------------------------------------
 // One persistent warp-specialised implicit-GEMM kernel for forward and dgrad. A policy P supplies
@@ -332,15 +325,7 @@ struct DCfg {
     static constexpr int PPF = HOUT * HOUT;                // output pixels per frame
 };
 
-// B operand of dgrad: step s = (tap, cb): N = C_in rows x 16 k (k = co within the block)
-template <typename C>
-__device__ __forceinline__ void pack_dgrad_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int i) {
-    using D = DCfg<C>;
-    const int k = i & 15, n = (i >> 4) % D::N, s = i / (16 * D::N);
-    const int tap = s / D::CB, cb = s % D::CB;
-    const float v = w[((size_t)(cb * 16 + k) * C::CIN + n) * (C::KS * C::KS) + tap];
-    out[(size_t)s * (D::B_STEP / 2) + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
-}
+// B operand of dgrad: step s = (tap, co/16): N = C_in rows x 16 k (k = co%16); written by pack_all_kernel.
 
 // ---- dgrad policy ---------------------------------------------------------------------------------
 template <typename C, int G_, int NSTAGE_>
@@ -645,25 +630,50 @@ int bc_unpool_launch(const bc_ctx* c, int layer, void* stream) {
 }
 
 namespace ctc {
-struct PackArgs { const float* w2; const float* w3; const float* w4; uint8_t* base; };
-constexpr int kNF2 = L2::NSTEP * L2::COUT * 16, kNF3 = L3::NSTEP * L3::COUT * 16, kNF4 = L4::NSTEP * L4::COUT * 16;
-constexpr int kND2 = DCfg<L2>::NSTEP * DCfg<L2>::N * 16, kND3 = DCfg<L3>::NSTEP * DCfg<L3>::N * 16, kND4 = DCfg<L4>::NSTEP * DCfg<L4>::N * 16;
-constexpr int kPackElems = kNF2 + kNF3 + kNF4 + kND2 + kND3 + kND4;
-// all six conv2-4 operand images (forward + dgrad) in one launch
+struct PackArgs { const float* w1; const float* w2; const float* w3; const float* w4; uint8_t* base; };
+
+// One source weight W[co][ci][tap] of conv2-4 -> its position in the forward image and in the dgrad image.
+// Threads walk the f32 weights in memory order (coalesced reads); the two bf16 writes are scattered but nothing waits on them.
+template <typename C>
+__device__ __forceinline__ void pack_src_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgr, int i) {
+    using D = DCfg<C>;
+    constexpr int KK = C::KS * C::KS;
+    const int tap = i % KK, ci = (i / KK) % C::CIN, co = i / (KK * C::CIN);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    {   // forward: step (tap, ci/16), row co, k = ci%16
+        const int sidx = tap * C::CB + (ci >> 4), k = ci & 15;
+        fwd[(size_t)sidx * (C::B_STEP / 2) + op_off(co, k >> 3) / 2 + (k & 7)] = v;
+    }
+    {   // dgrad: step (tap, co/16), row ci, k = co%16
+        const int sidx = tap * D::CB + (co >> 4), k = co & 15;
+        dgr[(size_t)sidx * (D::B_STEP / 2) + op_off(ci, k >> 3) / 2 + (k & 7)] = v;
+    }
+}
+constexpr int kNW2 = L2::COUT * L2::CIN * L2::KS * L2::KS, kNW3 = L3::COUT * L3::CIN * L3::KS * L3::KS, kNW4 = L4::COUT * L4::CIN * L4::KS * L4::KS;
+constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz image, element-ordered (it has structural zeros)
+constexpr int kPackElems = kNC1 + kNW2 + kNW3 + kNW4;
+// all seven operand images (conv1 Toeplitz, conv2-4 forward + dgrad) in one launch
 __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < kNF2) { pack_fwd_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + o2), i); return; } i -= kNF2;
-    if (i < kNF3) { pack_fwd_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + o3), i); return; } i -= kNF3;
-    if (i < kNF4) { pack_fwd_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + o4), i); return; } i -= kNF4;
-    if (i < kND2) { pack_dgrad_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + d2), i); return; } i -= kND2;
-    if (i < kND3) { pack_dgrad_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + d3), i); return; } i -= kND3;
-    if (i < kND4) pack_dgrad_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + d4), i);
+    if (i < kNC1) {
+        // step s = (ci,ky): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu)
+        const int k = i & 15, n = (i >> 4) & 63, st = i >> 10;
+        const int ci = st / 7, ky = st % 7, j = n >> 4, co = n & 15;
+        const int kx = k - 3 * j;
+        const float v = (kx >= 0 && kx < 7) ? a.w1[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
+        reinterpret_cast<__nv_bfloat16*>(a.base)[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
+        return;
+    }
+    i -= kNC1;
+    if (i < kNW2) { pack_src_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + o2), (__nv_bfloat16*)(a.base + d2), i); return; } i -= kNW2;
+    if (i < kNW3) { pack_src_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + o3), (__nv_bfloat16*)(a.base + d3), i); return; } i -= kNW3;
+    if (i < kNW4) pack_src_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + o4), (__nv_bfloat16*)(a.base + d4), i);
 }
 }  // namespace ctc
 
 int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
-    ctc::PackArgs pa{c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed};
+    ctc::PackArgs pa{c->params + a.w[0], c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed};
     ctc::pack_all_kernel<<<(ctc::kPackElems + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
     BC_CUDA_LAUNCH_CHECK("pack_all_kernel");
     return BC_OK;

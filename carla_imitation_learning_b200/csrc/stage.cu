@@ -95,7 +95,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out, int64_t n_units) {
+// `plain` (optional): the same frames also as plain (n,256,256) bf16 planes; unit (R,g) owns pixels [12g, 12g+12) (g = 20: 16)
+__global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ plain, int64_t n_units) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride)
         tp_write([&](int64_t plane, int R, int px0, uint32_t (&pk)[8]) {
@@ -116,6 +118,11 @@ __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __res
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            if (plain) {
+                uint2* dst = reinterpret_cast<uint2*>(plain + (plane * BC_H + R) * BC_W + px0);
+                dst[0] = make_uint2(pk[0], pk[1]); dst[1] = make_uint2(pk[2], pk[3]); dst[2] = make_uint2(pk[4], pk[5]);
+                if (px0 == 240) dst[3] = make_uint2(pk[6], pk[7]);
+            }
         }, out, u);
 }
 
@@ -162,6 +169,18 @@ extern "C" int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_plane
     return BC_OK;
 }
 
+extern "C" int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, int64_t n_frames, void* stream) {
+    BC_CHECK_ARG(rgb && tp && n_frames >= 0, "bc_stage_gray_tp: null pointer");
+    BC_CHECK_ARG(((uintptr_t)rgb % 4 == 0) && ((uintptr_t)tp % 16 == 0) && ((uintptr_t)plain_bf16 % 8 == 0), "bc_stage_gray_tp: alignment");
+    if (n_frames == 0) return BC_OK;
+    const int64_t units = n_frames * 3 * TP_NQ * TP_NG;
+    const int64_t cap = (int64_t)bc::num_sms() * 16;
+    const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
+    stage_gray_tp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
+    BC_CUDA_LAUNCH_CHECK("stage_gray_tp_kernel");
+    return BC_OK;
+}
+
 extern "C" int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
     BC_CHECK_ARG(in && out && n >= 0 && n % 4 == 0, "bc_cast_bf16: null pointer or n %% 4 != 0");
     BC_CHECK_ARG((uintptr_t)in % 16 == 0 && (uintptr_t)out % 8 == 0, "bc_cast_bf16: alignment");
@@ -187,7 +206,7 @@ extern "C" int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, i
         BC_CHECK_ARG(n_pixels % (BC_H * BC_W) == 0, "bc_stage_gray: the TP layout is defined for whole 256x256 frames");
         const int64_t units = n_pixels / (BC_H * BC_W) * 3 * TP_NQ * TP_NG;
         int blocks = (int)((units + 255) / 256 < (int64_t)sms * 16 ? (units + 255) / 256 : (int64_t)sms * 16);
-        stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, units);
+        stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, nullptr, units);
     } else if (out_dtype == BC_F32) {
         int64_t groups = n_pixels / 4;
         int blocks = (int)((groups + 255) / 256 < (int64_t)sms * 16 ? (groups + 255) / 256 : (int64_t)sms * 16);

@@ -58,6 +58,49 @@ def sliding_window(gray: torch.Tensor, frame_skip: int = 4) -> torch.Tensor:
     return gray.as_strided((n - frame_skip, frame_skip, h, w), (h * w, h * w, w, 1))
 
 
+class StagedBatch:
+    """bf16-mode input produced by stage_frames(): n staged frames = n - frame_skip samples, in the two layouts the
+    tcgen05 kernels read -- `tp` (n, TP_PLANE_ELEMS) Toeplitz-ready planes for conv1 forward and `plain` (n,256,256)
+    bf16 planes for conv1 wgrad -- both written by ONE pass of the staging kernel over the u8 frames."""
+
+    def __init__(self, tp: torch.Tensor, plain: torch.Tensor, frame_skip: int = 4):
+        self.tp, self.plain, self.frame_skip = tp, plain, frame_skip
+
+    @property
+    def x(self) -> torch.Tensor:
+        return sliding_window(self.plain, self.frame_skip)
+
+    @property
+    def shape(self):
+        return (self.plain.shape[0] - self.frame_skip, self.frame_skip, H, W)
+
+    @property
+    def device(self):
+        return self.tp.device
+
+    def to(self, *_a, **_k):
+        return self
+
+
+def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, frame_skip: int = 4) -> StagedBatch:
+    """(n,256,256,3) u8 RGB on the device -> StagedBatch. The bf16-mode replacement of SequentialTorchDataset's
+    per-sample numpy work (imitation_dataset.py:115-133): gray conversion, /255, 4-frame stacking (as a view) and
+    the MMA operand layout of conv1 in one fused kernel."""
+    _require_cuda(frames_u8, "frames")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or tuple(frames_u8.shape[1:]) != (H, W, 3) or not frames_u8.is_contiguous():
+        raise ValueError("frames must be a contiguous (n,256,256,3) uint8 tensor")
+    n = frames_u8.shape[0]
+    if n <= frame_skip:
+        raise ValueError(f"need more than {frame_skip} frames, got {n}")
+    if out is None:
+        out = StagedBatch(torch.empty((n, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=frames_u8.device),
+                          torch.empty((n, H, W), dtype=torch.bfloat16, device=frames_u8.device), frame_skip)
+    elif out.tp.shape[0] != n:
+        raise ValueError("out was staged for a different number of frames")
+    _lib.check(_lib.lib().bc_stage_gray_tp(frames_u8.data_ptr(), out.tp.data_ptr(), out.plain.data_ptr(), n, _stream_ptr()), "bc_stage_gray_tp")
+    return out
+
+
 @dataclass
 class StepBuffers:
     """Everything one forward produces and one backward consumes."""
@@ -105,8 +148,11 @@ class BCEngine:
         self.conv_mode = 0            # bit mask, see bc_ctx.conv_mode: 0 = exact f32 FFMA kernels, 15 = all tcgen05 kernels
 
     # ------------------------------------------------------------------ buffers
-    def alloc(self, batch: int, x: torch.Tensor, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
+    def alloc(self, batch: int, x, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
         dev, f32 = self.device, torch.float32
+        staged = x if isinstance(x, StagedBatch) else None
+        if staged is not None:
+            x = staged.x
         e = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=dev)
         bufs = StepBuffers(
             batch=batch, x=x, y=y,
@@ -114,7 +160,9 @@ class BCEngine:
             amax=[e(batch, *s, dt=torch.uint8) for s in ACT_SHAPES],
             hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
             dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
-        if (self.conv_mode & 1) and self.obs_size == 4 and batch:
+        if staged is not None:
+            bufs.x_tp, bufs.x_tp_strides = staged.tp, (_lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
+        elif (self.conv_mode & 1) and self.obs_size == 4 and batch:
             bufs.x_tp, bufs.x_tp_strides = self.to_tp(x)
         if self.conv_mode & 1:
             bufs.act_bf16 = [torch.empty((batch, s[1], s[2], s[0]), dtype=torch.bfloat16, device=dev) for s in ACT_SHAPES[:3]]
@@ -152,7 +200,13 @@ class BCEngine:
         e = _lib.TP_PLANE_ELEMS
         return tp, ((e, e) if sliding else (self.obs_size * e, e))
 
-    def check_input(self, x: torch.Tensor) -> torch.Tensor:
+    def check_input(self, x):
+        if isinstance(x, StagedBatch):
+            if not (self.conv_mode & 1) or self.obs_size != 4:
+                raise ValueError("a StagedBatch feeds the bf16 tensor-core mode (precision='bf16', obs_size 4)")
+            if x.device != self.device:
+                raise RuntimeError(f"x is on {x.device}, parameters on {self.device}")
+            return x
         _require_cuda(x, "x")
         if x.device != self.device:
             raise RuntimeError(f"x is on {x.device}, parameters on {self.device}")

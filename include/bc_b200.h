@@ -93,6 +93,10 @@ size_t bc_partials_floats(int obs_size, int n_actions);
  * of the reference's shuffle=False loader is the strided view x_stride_n = H*W, x_stride_c = H*W. */
 int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtype, void* stream);
 
+/* The staging kernel of bf16 mode: rgb (n,256,256,3) u8 -> BC_BF16_TP planes (n * BC_TP_PLANE_ELEMS bf16), and, when
+ * plain_bf16 is not NULL, the same gray values also as plain (n,256,256) bf16 planes, in one pass over the frames. */
+int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, int64_t n_frames, void* stream);
+
 /* plain planes (f32 or bf16; 256x256, rows contiguous, `plane_stride` elements apart) -> BC_BF16_TP planes:
  * how a reference-style (B,4,256,256) batch enters the tcgen05 conv1 (bf16 mode) */
 int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream);

@@ -399,3 +399,34 @@ def test_conv1_tcgen05_materialised_batch_equals_sliding_view(B):
     eng.check_device_errors()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_stage_frames_feeds_both_layouts_and_matches_the_plain_path():
+    """stage_frames (one fused pass: u8 -> Toeplitz-ready + plain bf16) == stage_gray + bc_planes_to_tp, and a training
+    step driven by the StagedBatch is bitwise the step driven by the plain sliding view."""
+    from carla_imitation_learning_b200 import stage_frames, stage_gray, sliding_window
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    B = 9
+    frames, labels = O.synth_frames(321, B + 4)
+    fr = torch.from_numpy(frames).to(dev)
+    y = torch.from_numpy(labels[4:4 + B]).to(dev)
+    sb = stage_frames(fr)
+    plain = stage_gray(fr, dtype=torch.bfloat16)
+    assert torch.equal(sb.plain.view(torch.int16), plain.view(torch.int16))
+    assert torch.equal(sb.tp.view(torch.int16), _tp_reference(plain).reshape(B + 4, -1).view(torch.int16))
+    assert tuple(sb.shape) == (B, 4, 256, 256)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
+    eng = net.engine()
+    b1 = eng.train_forward_backward(sb, y)
+    g1, l1 = eng.grads.clone(), b1.loss.clone()
+    b2 = eng.train_forward_backward(sliding_window(plain), y)
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    assert torch.equal(l1, b2.loss) and torch.equal(g1, eng.grads)
+    # the module shells take it too
+    assert torch.equal(net(sb), b2.logits)
+    with pytest.raises(ValueError):
+        ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev).engine().forward(sb)      # fp32 mode reads plain f32/bf16 planes
