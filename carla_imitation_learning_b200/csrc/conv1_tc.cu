@@ -342,28 +342,29 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ loader (one lane): 6 bulk copies per plane
-        if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, B_BYTES);
-            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+        // ------------------------------------------------------------------ loader: 6 bulk copies per plane, one per lane
+        {
+            if (lane == 0) {
+                tc05::mbar_expect_tx(b_full, B_BYTES);
+                tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+            }
             TileIter it(B, smax);
             int ty, b0, S;
             uint32_t k = 0;
             bool ok = true;
+            const int c = lane >> 1, h = lane & 1;               // lanes 0..5
+            const int src_off = lane < 6 ? (c * 2 + h) * TP_PIECE_BYTES : 0, dst_off = lane < 6 ? piece_off(c, h) : 0;
+            const uint32_t nbytes = c == 0 ? PIECE0 : PIECE12;
             while (ok && it.next(ty, b0, S)) {
                 const uint8_t* src0 = reinterpret_cast<const uint8_t*>(x + (int64_t)b0 * sn) + (size_t)(6 * ty) * ROWB;
                 for (int j = 0; j < S + 3; ++j, ++k) {
                     const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
                     ok = tc05::mbar_wait(slot_empty + slot, ph ^ 1, err);
                     if (!ok) break;
-                    tc05::mbar_expect_tx(slot_full + slot, SLOT_BYTES);
-                    const uint8_t* src = src0 + (int64_t)j * sc * 2;
-                    uint8_t* dst = smem + OFF_RING + slot * SLOT_BYTES;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            tc05::bulk_g2s(dst + piece_off(c, h), src + (c * 2 + h) * TP_PIECE_BYTES, c == 0 ? PIECE0 : PIECE12, slot_full + slot);
+                    if (lane == 0) tc05::mbar_expect_tx(slot_full + slot, SLOT_BYTES);
+                    __syncwarp();
+                    if (lane < 6)
+                        tc05::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES + dst_off, src0 + (int64_t)j * sc * 2 + src_off, nbytes, slot_full + slot);
                 }
             }
         }
@@ -749,6 +750,257 @@ conv1_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
 
 }  // namespace c1tc
 
+
+// ================================================================================================
+// conv1 wgrad, second generation: Toeplitz-ready planes in, no repack, every plane loaded once.
+//   dWt[ci][(ky,p)][(j,co)] = sum_b sum_{r=(oy,g)} plane(b+ci)[3oy+ky][12g+p] * dY(b)[r][(j,co)]
+// is regrouped BY PLANE: plane P meets dY(P), dY(P-1), dY(P-2), dY(P-3) as channel ci = 0..3 (sliding window), so one
+// "job" = (tile row ty, plane P) loads P's tile once and runs 4 accumulation groups, one per ci, each into its own
+// accumulator D[ci] (4 x 64 TMEM columns, resident for the whole kernel).
+//   A operand (MN-major, M = (ky,p) = 7 x 16 rows + one all-ones block whose row is the bias gradient): 14 bulk
+//     copies lay the slices (ky,h) = rows d..d+5 of TP piece (c,h) at a uniform 2016 B stride, which is exactly the
+//     SBO of an MN-major no-swizzle operand; K = the 126 rows (oy,g), 16 B apart (LBO 128 B per 8 rows).
+//   B operand (MN-major, N = (j,co) = 64): dY(b), built once per sample tile from (gact0, act1, amax1) into a ring
+//     of 5 slots: 4 live + 1 being built.
+//   4 MMA issuers, issuer ci owns D[ci] (a queued tcgen05.mma pins its uniform registers, see the forward kernel).
+//   A materialised batch (sn != sc) runs the same pipeline with jobs (b, ci): 4x the loads, same result.
+namespace c1wg2 {
+using c1tc::MROWS; using c1tc::NG; using c1tc::TILES_PER_FRAME;
+constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, 1-3 and 8 issuers, 4-7 / 9-12 dY builder groups (4-7 also epilogue)
+constexpr int ROWB = 336;
+constexpr int VIEW = 6 * ROWB;               // 2016: one (ky,h) slice = 126 rows x 16 B
+constexpr int A_SLOT = 16 * VIEW;            // 14 slices + 2 all-ones blocks
+constexpr int NA = 4;
+constexpr int DY_BYTES = 64 * 256;           // [8 n-blocks][128 rows][16 B]
+constexpr int NDY = 5;
+constexpr int TP_PIECE_BYTES = 86 * ROWB;
+constexpr int OFF_A = 0;
+constexpr int OFF_DY = (OFF_A + NA * A_SLOT + 64 + 1023) / 1024 * 1024;
+constexpr int OFF_BAR = OFF_DY + NDY * DY_BYTES;
+constexpr int NBAR = 2 * NA + 2 * NDY + 1;
+constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 32;   // + TMEM address and the 4 'accumulator written' flags
+constexpr int TMEM_COLS = 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "conv1 wgrad (TP) shared memory");
+
+// One CTA owns a contiguous range of the job list i = ty * NJ + P; a "segment" is the part of it inside one tile row.
+struct Seg { int ty, Pa, Pb, sa, sb; };
+struct SegIter {
+    int i, hi, NJ, B; bool sliding;
+    __device__ SegIter(int B_, bool sliding_) : B(B_), sliding(sliding_) {
+        NJ = sliding_ ? B_ + 3 : 4 * B_;
+        const long long T = (long long)NJ * TILES_PER_FRAME;
+        i = (int)(T * blockIdx.x / gridDim.x);
+        hi = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    }
+    __device__ bool next(Seg& s) {
+        if (i >= hi) return false;
+        s.ty = i / NJ; s.Pa = i - s.ty * NJ;
+        const int n = min(hi - i, NJ - s.Pa);
+        s.Pb = s.Pa + n - 1;
+        if (sliding) { s.sa = max(0, s.Pa - 3); s.sb = min(B - 1, s.Pb); }
+        else { s.sa = s.Pa >> 2; s.sb = s.Pb >> 2; }
+        i += n;
+        return true;
+    }
+    __device__ int job_of(int smp, int ci) const { return sliding ? smp + ci : 4 * smp + ci; }
+    __device__ int sample_of(int P, int ci) const {
+        const int sm = sliding ? P - ci : ((P & 3) == ci ? (P >> 2) : -1);
+        return (sm >= 0 && sm < B) ? sm : -1;
+    }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
+                      const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
+                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* a_full = bars;                  // [NA]
+    uint64_t* a_empty = bars + NA;            // [NA]   4 issuers
+    uint64_t* dy_full = bars + 2 * NA;        // [NDY]  4 builder warps
+    uint64_t* dy_empty = bars + 2 * NA + NDY; // [NDY]  4 issuers
+    uint64_t* done = bars + 2 * NA + 2 * NDY; //        4 issuers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool sliding = sn == sc;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NA; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 4); }
+        for (int i = 0; i < NDY; ++i) { tc05::mbar_init(dy_full + i, 4); tc05::mbar_init(dy_empty + i, 4); }
+        tc05::mbar_init(done, 4);
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
+    // A slots start as zeros (the K rows 126,127 of a slice read 32 B of its neighbour: never a NaN pattern) with
+    // the two trailing blocks of every slot set to bf16 ones (accumulator rows 112.. = sum_r dY = the bias gradient)
+    for (int i = threadIdx.x; i < (NA * A_SLOT + 64) / 16; i += NTHREADS) {
+        const int within = (i * 16) % A_SLOT;
+        const uint32_t v = (i * 16 < NA * A_SLOT && within >= 14 * VIEW) ? 0x3f803f80u : 0u;
+        reinterpret_cast<uint4*>(smem + OFF_A)[i] = make_uint4(v, v, v, v);
+    }
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader: 14 bulk copies per job, one per lane
+        {
+            SegIter it(B, sliding);
+            Seg sg;
+            uint32_t k = 0;
+            bool ok = true;
+            const int ky = lane >> 1, h = lane & 1;
+            const int src_off = ((ky % 3) * 2 + h) * TP_PIECE_BYTES + (ky / 3) * ROWB, dst_off = (ky * 2 + h) * VIEW;
+            while (ok && it.next(sg)) {
+                for (int P = sg.Pa; P <= sg.Pb; ++P, ++k) {
+                    const uint32_t slot = k % NA, ph = (k / NA) & 1;
+                    ok = tc05::mbar_wait(a_empty + slot, ph ^ 1, err);
+                    if (!ok) break;
+                    const int64_t pl = sliding ? (int64_t)P * sc : (int64_t)(P >> 2) * sn + (int64_t)(P & 3) * sc;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(x + pl) + (size_t)(6 * sg.ty) * ROWB;
+                    uint8_t* dst = smem + OFF_A + slot * A_SLOT;
+                    if (lane == 0) tc05::mbar_expect_tx(a_full + slot, 14 * VIEW);
+                    __syncwarp();
+                    if (lane < 14) tc05::bulk_g2s(dst + dst_off, src + src_off, VIEW, a_full + slot);
+                }
+            }
+        }
+    } else if (warp <= 3 || warp == 8) {
+        // ------------------------------------------------------------------ issuer ci: D[ci] += A(job)^T dY(sample)
+        const int ci = warp == 8 ? 0 : warp;
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 1, 1);      // MN-major A and B
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_A), 128, VIEW, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_DY), 128, 2048, tc05::SW_NONE);
+        const uint32_t d_tmem = tmem_base + ci * 64;
+        SegIter it(B, sliding);
+        Seg sg;
+        uint32_t k = 0, kb0 = 0;               // job counter, build counter at the start of the segment
+        bool ok = true, first = true;
+        auto orphan = [&](int smp) {           // a sample this issuer never multiplies inside this segment
+            const uint32_t kb = kb0 + (uint32_t)(smp - sg.sa), slot = kb % NDY;
+            ok = ok && tc05::mbar_wait(dy_full + slot, (kb / NDY) & 1, err);
+            if (ok && lane == 0) tc05::mbar_arrive(dy_empty + slot);
+            __syncwarp();
+        };
+        while (ok && it.next(sg)) {
+            for (int smp = sg.sa; ok && smp <= sg.sb && it.job_of(smp, ci) < sg.Pa; ++smp) orphan(smp);
+            for (int P = sg.Pa; ok && P <= sg.Pb; ++P, ++k) {
+                const uint32_t slot = k % NA, ph = (k / NA) & 1;
+                ok = tc05::mbar_wait(a_full + slot, ph, err);
+                const int smp = it.sample_of(P, ci);
+                if (smp >= sg.sa && smp <= sg.sb) {
+                    const uint32_t kb = kb0 + (uint32_t)(smp - sg.sa), dslot = kb % NDY;
+                    ok = ok && tc05::mbar_wait(dy_full + dslot, (kb / NDY) & 1, err);
+                    tc05::tc_fence_after();
+                    if (ok && tc05::elect_one()) {
+                        const uint64_t a_st = ad0 + (uint64_t)((slot * A_SLOT) >> 4);
+                        const uint64_t b_st = bd0 + (uint64_t)((dslot * DY_BYTES) >> 4);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            tc05::mma_bf16(d_tmem, a_st + (uint64_t)(u * 16), b_st + (uint64_t)(u * 16), idesc, (first && u == 0) ? 0u : 1u);
+                        tc05::mma_commit(a_empty + slot);
+                        tc05::mma_commit(dy_empty + dslot);
+                    }
+                    __syncwarp();
+                    first = false;
+                } else if (lane == 0) {
+                    tc05::mbar_arrive(a_empty + slot);
+                }
+            }
+            for (int smp = sg.sa; ok && smp <= sg.sb; ++smp)
+                if (it.job_of(smp, ci) > sg.Pb) orphan(smp);
+            kb0 += (uint32_t)(sg.sb - sg.sa + 1);
+        }
+        // tell the epilogue whether D[ci] was ever written (an issuer with no valid pair leaves garbage in TMEM)
+        if (lane == 0) reinterpret_cast<volatile uint32_t*>(tmem_slot)[1 + ci] = first ? 0u : 1u;
+        __threadfence_block();
+        __syncwarp();
+        if (tc05::elect_one()) tc05::mma_commit(done);
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ two dY builder groups (alternate samples), then the folding epilogue
+        const int grp = warp >= 9 ? 1 : 0;
+        const int ew = warp - 4;
+        const int te = threadIdx.x - (grp ? 288 : 128);
+        SegIter it(B, sliding);
+        Seg sg;
+        uint32_t kb = 0;
+        bool ok = true;
+        while (ok && it.next(sg)) {
+            for (int smp = sg.sa; ok && smp <= sg.sb; ++smp, ++kb) {
+                if ((int)(kb & 1) != grp) continue;
+                const uint32_t slot = kb % NDY;
+                ok = tc05::mbar_wait(dy_empty + slot, ((kb / NDY) & 1) ^ 1, err);
+                if (!ok) break;
+                uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
+#pragma unroll
+                for (int q = 0; q < DY_BYTES / 16 / 128; ++q) reinterpret_cast<uint4*>(dy)[te + 128 * q] = make_uint4(0, 0, 0, 0);
+                if (grp) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    const int o = te + 128 * q;                      // 2 pooled rows x 16 channels x 28 columns
+                    const int px = o % 28, co = (o / 28) & 15, pyl = o / 448;
+                    const size_t g = (((size_t)smp * 16 + co) * 28 + 2 * sg.ty + pyl) * 28 + px;
+                    const float gv = aP[g] > 0.f ? gP[g] : 0.f;
+                    const int pos = amax[g];
+                    const int oyl = 3 * pyl + pos / 3, ox = 3 * px + pos % 3;
+                    const int r = oyl * NG + (ox >> 2), n = (ox & 3) * 16 + co;
+                    *reinterpret_cast<__nv_bfloat16*>(dy + (n >> 3) * 2048 + r * 16 + (n & 7) * 2) = __float2bfloat16_rn(gv);
+                }
+                tc05::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(dy_full + slot);
+            }
+        }
+        // ---- epilogue (warps 4-7): fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
+        if (grp) goto fin;
+        float* dst = part + (size_t)blockIdx.x * seg_len;
+        if ((int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
+            for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
+                for (int i = te; i < 3136 + 16; i += 128) part[(size_t)s2 * seg_len + (i < 3136 ? w_off + i : b_off + i - 3136)] = 0.f;
+        }
+        if (ok && tc05::mbar_wait(done, 0, err)) {
+            tc05::tc_fence_after();
+            const int ky = 2 * ew + (lane >> 4), p = lane & 15;     // accumulator row m = ky*16 + p
+            const bool wrow = ky < 7 && p < 7;                      // this lane writes tap kx = p
+#pragma unroll 1
+            for (int ci = 0; ci < 4; ++ci) {
+                float v[64];
+                if (reinterpret_cast<volatile uint32_t*>(tmem_slot)[1 + ci]) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + ci * 64 + c0, v + c0);
+                    tc05::tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) v[c] = 0.f;
+                }
+                const bool brow = ci == 0 && ky == 7 && p == 0;     // ones block: bias gradient (every sample is ci = 0 of exactly one job)
+#pragma unroll
+                for (int co = 0; co < 16; ++co) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // dW[.., kx] += dWt[p = 3j + kx][(j, co)]: fetch column j*16+co from the lane holding row 3j+kx
+                        const int srcl = (lane & 16) + ((3 * j + p) & 15);
+                        const float o = __shfl_sync(0xffffffffu, v[j * 16 + co], srcl);
+                        acc += brow ? v[j * 16 + co] : o;
+                    }
+                    if (wrow) dst[w_off + ((size_t)(co * 4 + ci) * 7 + ky) * 7 + p] = acc;
+                    else if (brow) dst[b_off + co] = acc;
+                }
+            }
+        }
+    }
+fin:
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace c1wg2
+
 extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c && c->params && c->w_packed, "bc_pack_weights: null buffer");
     BC_CHECK_ARG(c->obs_size == 4, "bc_pack_weights: the tcgen05 conv1 operand exists for obs_size 4 only");
@@ -803,7 +1055,34 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
     return BC_OK;
 }
 
+static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05, TP): null buffer");
+    BC_CHECK_ARG(c->obs_size == 4, "conv1 wgrad (tcgen05, TP): obs_size 4 only");
+    BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0,
+                 "conv1 wgrad (tcgen05, TP): x_tp and its strides must be 16 B aligned");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(c1wg2::conv1_wgrad_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1wg2::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05, TP): smem opt-in %d B failed: %s", c1wg2::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
+    const bc::Partials pl = bc::partials_layout(ar);
+    const int nparts = bc::kWgradParts[0];
+    const bool sliding = c->x_tp_stride_n == c->x_tp_stride_c;
+    const int njobs = (sliding ? c->batch + 3 : 4 * c->batch) * c1tc::TILES_PER_FRAME;
+    int grid = bc::num_sms();
+    if (grid > nparts) grid = nparts;
+    if (grid > njobs) grid = njobs;
+    c1wg2::conv1_wgrad_tp_kernel<<<grid, c1wg2::NTHREADS, c1wg2::SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
+        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], nparts, c->batch, c->err_flag);
+    BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
+    return BC_OK;
+}
+
 int bc_conv1_wgrad_tc_launch(const bc_ctx* c, void* stream) {
+    if (c->x_tp) return conv1_wgrad_tp_launch(c, stream);
     BC_CHECK_ARG(c->x && c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05): null buffer");
     BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 wgrad (tcgen05): needs bf16 gray planes and obs_size 4");
     static bool configured = false;

@@ -73,13 +73,13 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const __nv_bfloat
 // mode 3+: full producer/consumer ring with NS = mode-2 stages: warp 1+st "refills" stage st (waits the
 //          stage's empty barrier, fence.proxy.async, arrives on its full barrier), the MMA thread waits full,
 //          issues, commits to empty -- the synchronisation skeleton of the conv kernels without any data movement.
-__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, int M, long long* cycles, int* err) {
+__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, int M, int mn_major, long long* cycles, int* err) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar, full[14], empty[14];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NS = mode >= 3 ? mode - 2 : 0;
-    for (int i = threadIdx.x; i < (8 * 4096 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    for (int i = threadIdx.x; i < (8 * 4096 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         tc05::mbar_init(&bar, 1);
         for (int i = 0; i < 14; ++i) { tc05::mbar_init(full + i, 1); tc05::mbar_init(empty + i, 1); }
@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
     const uint32_t tmem_base = tmem_base_s;
     if (warp == 0) {
         // whole warp runs the loop, one elected lane issues (the pattern of the conv kernels)
-        const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, (uint32_t)M, (uint32_t)N, 0, 0);
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, 256, tc05::SW_NONE);
-        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, 256, tc05::SW_NONE);
+        // mn_major: both operands MN-major, [core along M/N at 2048 B][16 K rows x 16 B] (the wgrad kernels' layout)
+        const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, (uint32_t)M, (uint32_t)N, mn_major, mn_major);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, mn_major ? 2048 : 256, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, mn_major ? 2048 : 256, tc05::SW_NONE);
         const long long t0 = clock64();
         bool ok = true;
         uint32_t st = 0, ph = 0;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
                 if (tc05::elect_one()) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        tc05::mma_bf16(tmem_base, ad0 + (uint64_t)(u * 256), bd0 + (uint64_t)(u * 16), idesc, (i | u) > 0);
+                        tc05::mma_bf16(tmem_base, ad0 + (uint64_t)(mn_major ? u * 16 : u * 256), bd0 + (uint64_t)(u * 16), idesc, (i | u) > 0);
                 }
                 __syncwarp();
             }
@@ -150,12 +151,15 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
 
 extern "C" int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream) {
     const int M = (mode & (1 << 20)) ? 64 : 128;          // bit 20: M=64 instructions
-    mode &= ~(1 << 20);
+    const int mn_major = (mode >> 21) & 1;                // bit 21: MN-major operands
+    mode &= ~(3 << 20);
+    BC_CHECK_ARG(!mn_major || N <= 64, "bc_tc_mma_bench: the MN-major variant has room for N <= 64");
     const int threads = (mode >> 8) ? (mode >> 8) : 512;   // bits 8.. of mode: CTA size override
     mode &= 0xff;
     BC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && cycles2 && err_flag, "bc_tc_mma_bench: bad arguments");
-    const int smem = 8 * 4096 + 8192;
-    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, M, cycles2, err_flag);
+    const int smem = 8 * 4096 + 16384;
+    cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, M, mn_major, cycles2, err_flag);
     BC_CUDA_LAUNCH_CHECK("tc_mma_bench_kernel");
     return BC_OK;
 }

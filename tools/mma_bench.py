@@ -21,5 +21,7 @@ for N in (16, 64, 128, 256):
     print(f"N {N:3d} unrolled x8 groups, one commit   : issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1))
 for th in (512, 64, 128, 256, 512):
     print(f"N  64 back-to-back, CTA of {th:3d} threads: issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, (th << 8) | 0))
-for N in (32, 64, 128):
+for N in (32, 64):
     print(f"M=64 N {N:3d} unrolled x8 groups, one commit: issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1 | (1 << 20)))
+for N in (16, 32, 64):
+    print(f"MN-major M=128 N {N:3d} unrolled x8 groups: issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1 | (1 << 21)))
