@@ -184,7 +184,7 @@ def run_b200(args):
         dev_frames.append(hf.to(dev)); dev_labels.append(hl.to(dev))
     if args.mode == "bf16":
         eng.set_mode("bf16")           # before alloc(): bf16 mode adds the NHWC bf16 activation copies
-        staged = stage_frames(dev_frames[0])          # Toeplitz-ready + plain bf16 planes, rewritten in place every step
+        staged = stage_frames(dev_frames[0])          # Toeplitz-ready bf16 planes, rewritten in place every step
         bufs = eng.alloc(B, staged, dev_labels[0], True)
 
         def stage(frames_u8):
@@ -360,8 +360,8 @@ def run_b200(args):
         breakdown[name] = round(k0.elapsed_time(k1) / 10 * 1e3, 1)
     k_ms = breakdown["conv1_fwd"] * 1e-3
     stage_ms = breakdown["stage_gray"] * 1e-3
-    # algorithmic bytes of the staging kernel: u8 RGB in; gray planes out (bf16 mode: Toeplitz-ready + plain bf16 planes)
-    stage_bytes = (B + 4) * (FRAME_BYTES + (2 * _lib.TP_PLANE_ELEMS + 2 * 65536 if args.mode == "bf16" else 65536 * 4))
+    # algorithmic bytes of the staging kernel: u8 RGB in; gray planes out (bf16 mode: Toeplitz-ready bf16 planes)
+    stage_bytes = (B + 4) * (FRAME_BYTES + (2 * _lib.TP_PLANE_ELEMS if args.mode == "bf16" else 65536 * 4))
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

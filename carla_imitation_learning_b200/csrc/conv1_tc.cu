@@ -9,256 +9,33 @@
 // i.e. M = (conv row, group of 4 columns), N = 4*16 = 64, K = 28 steps of 16 pixels: 44 % of the
 // issued MACs are useful, but A traffic per output drops 4x and every MMA is M=128,N=64,K=16.
 //
-// Per CTA (persistent, one per SM), tile = 6 conv rows x 84 columns of one frame (= 2 pooled rows):
-//   warp 0      loader   : cp.async.bulk (TMA engine), one 11 KB copy per input plane (22 contiguous rows),
-//                          pipelined PER PLANE: plane ci of tile t+1 streams in while planes ci+1.. of tile t repack
-//   warp 1      MMA      : one thread issues 28 tcgen05.mma per tile (fully unrolled, static descriptors)
-//                          into one of two TMEM accumulators
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue : tcgen05.ld -> smem -> 3x3 max / first-max argmax / +bias / ReLU -> global
-//   warps 8-14  repack   : warp w = kernel row ky: raw rows -> 128x16 bf16 A chunk (UMMA K-major canonical layout)
-// mbarrier rings: plane full/empty (4), A-stage full/empty (14 stages), TMEM full/empty (2). All waits bounded.
+// The input arrives as "Toeplitz-ready" (TP) planes (stage.cu): the 16-pixel segments are stored so that the
+// A operand of every (ci, ky) K-step is a plain strided view of what a bulk copy lands in shared memory --
+// no repack warps, no LDS/STS between the copy engine and the tensor core. Two kernels below:
+// conv1_tp_kernel (forward + bias + ReLU + pool3 + argmax) and conv1_wgrad_tp_kernel (weight/bias gradient).
+// All mbarrier waits are bounded and raise a device flag instead of hanging.
 #include "bc_common.cuh"
 #include "tc05.cuh"
 
 namespace c1tc {
 
-constexpr int NREPACK = 7;               // repack warps: warp w owns kernel row ky = w
-constexpr int NTHREADS = (8 + NREPACK) * 32;   // 480
-constexpr int ROWS_IN = 22;              // input rows per tile: 3*(6-1)+7
 constexpr int NG = 21;                   // groups of 4 output columns per conv row
 constexpr int MROWS = 126;               // 6 conv rows x 21 groups (of the MMA's 128)
 constexpr int NSTEP = 28;                // K steps (ci, ky) of 16 pixels
-constexpr int NST = 7;                   // A stages: stage ky holds the TWO chunks (2cp, ky), (2cp+1, ky) of one fill
-constexpr int ROW_BYTES = 512;           // 256 px bf16
-constexpr int PLANE_BYTES = ROWS_IN * ROW_BYTES;         // 11264: the tile's rows of one input plane, contiguous in HBM
-constexpr int A_CHUNK = 128 * 32;                        // 4096: one K=16 slice of the 128-row A tile
-constexpr int A_STAGE = 2 * A_CHUNK;                     // 8192
-constexpr int B_STEP = 64 * 32;                          // 2048
+constexpr int B_STEP = 64 * 32;                          // 2048: one K-step of the Toeplitz weight operand
 constexpr int B_BYTES = NSTEP * B_STEP;                  // 57344
 constexpr int S_PITCH = 68;                              // floats; 4-bank skew per row => conflict-free STS.128
 constexpr int S_BYTES = MROWS * S_PITCH * 4;             // 34272
-constexpr int OFF_B = 0;
-constexpr int OFF_RAW = OFF_B + B_BYTES;                 // 4 plane buffers (pipelined per plane, not per tile)
-constexpr int OFF_A = OFF_RAW + 4 * PLANE_BYTES;
-constexpr int OFF_S = OFF_A + NST * A_STAGE;
-constexpr int OFF_BAR = (OFF_S + S_BYTES + 127) / 128 * 128;
-constexpr int NBAR = 1 + 4 + 4 + NST + NST + 2 + 2;
-constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
-constexpr int TILES_PER_FRAME = 14;
-constexpr int TMEM_COLS = 128;
+constexpr int TILES_PER_FRAME = 14;      // tile = 6 conv rows x 84 columns of one frame (= 2 pooled rows)
 
-// UMMA K-major no-swizzle canonical layout used for both operands: a K=16 slice of `rows` rows is
-// stored as 8-row groups of 256 B; inside a group the two 16-byte K-chunks are 128 B apart:
-//   byte(r, k) = (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2          => LBO = 128 B, SBO = 256 B
-__host__ __device__ constexpr int op_off(int r, int chunk) { return (r >> 3) * 256 + chunk * 128 + (r & 7) * 16; }
-
-// The Toeplitz bf16 weight operand (step s=(ci,ky): 64 rows n=(j*16+co) x 16 k) is written by pack_all_kernel (conv_tc.cu).
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv1_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
-                const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
-                __nv_bfloat16* __restrict__ ybf, int B, int* err) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* b_full = bars;
-    uint64_t* raw_full = bars + 1;                 // [4] one per input plane
-    uint64_t* raw_empty = bars + 5;                // [4]
-    uint64_t* a_full = bars + 9;                   // [NST]
-    uint64_t* a_empty = bars + 9 + NST;            // [NST]
-    uint64_t* t_full = bars + 9 + 2 * NST;         // [2]
-    uint64_t* t_empty = bars + 11 + 2 * NST;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = B * TILES_PER_FRAME;
-
-    if (threadIdx.x == 0) {
-        tc05::mbar_init(b_full, 1);
-        for (int i = 0; i < 4; ++i) { tc05::mbar_init(raw_full + i, 1); tc05::mbar_init(raw_empty + i, NREPACK); }
-        for (int i = 0; i < 2; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
-        for (int i = 0; i < NST; ++i) { tc05::mbar_init(a_full + i, 1); tc05::mbar_init(a_empty + i, 1); }
-        tc05::mbar_fence_init();
-    }
-    if (warp == 2) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
-    // rows 126,127 of every A stage are never produced: keep them zero
-    for (int i = threadIdx.x; i < NST * 2 * 2 * 2 * 4; i += NTHREADS) {
-        const int ch = i / 16, rem = i % 16, c = rem / 8, r = 126 + (rem % 8) / 4, q = rem % 4;   // ch = stage*2 + chunk
-        reinterpret_cast<uint32_t*>(smem + OFF_A + ch * A_CHUNK + op_off(r, c))[q] = 0u;
-    }
-    tc05::fence_async_smem();
-    tc05::tc_fence_before();
-    __syncthreads();
-    tc05::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ loader (one lane)
-        if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, B_BYTES);
-            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
-            int it = 0;
-            bool ok = true;
-            for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-                const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
-                const __nv_bfloat16* src = x + (size_t)b * sn + (size_t)(ty * 18) * 256;
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
-                    // plane buffer ci is free once all repack warps are past plane ci of the previous tile
-                    ok = ok && tc05::mbar_wait(raw_empty + ci, (it & 1) ^ 1, err);
-                    if (!ok) break;
-                    tc05::mbar_expect_tx(raw_full + ci, PLANE_BYTES);
-                    tc05::bulk_g2s(smem + OFF_RAW + ci * PLANE_BYTES, src + (size_t)ci * sc, PLANE_BYTES, raw_full + ci);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        // The whole warp runs the loop (so every operand stays in uniform registers); one elected lane
-        // issues. Per tile: 14 stage visits (cp-major, ky-minor), 2 MMAs + 1 commit each.
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_A), 128, 256, tc05::SW_NONE);
-        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_B), 128, 256, tc05::SW_NONE);
-        bool ok = tc05::mbar_wait(b_full, 0, err);
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const int acc = it & 1;
-            ok = tc05::mbar_wait(t_empty + acc, ((it >> 1) & 1) ^ 1, err);
-            tc05::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 64;
-#pragma unroll
-            for (int v = 0; v < 14; ++v) {
-                const int cp = v / 7, ky = v % 7;            // static after unrolling
-                if (ok) ok = tc05::mbar_wait(a_full + ky, (uint32_t)(it * 2 + cp) & 1, err);
-                tc05::tc_fence_after();
-                if (ok && tc05::elect_one()) {
-                    // descriptors differ from the base only in the 14-bit start-address field (>>4)
-                    const uint64_t a0 = ad0 + (uint64_t)(ky * (A_STAGE >> 4));
-                    tc05::mma_bf16(d_tmem, a0, bd0 + (uint64_t)(((2 * cp) * 7 + ky) * (B_STEP >> 4)), idesc, v > 0);
-                    tc05::mma_bf16(d_tmem, a0 + (A_CHUNK >> 4), bd0 + (uint64_t)(((2 * cp + 1) * 7 + ky) * (B_STEP >> 4)), idesc, 1);
-                    tc05::mma_commit(a_empty + ky);          // stage reusable once both MMAs have read it
-                    if (v == 13) tc05::mma_commit(t_full + acc);   // accumulator complete
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ epilogue
-        const int ew = warp - 4;                 // == warp % 4: TMEM lanes [32*ew, 32*ew+32)
-        const int te = threadIdx.x - 128;        // 0..127
-        const int r = ew * 32 + lane;            // accumulator row
-        float* S = reinterpret_cast<float*>(smem + OFF_S);
-        float breg[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) breg[i] = bias[(te + 128 * i) & 15];
-        int it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int acc = it & 1;
-            if (!tc05::mbar_wait(t_full + acc, (it >> 1) & 1, err)) break;
-            tc05::tc_fence_after();
-            float v[64];
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * 64 + c0, v + c0);
-            tc05::tmem_ld_wait();
-            tc05::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(t_empty + acc);   // accumulator drained: the MMA may overwrite it
-            if (r < MROWS) {
-                float4* dst = reinterpret_cast<float4*>(S + r * S_PITCH);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // S complete (epilogue warps only)
-            const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const int o = te + 128 * i;                     // 2 pooled rows x 28 x 16 = 896 outputs
-                const int co = o & 15, px = (o >> 4) % 28, pyl = o / 448;
-                // S[(oy_l*21 + ox/4) * S_PITCH + (ox%4)*16 + co], ox = 3*px + dx
-                int coff[3];
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int ox = 3 * px + dx;
-                    coff[dx] = (ox >> 2) * S_PITCH + (ox & 3) * 16 + co;
-                }
-                const float* s0 = S + (3 * pyl) * NG * S_PITCH;
-                float best = s0[coff[0]];
-                int idx = 0;
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        if (dy == 0 && dx == 0) continue;
-                        const float vv = s0[dy * NG * S_PITCH + coff[dx]];
-                        if (vv > best) { best = vv; idx = dy * 3 + dx; }     // strict: first maximum wins
-                    }
-                const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
-                const float out = fmaxf(best + breg[i], 0.f);
-                y[g] = out;
-                amax[g] = (uint8_t)idx;
-                // NHWC bf16 copy for the tensor-core conv2 (16 lanes = 16 channels = 32 contiguous bytes)
-                if (ybf) ybf[(((size_t)b * 28 + 2 * ty + pyl) * 28 + px) * 16 + co] = __float2bfloat16_rn(out);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // everyone done reading S
-        }
-    } else if (warp >= 8) {
-        // ------------------------------------------------------------------ repack (A producer); warp <-> ky
-        const int ky = warp - 8;
-        int src_off[4], dst_off[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int r = q * 32 + lane;
-            src_off[q] = r < MROWS ? (3 * (r / NG) + ky) * ROW_BYTES + 24 * (r % NG) : -1;
-            dst_off[q] = op_off(r, 0);
-        }
-        uint32_t fills = 0;                       // fills of stage ky by this warp: 2 per tile (channel pairs)
-        bool ok = true;
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-#pragma unroll
-            for (int cp = 0; cp < 2; ++cp, ++fills) {
-                ok = ok && tc05::mbar_wait(raw_full + 2 * cp, it & 1, err) && tc05::mbar_wait(raw_full + 2 * cp + 1, it & 1, err);
-                ok = ok && tc05::mbar_wait(a_empty + ky, (fills & 1) ^ 1, err);
-                if (!ok) break;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint8_t* base = smem + OFF_RAW + (2 * cp + h) * PLANE_BYTES;
-                    uint8_t* dst = smem + OFF_A + ky * A_STAGE + h * A_CHUNK;
-                    uint2 v[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (src_off[q] >= 0) {
-                            const uint2* p = reinterpret_cast<const uint2*>(base + src_off[q]);
-                            v[q][0] = p[0]; v[q][1] = p[1]; v[q][2] = p[2]; v[q][3] = p[3];
-                        }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (src_off[q] >= 0) {
-                            uint8_t* d = dst + dst_off[q];
-                            *reinterpret_cast<uint4*>(d) = make_uint4(v[q][0].x, v[q][0].y, v[q][1].x, v[q][1].y);
-                            *reinterpret_cast<uint4*>(d + 128) = make_uint4(v[q][2].x, v[q][2].y, v[q][3].x, v[q][3].y);
-                        }
-                }
-                tc05::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tc05::mbar_arrive(a_full + ky);
-                    tc05::mbar_arrive(raw_empty + 2 * cp);       // done with both planes of this pair for this tile
-                    tc05::mbar_arrive(raw_empty + 2 * cp + 1);
-                }
-            }
-        }
-    }
-    tc05::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
+// The Toeplitz bf16 weight operand (step s=(ci,ky): 64 rows n=(j*16+co) x 16 k, UMMA K-major no-swizzle canonical
+// layout byte(r,k) = (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2, i.e. LBO 128 B, SBO 256 B) is written by
+// pack_all_kernel (conv_tc.cu).
 
 }  // namespace c1tc
 
 // ================================================================================================
-// conv1 forward, second generation: the A operand comes straight from "Toeplitz-ready" (TP) planes
-// (stage.cu): no repack warps, no LDS/STS between the bulk copy and the MMA.
+// conv1 forward: the A operand comes straight from "Toeplitz-ready" (TP) planes (stage.cu).
 //   * a plane slot in shared memory holds, for one tile (6 conv rows), the 6 pieces (c = row class, h = K half)
 //     of one input plane exactly as they lie in HBM: piece (c,h) = rows q0..q0+nq(c)-1, 336 B each. The A
 //     operand of kernel row ky = 3d + c is the 126 x 16 slice starting d rows into pieces (c,0) / (c,1):
@@ -507,252 +284,10 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
 
 }  // namespace c1tp
 
-namespace c1tc {
-
-// ================================================================================================
-// conv1 wgrad on tcgen05 (bf16 mode). Same Toeplitz view as the forward, transposed:
-//   dWt[(ci,ky,p)][(j,co)] = sum_{rows r=(oy,g)}  in[ci][3oy+ky][12g+p] * dY[r][(j,co)]        (GEMM, K = rows)
-//   dW[co][ci][ky][kx]     = sum_{j=0..3} dWt[(ci,ky,3j+kx)][(j,co)]                          (fold, epilogue)
-// dY = pooled gradient routed to the saved first-max position, masked by ReLU; built per tile in smem
-// from (gact0, act1, amax1). Both operands are MN-major: the repacked A chunks keep the row (=K) index at
-// 16 B stride with 8 pixels contiguous, so 8 chunks form one M=128 operand (SBO 2048 / LBO 128).
-// M = 448 -> 4 M-tiles of 8 chunks ordered (ky, ci): tile mt holds kernel rows 2mt, 2mt+1 (tile 3: row 6,
-// plus an all-ones chunk whose accumulator row is the bias gradient). 4 accumulators x 64 columns stay
-// in TMEM for the whole kernel; one partial dW per CTA leaves at the end, already folded to OIHW.
-namespace wg {
-constexpr int NTHREADS = 512;
-constexpr int RAW_BYTES = 4 * PLANE_BYTES;               // 45056, whole tile (all 4 planes), double buffered
-constexpr int STAGE_BYTES = 8 * A_CHUNK;                 // 32768: one M-tile of chunks
-constexpr int NSTAGE = 3;
-constexpr int DY_BYTES = 64 * 256;                       // [8 n-blocks][128 rows][16 B]
-constexpr int OFF_RAW = 0;
-constexpr int OFF_A = OFF_RAW + 2 * RAW_BYTES;           // 90112
-constexpr int OFF_DY = OFF_A + NSTAGE * STAGE_BYTES;     // 188416
-constexpr int OFF_BAR = OFF_DY + 2 * DY_BYTES;           // 221184
-constexpr int NBAR = 2 + 2 + NSTAGE + NSTAGE + 2 + 2 + 1;
-constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
-constexpr int TMEM_COLS = 256;
-}  // namespace wg
-
-__global__ void __launch_bounds__(wg::NTHREADS, 1)
-conv1_wgrad_tc_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
-                      const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
-                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + wg::OFF_BAR);
-    uint64_t* raw_full = bars;            // [2]
-    uint64_t* raw_empty = bars + 2;       // [2]
-    uint64_t* a_full = bars + 4;          // [wg::NSTAGE]
-    uint64_t* a_empty = bars + 4 + wg::NSTAGE;
-    uint64_t* dy_full = bars + 4 + 2 * wg::NSTAGE;   // [2]
-    uint64_t* dy_empty = bars + 6 + 2 * wg::NSTAGE;  // [2]
-    uint64_t* done = bars + 8 + 2 * wg::NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + wg::NBAR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = B * TILES_PER_FRAME;
-    const bool any = (int)blockIdx.x < ntiles;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc05::mbar_init(raw_full + i, 1); tc05::mbar_init(raw_empty + i, 8);
-            tc05::mbar_init(dy_full + i, 4); tc05::mbar_init(dy_empty + i, 1);
-        }
-        for (int i = 0; i < wg::NSTAGE; ++i) { tc05::mbar_init(a_full + i, 8); tc05::mbar_init(a_empty + i, 1); }
-        tc05::mbar_init(done, 1);
-        tc05::mbar_fence_init();
-    }
-    if (warp == 2) tc05::tmem_alloc(tmem_slot, wg::TMEM_COLS);
-    // zero the A stages once: rows 126,127 and the unused chunks of M-tile 3 must never hold NaN patterns
-    for (int i = threadIdx.x; i < wg::NSTAGE * wg::STAGE_BYTES / 16; i += wg::NTHREADS) reinterpret_cast<uint4*>(smem + wg::OFF_A)[i] = make_uint4(0, 0, 0, 0);
-    tc05::fence_async_smem();
-    tc05::tc_fence_before();
-    __syncthreads();
-    tc05::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ loader: whole tile (4 planes), double buffered
-        if (lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                if (!tc05::mbar_wait(raw_empty + buf, ((it >> 1) & 1) ^ 1, err)) break;
-                const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
-                const __nv_bfloat16* src = x + (size_t)b * sn + (size_t)(ty * 18) * 256;
-                tc05::mbar_expect_tx(raw_full + buf, wg::RAW_BYTES);
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci)
-                    tc05::bulk_g2s(smem + wg::OFF_RAW + buf * wg::RAW_BYTES + ci * PLANE_BYTES, src + (size_t)ci * sc, PLANE_BYTES, raw_full + buf);
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer: per tile 4 visits (M-tiles) x 8 K-steps
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 1, 1);      // MN-major A and B
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + wg::OFF_A), 128, 2048, tc05::SW_NONE);
-        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + wg::OFF_DY), 128, 2048, tc05::SW_NONE);
-        uint32_t st = 0, ph = 0;
-        bool ok = true;
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            ok = tc05::mbar_wait(dy_full + buf, (it >> 1) & 1, err);
-#pragma unroll 1
-            for (int mt = 0; ok && mt < 4; ++mt) {
-                ok = tc05::mbar_wait(a_full + st, ph, err);
-                tc05::tc_fence_after();
-                if (ok && tc05::elect_one()) {
-                    const uint64_t a_st = ad0 + (uint64_t)(st * (wg::STAGE_BYTES >> 4));
-                    const uint64_t b_t = bd0 + (uint64_t)(buf * (wg::DY_BYTES >> 4));
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        tc05::mma_bf16(tmem_base + mt * 64, a_st + (uint64_t)(u * 16), b_t + (uint64_t)(u * 16), idesc, (it > 0 || u > 0) ? 1u : 0u);
-                    tc05::mma_commit(a_empty + st);
-                    if (mt == 3) tc05::mma_commit(dy_empty + buf);
-                }
-                __syncwarp();
-                if (++st == wg::NSTAGE) { st = 0; ph ^= 1; }
-            }
-        }
-        if (tc05::elect_one()) tc05::mma_commit(done);
-        __syncwarp();
-    } else if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ dY builder, then the folding epilogue
-        const int ew = warp - 4;
-        const int te = threadIdx.x - 128;
-        bool ok = true;
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            ok = tc05::mbar_wait(dy_empty + buf, ((it >> 1) & 1) ^ 1, err);
-            if (!ok) break;
-            uint8_t* dy = smem + wg::OFF_DY + buf * wg::DY_BYTES;
-#pragma unroll
-            for (int q = 0; q < wg::DY_BYTES / 16 / 128; ++q) reinterpret_cast<uint4*>(dy)[te + 128 * q] = make_uint4(0, 0, 0, 0);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int b = t / TILES_PER_FRAME, ty = t % TILES_PER_FRAME;
-#pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                const int o = te + 128 * q;                      // 2 pooled rows x 16 channels x 28 columns
-                const int px = o % 28, co = (o / 28) & 15, pyl = o / 448;
-                const size_t g = (((size_t)b * 16 + co) * 28 + 2 * ty + pyl) * 28 + px;
-                const float gv = aP[g] > 0.f ? gP[g] : 0.f;
-                const int pos = amax[g];
-                const int oyl = 3 * pyl + pos / 3, ox = 3 * px + pos % 3;
-                const int r = oyl * NG + (ox >> 2), n = (ox & 3) * 16 + co;
-                *reinterpret_cast<__nv_bfloat16*>(dy + (n >> 3) * 2048 + r * 16 + (n & 7) * 2) = __float2bfloat16_rn(gv);
-            }
-            tc05::fence_async_smem();
-            __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(dy_full + buf);
-        }
-        // ---- epilogue: fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
-        float* dst = part + (size_t)blockIdx.x * seg_len;
-        if ((int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
-            for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
-                for (int i = te; i < 3136 + 16; i += 128) part[(size_t)s2 * seg_len + (i < 3136 ? w_off + i : b_off + i - 3136)] = 0.f;
-        }
-        if (ok && tc05::mbar_wait(done, 0, err)) {
-            tc05::tc_fence_after();
-            const int i = ew * 32 + lane;                            // accumulator row: chunk = i/16 (ky half, ci), p = i%16
-            const int chunk = i >> 4, p = i & 15;
-#pragma unroll 1
-            for (int mt = 0; mt < 4; ++mt) {
-                float v[64];
-                if (any) {
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + mt * 64 + c0, v + c0);
-                    tc05::tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 64; ++c) v[c] = 0.f;
-                }
-                const int ky = 2 * mt + (chunk >> 2), ci = chunk & 3;
-                const bool wrow = ky < 7 && p < 7;                  // this lane writes tap kx = p
-                const bool brow = mt == 3 && chunk == 4 && p == 0;  // ones chunk: bias gradient
-#pragma unroll
-                for (int co = 0; co < 16; ++co) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // dW[.., kx] += dWt[p = 3j + kx][(j, co)]: fetch column j*16+co from the lane holding row 3j+kx
-                        const int srcl = (lane & 16) + ((3 * j + p) & 15);
-                        const float o = __shfl_sync(0xffffffffu, v[j * 16 + co], srcl);
-                        acc += brow ? v[j * 16 + co] : o;
-                    }
-                    if (wrow) dst[w_off + ((size_t)(co * 4 + ci) * 7 + ky) * 7 + p] = acc;
-                    else if (brow) dst[b_off + co] = acc;
-                }
-            }
-        }
-    } else if (warp >= 8) {
-        // ------------------------------------------------------------------ repack: warp w fills chunk w of every M-tile stage
-        const int pw = warp - 8;
-        const int ci = pw & 3;
-        int src_off[4], dst_off[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int r = q * 32 + lane;
-            src_off[q] = r < MROWS ? (3 * (r / NG)) * ROW_BYTES + 24 * (r % NG) : -1;
-            dst_off[q] = (r >> 3) * 128 + (r & 7) * 16;            // wgrad image: chunk half c at +2048
-        }
-        uint32_t st = 0, ph = 1;
-        bool ok = true;
-        int it = 0;
-        for (int t = blockIdx.x; ok && t < ntiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            ok = tc05::mbar_wait(raw_full + buf, (it >> 1) & 1, err);
-#pragma unroll 1
-            for (int mt = 0; ok && mt < 4; ++mt) {
-                ok = tc05::mbar_wait(a_empty + st, ph, err);
-                if (!ok) break;
-                const int ky = 2 * mt + (pw >> 2);
-                uint8_t* dst = smem + wg::OFF_A + st * wg::STAGE_BYTES + pw * A_CHUNK;
-                if (ky < 7) {
-                    const uint8_t* base = smem + wg::OFF_RAW + buf * wg::RAW_BYTES + ci * PLANE_BYTES + ky * ROW_BYTES;
-                    uint2 v[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (src_off[q] >= 0) {
-                            const uint2* pp = reinterpret_cast<const uint2*>(base + src_off[q]);
-                            v[q][0] = pp[0]; v[q][1] = pp[1]; v[q][2] = pp[2]; v[q][3] = pp[3];
-                        }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (src_off[q] >= 0) {
-                            uint8_t* d = dst + dst_off[q];
-                            *reinterpret_cast<uint4*>(d) = make_uint4(v[q][0].x, v[q][0].y, v[q][1].x, v[q][1].y);
-                            *reinterpret_cast<uint4*>(d + 2048) = make_uint4(v[q][2].x, v[q][2].y, v[q][3].x, v[q][3].y);
-                        }
-                } else if (mt == 3 && pw == 4) {
-                    // the ones chunk: accumulator row 64 of M-tile 3 becomes sum_r dY[r][n]
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint8_t* d = dst + dst_off[q];
-                        const uint4 one = (q * 32 + lane) < MROWS ? make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u) : make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(d) = one;
-                        *reinterpret_cast<uint4*>(d + 2048) = one;
-                    }
-                }
-                tc05::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(a_full + st);
-                if (++st == wg::NSTAGE) { st = 0; ph ^= 1; }
-            }
-            if (!ok) break;
-            __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(raw_empty + buf);
-        }
-    }
-    tc05::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tc05::tmem_dealloc(tmem_base, wg::TMEM_COLS);
-}
-
-}  // namespace c1tc
 
 
 // ================================================================================================
-// conv1 wgrad, second generation: Toeplitz-ready planes in, no repack, every plane loaded once.
+// conv1 wgrad: Toeplitz-ready planes in, no repack, every plane loaded once.
 //   dWt[ci][(ky,p)][(j,co)] = sum_b sum_{r=(oy,g)} plane(b+ci)[3oy+ky][12g+p] * dY(b)[r][(j,co)]
 // is regrouped BY PLANE: plane P meets dY(P), dY(P-1), dY(P-2), dY(P-3) as channel ci = 0..3 (sliding window), so one
 // "job" = (tile row ty, plane P) loads P's tile once and runs 4 accumulation groups, one per ci, each into its own
@@ -1033,26 +568,8 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
 }
 
 int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
-    if (c->x_tp) return conv1_tp_launch(c, stream);
-    BC_CHECK_ARG(c->x && c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05): null buffer (x, w_packed, err_flag, act, amax)");
-    BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 (tcgen05): needs bf16 gray planes and obs_size 4");
-    BC_CHECK_ARG(((uintptr_t)c->x % 16 == 0) && (c->x_stride_n * 2) % 16 == 0 && (c->x_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
-                 "conv1 (tcgen05): x, its strides and w_packed must be 16 B aligned");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(c1tc::conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tc::SMEM_BYTES);
-        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05): smem opt-in %d B failed: %s", c1tc::SMEM_BYTES, cudaGetErrorString(e));
-        configured = true;
-    }
-    const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
-    const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
-    int grid = bc::num_sms();
-    if (grid > ntiles) grid = ntiles;
-    c1tc::conv1_tc_kernel<<<grid, c1tc::NTHREADS, c1tc::SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
-        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
-    BC_CUDA_LAUNCH_CHECK("conv1_tc_kernel");
-    return BC_OK;
+    BC_CHECK_ARG(c->x_tp, "conv1 (tcgen05): bf16 mode reads Toeplitz-ready planes (bc_ctx.x_tp; bc_stage_gray_tp / bc_planes_to_tp)");
+    return conv1_tp_launch(c, stream);
 }
 
 static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
@@ -1082,23 +599,6 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
 }
 
 int bc_conv1_wgrad_tc_launch(const bc_ctx* c, void* stream) {
-    if (c->x_tp) return conv1_wgrad_tp_launch(c, stream);
-    BC_CHECK_ARG(c->x && c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05): null buffer");
-    BC_CHECK_ARG(c->x_dtype == BC_BF16 && c->obs_size == 4, "conv1 wgrad (tcgen05): needs bf16 gray planes and obs_size 4");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(c1tc::conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tc::wg::SMEM_BYTES);
-        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05): smem opt-in %d B failed: %s", c1tc::wg::SMEM_BYTES, cudaGetErrorString(e));
-        configured = true;
-    }
-    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
-    const bc::Partials pl = bc::partials_layout(ar);
-    const int nparts = bc::kWgradParts[0];
-    int grid = bc::num_sms();
-    if (grid > nparts) grid = nparts;
-    c1tc::conv1_wgrad_tc_kernel<<<grid, c1tc::wg::NTHREADS, c1tc::wg::SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)c->x, c->x_stride_n, c->x_stride_c, c->gact[0], c->act[0], c->amax[0],
-        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], nparts, c->batch, c->err_flag);
-    BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tc_kernel");
-    return BC_OK;
+    BC_CHECK_ARG(c->x_tp, "conv1 wgrad (tcgen05): bf16 mode reads Toeplitz-ready planes (bc_ctx.x_tp)");
+    return conv1_wgrad_tp_launch(c, stream);
 }

@@ -56,18 +56,6 @@ __global__ void __launch_bounds__(256) stage_gray_kernel(const uint8_t* __restri
     }
 }
 
-// f32 -> bf16 cast of an already-normalised batch (bf16 mode fed with reference-style f32 samples)
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 v = __ldg(in + i);
-        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
-        out[i] = o;
-    }
-}
-
 // ---- "Toeplitz-ready" (TP) bf16 planes: the layout conv1's tcgen05 kernels consume without any repack.
 // conv1 is a 7x7 stride-3 convolution evaluated as D[(oy,g),(j,co)] = sum A[(oy,g),(ci,ky,p)] * Wt (conv1_tc.cu):
 // row (oy,g) of the A operand for kernel row ky is the 16-pixel segment [12g, 12g+16) of image row 3*oy+ky.
@@ -178,19 +166,6 @@ extern "C" int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, 
     const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
     stage_gray_tp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
     BC_CUDA_LAUNCH_CHECK("stage_gray_tp_kernel");
-    return BC_OK;
-}
-
-extern "C" int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream) {
-    BC_CHECK_ARG(in && out && n >= 0 && n % 4 == 0, "bc_cast_bf16: null pointer or n %% 4 != 0");
-    BC_CHECK_ARG((uintptr_t)in % 16 == 0 && (uintptr_t)out % 8 == 0, "bc_cast_bf16: alignment");
-    if (n == 0) return BC_OK;
-    const int64_t n4 = n / 4;
-    int64_t blocks = (n4 + 255) / 256;
-    const int64_t cap = (int64_t)bc::num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)in, (uint2*)out, n4);
-    BC_CUDA_LAUNCH_CHECK("cast_bf16_kernel");
     return BC_OK;
 }
 

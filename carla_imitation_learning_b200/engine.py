@@ -59,20 +59,21 @@ def sliding_window(gray: torch.Tensor, frame_skip: int = 4) -> torch.Tensor:
 
 
 class StagedBatch:
-    """bf16-mode input produced by stage_frames(): n staged frames = n - frame_skip samples, in the two layouts the
-    tcgen05 kernels read -- `tp` (n, TP_PLANE_ELEMS) Toeplitz-ready planes for conv1 forward and `plain` (n,256,256)
-    bf16 planes for conv1 wgrad -- both written by ONE pass of the staging kernel over the u8 frames."""
+    """bf16-mode input produced by stage_frames(): n staged frames = n - frame_skip samples as `tp`
+    (n, TP_PLANE_ELEMS) Toeplitz-ready bf16 planes, the layout both tcgen05 conv1 kernels consume as it is
+    (include/bc_b200.h, BC_BF16_TP). `plain` (n,256,256) bf16 is optional: the same gray values as ordinary
+    planes (diagnostics, or the exact-f32 kernels), written by the same pass of the staging kernel."""
 
-    def __init__(self, tp: torch.Tensor, plain: torch.Tensor, frame_skip: int = 4):
+    def __init__(self, tp: torch.Tensor, plain: Optional[torch.Tensor] = None, frame_skip: int = 4):
         self.tp, self.plain, self.frame_skip = tp, plain, frame_skip
 
     @property
-    def x(self) -> torch.Tensor:
-        return sliding_window(self.plain, self.frame_skip)
+    def x(self) -> Optional[torch.Tensor]:
+        return None if self.plain is None else sliding_window(self.plain, self.frame_skip)
 
     @property
     def shape(self):
-        return (self.plain.shape[0] - self.frame_skip, self.frame_skip, H, W)
+        return (self.tp.shape[0] - self.frame_skip, self.frame_skip, H, W)
 
     @property
     def device(self):
@@ -82,7 +83,8 @@ class StagedBatch:
         return self
 
 
-def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, frame_skip: int = 4) -> StagedBatch:
+def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, frame_skip: int = 4,
+                 plain: bool = False) -> StagedBatch:
     """(n,256,256,3) u8 RGB on the device -> StagedBatch. The bf16-mode replacement of SequentialTorchDataset's
     per-sample numpy work (imitation_dataset.py:115-133): gray conversion, /255, 4-frame stacking (as a view) and
     the MMA operand layout of conv1 in one fused kernel."""
@@ -94,10 +96,11 @@ def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, fra
         raise ValueError(f"need more than {frame_skip} frames, got {n}")
     if out is None:
         out = StagedBatch(torch.empty((n, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=frames_u8.device),
-                          torch.empty((n, H, W), dtype=torch.bfloat16, device=frames_u8.device), frame_skip)
+                          torch.empty((n, H, W), dtype=torch.bfloat16, device=frames_u8.device) if plain else None, frame_skip)
     elif out.tp.shape[0] != n:
         raise ValueError("out was staged for a different number of frames")
-    _lib.check(_lib.lib().bc_stage_gray_tp(frames_u8.data_ptr(), out.tp.data_ptr(), out.plain.data_ptr(), n, _stream_ptr()), "bc_stage_gray_tp")
+    _lib.check(_lib.lib().bc_stage_gray_tp(frames_u8.data_ptr(), out.tp.data_ptr(),
+                                           out.plain.data_ptr() if out.plain is not None else None, n, _stream_ptr()), "bc_stage_gray_tp")
     return out
 
 
@@ -105,7 +108,7 @@ def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, fra
 class StepBuffers:
     """Everything one forward produces and one backward consumes."""
     batch: int
-    x: torch.Tensor
+    x: Optional[torch.Tensor]         # None when the input exists only as Toeplitz-ready planes (x_tp)
     y: Optional[torch.Tensor]
     act: List[torch.Tensor]
     amax: List[torch.Tensor]
@@ -178,13 +181,6 @@ class BCEngine:
             if self.conv_mode and bufs.act_bf16:
                 bufs.dy_bf16 = torch.empty((bufs.batch, 24, 24, 32), dtype=torch.bfloat16, device=self.device)
 
-    def cast_bf16(self, x: torch.Tensor) -> torch.Tensor:
-        """Contiguous f32 -> bf16 copy with our own kernel (bf16 mode fed with the reference's f32 batches)."""
-        x = x.contiguous()
-        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-        _lib.check(self.lib.bc_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream_ptr()), "bc_cast_bf16")
-        return out
-
     def to_tp(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
         """(B,4,256,256) f32/bf16 batch -> Toeplitz-ready bf16 planes (include/bc_b200.h BC_BF16_TP) + strides.
         A sliding-window view (sliding_window()) is converted once per PLANE, not per sample."""
@@ -214,8 +210,6 @@ class BCEngine:
             raise ValueError(f"x must be (B,{self.obs_size},{H},{W}) like nets.py:14, got {tuple(x.shape)}")
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
-        if (self.conv_mode & 1) and x.dtype == torch.float32 and self.obs_size == 4:
-            x = self.cast_bf16(x)           # tensor-core conv1 reads bf16 planes
         esz = x.element_size()
         ok = (x.stride(3) == 1 and x.stride(2) == W and (x.stride(0) * esz) % 16 == 0 and (x.stride(1) * esz) % 16 == 0
               and x.data_ptr() % 16 == 0)
@@ -224,9 +218,12 @@ class BCEngine:
     def ctx(self, b: StepBuffers, loss_scale: Optional[float] = None) -> _lib.BcCtx:
         c = _lib.BcCtx()
         c.obs_size, c.n_actions, c.batch = self.obs_size, self.n_actions, b.batch
-        c.x_dtype = _lib.BC_F32 if b.x.dtype == torch.float32 else _lib.BC_BF16
-        c.x_stride_n, c.x_stride_c = (b.x.stride(0), b.x.stride(1)) if b.batch else (0, 0)
-        c.x = b.x.data_ptr()
+        if b.x is None:
+            c.x, c.x_dtype, c.x_stride_n, c.x_stride_c = None, _lib.BC_BF16_TP, 0, 0
+        else:
+            c.x_dtype = _lib.BC_F32 if b.x.dtype == torch.float32 else _lib.BC_BF16
+            c.x_stride_n, c.x_stride_c = (b.x.stride(0), b.x.stride(1)) if b.batch else (0, 0)
+            c.x = b.x.data_ptr()
         c.y = b.y.data_ptr() if b.y is not None else None
         c.params, c.grads = self.arena.data_ptr(), self.grads.data_ptr()
         for i in range(4):

@@ -56,7 +56,7 @@ typedef struct {
     int32_t x_dtype;         /* bc_dtype of x                          */
     int64_t x_stride_n;      /* element stride between samples of x    */
     int64_t x_stride_c;      /* element stride between channels of x   */
-    const void* x;           /* (batch, obs, 256, 256) planar, rows contiguous */
+    const void* x;           /* (batch, obs, 256, 256) planar, rows contiguous; may be NULL in bf16 mode (x_tp only) */
     const int64_t* y;        /* (batch,) labels, may be NULL for forward-only  */
     const float* params;     /* parameter arena                        */
     float* grads;            /* gradient arena (same layout)           */
@@ -100,9 +100,6 @@ int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, int64_t n_f
 /* plain planes (f32 or bf16; 256x256, rows contiguous, `plane_stride` elements apart) -> BC_BF16_TP planes:
  * how a reference-style (B,4,256,256) batch enters the tcgen05 conv1 (bf16 mode) */
 int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream);
-
-/* bf16 mode fed with f32 samples (the reference's batch format): contiguous f32 -> bf16 cast, n % 4 == 0 */
-int bc_cast_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* bf16 tensor-core mode: re-pack the f32 master weights into the smem images the tcgen05 kernels
  * read (conv1: Toeplitz-expanded [64 x 448] bf16). Call after every optimiser step. */

@@ -412,10 +412,12 @@ def test_stage_frames_feeds_both_layouts_and_matches_the_plain_path():
     frames, labels = O.synth_frames(321, B + 4)
     fr = torch.from_numpy(frames).to(dev)
     y = torch.from_numpy(labels[4:4 + B]).to(dev)
-    sb = stage_frames(fr)
+    sb = stage_frames(fr, plain=True)
     plain = stage_gray(fr, dtype=torch.bfloat16)
     assert torch.equal(sb.plain.view(torch.int16), plain.view(torch.int16))
     assert torch.equal(sb.tp.view(torch.int16), _tp_reference(plain).reshape(B + 4, -1).view(torch.int16))
+    assert stage_frames(fr).plain is None and torch.equal(stage_frames(fr).tp.view(torch.int16), sb.tp.view(torch.int16))
+    sb = stage_frames(fr)                       # the product path: Toeplitz-ready planes only
     assert tuple(sb.shape) == (B, 4, 256, 256)
     torch.manual_seed(12345)
     net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
