@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "conv_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 

@@ -14,6 +14,8 @@ int bc_conv_tc_pack(const bc_ctx* c, void* stream);
 int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 int bc_unpool_launch(const bc_ctx* c, int layer, void* stream);
+int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);     // conv_sw.cu (layers 1, 2)
+int bc_conv_sw_dgrad_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);
 void bc_tc_set_dy_ready(bool v);
 size_t bc_conv_tc_pack_total();
 

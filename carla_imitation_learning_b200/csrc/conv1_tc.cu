@@ -266,13 +266,14 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                         __nv_bfloat162 p01 = __floats2bfloat162_rn(outv[0], outv[1]), p23 = __floats2bfloat162_rn(outv[2], outv[3]);
                         uint2 pk;
                         pk.x = *reinterpret_cast<uint32_t*>(&p01); pk.y = *reinterpret_cast<uint32_t*>(&p23);
-                        *reinterpret_cast<uint2*>(P_ + (pyl * 28 + px) * 16 + 4 * cq) = pk;   // NHWC bf16 tile, stored in pass B
+                        *reinterpret_cast<uint2*>(P_ + ((cq >> 1) * 56 + pyl * 28 + px) * 8 + (cq & 1) * 4) = pk;   // P8 bf16 tile [c/8][pixel][8], stored in pass B
                     }
                 }
                 if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-                // pass B: the tile's NHWC bf16 copy for the tensor-core conv2 is one contiguous 1792 B block
+                // pass B: the bf16 copy conv2's shifted-window kernel reads, layout P8 = [b][c/8][pixel][8] (conv_sw.cu):
+                // the tile is 56 consecutive pixels of each of the two 8-channel planes
                 if (ybf && te < 112)
-                    reinterpret_cast<uint4*>(ybf + (((size_t)b * 28 + 2 * ty) * 28) * 16)[te] = reinterpret_cast<const uint4*>(P_)[te];
+                    reinterpret_cast<uint4*>(ybf)[((size_t)b * 2 + te / 56) * 784 + 2 * ty * 28 + te % 56] = reinterpret_cast<const uint4*>(P_)[te];
                 // S_ and P_ are rewritten only after the next tile's first barrier, which every thread reaches after this store
             }
         }

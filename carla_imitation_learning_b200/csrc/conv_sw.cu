@@ -1,0 +1,505 @@
+// K2, K3 (bf16 tensor-core variant, second generation): Conv2d(stride 1) + bias + ReLU + MaxPool(2) and its dgrad
+// as "shifted-window" implicit GEMMs: the whole input image of one sample sits in shared memory and the A operand
+// of every (tap, channel block) K-step is the SAME bytes seen through a descriptor whose start address is shifted
+// by the tap -- no im2col gather, no per-step copies, nothing between the bulk copy and the tensor core.
+// Replaces cnn_base[3:9] of /root/reference/src/architectures/nets.py:21-26 (forward) and the autograd backward of
+// the same lines (input gradient) in bf16 mode.
+//
+// Layout that makes it work ("P8"): activations are stored [b][c/8][pixel][8 channels] bf16, so one pixel of one
+// 8-channel group is 16 bytes and consecutive pixels are 16 bytes apart. With GEMM row m = linear pixel index
+// (oy * W_in + ox) the A operand of tap (ky,kx), channel block cb is
+//     start = image + (m0 + ky*W_in + kx) * 16 + (2 cb) * PLANE,   SBO = 128 B (8 pixels),   LBO = PLANE (next 8 channels)
+// which is exactly the UMMA K-major no-swizzle canonical layout. Rows with ox >= W_out are computed and ignored
+// (M efficiency 24/28 for conv2, 9/12 for conv3); in exchange the L2 traffic per image is the image itself, once,
+// instead of 25x (conv2) / 16x (conv3) im2col amplification through LDG gathers.
+//
+//   forward : tile = RT conv rows (MT = RT*W_in <= 128 GEMM rows) of one image; epilogue TMEM -> smem -> 2x2 max /
+//             first-max argmax / +bias / ReLU -> f32 NCHW + argmax + bf16 copy for the next layer.
+//   dgrad   : dX[iy][ix][ci] = sum dYp[iy+ky'][ix+kx'][co] * W[co][ci][K-1-ky'][K-1-kx'] over the zero-padded routed
+//             gradient dYp, which the kernel BUILDS in shared memory from (pooled gradient, activation, argmax):
+//             no unpool kernel, no dense dY in HBM.
+// Roles per CTA (persistent): warp 0 loader / TMEM owner, warps 1-3 and 12 MMA issuers (tile c -> issuer c % 4,
+// accumulator c % NACC), warps 4-11 two epilogue groups (forward) or dY builders + epilogue (dgrad).
+#include "bc_common.cuh"
+#include "tc05.cuh"
+
+namespace csw {
+
+constexpr int NTHREADS = 13 * 32;
+
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+// contiguous balanced range of the (image, tile) list
+struct TileRange {
+    int i, hi, tpi;
+    __device__ TileRange(int B, int tpi_) : tpi(tpi_) {
+        const long long T = (long long)B * tpi_;
+        i = (int)(T * blockIdx.x / gridDim.x);
+        hi = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    }
+    __device__ bool next(int& b, int& t) {
+        if (i >= hi) return false;
+        b = i / tpi; t = i - b * tpi;
+        ++i;
+        return true;
+    }
+};
+
+// ================================================================================================ forward
+template <int CIN_, int COUT_, int KS_, int HIN_, int HP_, int RT_, bool OUT_P8_>
+struct FCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, HIN = HIN_, HP = HP_, RT = RT_;
+    static constexpr bool OUT_P8 = OUT_P8_;
+    static constexpr int CG = CIN / 8, CB = CIN / 16, NSTEP = KS * KS * CB;
+    static constexpr int PLANE = HIN * HIN * 16;            // bytes of one 8-channel plane of one image
+    static constexpr int IMG = CG * PLANE;
+    static constexpr int MT = RT * HIN;                     // GEMM rows of a tile that can be valid
+    static constexpr int TPI = 2 * HP / RT;                 // tiles per image (only rows that feed a pool window)
+    static constexpr int B_STEP = COUT * 32, B_BYTES = NSTEP * B_STEP;
+    static constexpr int NIMG = 3;
+    static constexpr int NACC = cmin(8, 512 / COUT);
+    static constexpr int S_PITCH = COUT + 4;                // floats
+    static constexpr int S_BYTES = MT * S_PITCH * 4;
+    static constexpr int P_BYTES = (RT / 2) * HP * COUT * 2; // one tile's pooled outputs as bf16
+    static constexpr int OFF_B = 0;
+    static constexpr int OFF_IMG = (B_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_S = (OFF_IMG + NIMG * IMG + 4096 + 127) / 128 * 128;   // 4 KB: over-read of the last tile's shifted windows
+    static constexpr int OFF_P = OFF_S + 2 * S_BYTES;
+    static constexpr int OFF_BIAS = (OFF_P + 2 * P_BYTES + 15) / 16 * 16;
+    static constexpr int OFF_BAR = (OFF_BIAS + COUT * 4 + 127) / 128 * 128;
+    static constexpr int NBAR = 1 + 2 * NIMG + 2 * NACC;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+    static_assert(MT <= 128 && RT % 2 == 0 && (2 * HP) % RT == 0, "tile shape");
+    static_assert((128 + (KS - 1) * HIN + KS) * 16 + (TPI - 1) * MT * 16 <= PLANE + 4096, "over-read pad");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct FwdArgs {
+    const __nv_bfloat16* in;      // P8 bf16 activations of the previous layer
+    const __nv_bfloat16* wpk;     // forward operand image (pack_all_kernel): step (tap, cb): COUT rows x 16 k
+    const float* bias;
+    float* y; uint8_t* amax; __nv_bfloat16* ybf;
+    int B; int* err;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(NTHREADS, 1) sw_fwd_kernel(const FwdArgs a) {
+    constexpr int COUT = C::COUT, HIN = C::HIN, HP = C::HP, RT = C::RT, NIMG = C::NIMG, NACC = C::NACC, MT = C::MT, SP = C::S_PITCH;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* b_full = bars;
+    uint64_t* img_full = bars + 1;               // [NIMG]
+    uint64_t* img_empty = bars + 1 + NIMG;       // [NIMG]  4 issuers
+    uint64_t* t_full = bars + 1 + 2 * NIMG;      // [NACC]
+    uint64_t* t_empty = t_full + NACC;           // [NACC]  4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* err = a.err;
+
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(b_full, 1);
+        for (int i = 0; i < NIMG; ++i) { tc05::mbar_init(img_full + i, 1); tc05::mbar_init(img_empty + i, 4); }
+        for (int i = 0; i < NACC; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < 4096 / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_IMG + NIMG * C::IMG)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < COUT) reinterpret_cast<float*>(smem + C::OFF_BIAS)[threadIdx.x] = a.bias[threadIdx.x];
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader: one bulk copy per image
+        if (lane == 0) {
+            tc05::mbar_expect_tx(b_full, C::B_BYTES);
+            tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
+            TileRange it(a.B, C::TPI);
+            int b, t, lastb = -1;
+            uint32_t k = 0;
+            while (it.next(b, t)) {
+                if (b == lastb) continue;
+                lastb = b;
+                const uint32_t slot = k % NIMG, ph = (k / NIMG) & 1;
+                if (!tc05::mbar_wait(img_empty + slot, ph ^ 1, err)) break;
+                tc05::mbar_expect_tx(img_full + slot, C::IMG);
+                tc05::bulk_g2s(smem + C::OFF_IMG + slot * C::IMG, reinterpret_cast<const uint8_t*>(a.in) + (size_t)b * C::IMG, C::IMG, img_full + slot);
+                ++k;
+            }
+        }
+    } else if (warp <= 3 || warp == 12) {
+        // ------------------------------------------------------------------ 4 MMA issuers
+        const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, COUT, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_IMG), C::PLANE, 128, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_B), 128, 256, tc05::SW_NONE);
+        bool ok = tc05::mbar_wait(b_full, 0, err);
+        TileRange it(a.B, C::TPI);
+        int b, t, lastb = -1;
+        uint32_t k = 0, use = 0, cnt = 0;          // k = images seen so far (the current one is k-1)
+        while (ok && it.next(b, t)) {
+            if (b != lastb) {
+                if (lastb >= 0) {                  // done with the previous image: our MMAs on it release our share of its slot
+                    if (tc05::elect_one()) tc05::mma_commit(img_empty + (k - 1) % NIMG);
+                    __syncwarp();
+                }
+                lastb = b;
+                ok = tc05::mbar_wait(img_full + k % NIMG, (k / NIMG) & 1, err);
+                ++k;
+            }
+            const uint32_t c = cnt++;
+            if ((c & 3) != w) continue;
+            const uint32_t acc = c % NACC, slot = (k - 1) % NIMG;
+            ok = ok && tc05::mbar_wait(t_empty + acc, ((use >> acc) & 1) ^ 1, err);
+            tc05::tc_fence_after();
+            if (ok && tc05::elect_one()) {
+                const uint64_t a0 = ad0 + (uint64_t)((slot * C::IMG + t * MT * 16) >> 4);
+                const uint32_t d_tmem = tmem_base + acc * COUT;
+#pragma unroll
+                for (int s = 0; s < C::NSTEP; ++s) {
+                    const int tap = s / C::CB, cb = s % C::CB;
+                    tc05::mma_bf16(d_tmem, a0 + (uint64_t)(((tap / C::KS) * HIN + tap % C::KS) + 2 * cb * (C::PLANE >> 4)),
+                                   bd0 + (uint64_t)(s * (C::B_STEP >> 4)), idesc, s > 0);
+                }
+                tc05::mma_commit(t_full + acc);
+            }
+            __syncwarp();
+            use ^= 1u << acc;
+        }
+        if (lastb >= 0) {
+            if (tc05::elect_one()) tc05::mma_commit(img_empty + (k - 1) % NIMG);
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 4-11): two groups take alternate tiles
+        const int eg = (warp - 4) >> 2, ew = warp & 3;
+        const int te = (warp - 4 - 4 * eg) * 32 + lane;
+        const int r = ew * 32 + lane;
+        float* S_ = reinterpret_cast<float*>(smem + C::OFF_S + eg * C::S_BYTES);
+        __nv_bfloat16* P_ = reinterpret_cast<__nv_bfloat16*>(smem + C::OFF_P + eg * C::P_BYTES);
+        const float* bias_s = reinterpret_cast<const float*>(smem + C::OFF_BIAS);
+        TileRange it(a.B, C::TPI);
+        int b, t;
+        uint32_t use = 0, cnt = 0;
+        bool ok = true;
+        while (ok && it.next(b, t)) {
+            const uint32_t c = cnt++;
+            const uint32_t acc = c % NACC, par = (use >> acc) & 1;
+            use ^= 1u << acc;
+            if ((int)(c & 1) != eg) continue;
+            ok = tc05::mbar_wait(t_full + acc, par, err);
+            if (!ok) break;
+            tc05::tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+                float v[16];
+                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * COUT + c0, v);
+                tc05::tmem_ld_wait();
+                if (r < MT) {
+                    float4* dst = reinterpret_cast<float4*>(S_ + r * SP + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            }
+            tc05::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(t_empty + acc);
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            // pooled outputs of this tile: RT/2 rows x HP columns x COUT channels; item = (4 channels, pooled pixel)
+            constexpr int NPP = (RT / 2) * HP, NITEM = NPP * (COUT / 4);
+#pragma unroll
+            for (int i = 0; i < (NITEM + 127) / 128; ++i) {
+                const int o = te + 128 * i;
+                if (o < NITEM) {
+                    const int pp = o % NPP, cq = o / NPP;
+                    const int pr = pp / HP, pc = pp % HP;
+                    const float* s0 = S_ + ((2 * pr) * HIN + 2 * pc) * SP + 4 * cq;
+                    float4 best = *reinterpret_cast<const float4*>(s0);
+                    int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int pos = 1; pos < 4; ++pos) {
+                        const float4 vv = *reinterpret_cast<const float4*>(s0 + ((pos >> 1) * HIN + (pos & 1)) * SP);
+                        // strict: first maximum wins (torch's max_pool2d routing)
+                        if (vv.x > best.x) { best.x = vv.x; bi[0] = pos; }
+                        if (vv.y > best.y) { best.y = vv.y; bi[1] = pos; }
+                        if (vv.z > best.z) { best.z = vv.z; bi[2] = pos; }
+                        if (vv.w > best.w) { best.w = vv.w; bi[3] = pos; }
+                    }
+                    const float bv[4] = {best.x, best.y, best.z, best.w};
+                    float outv[4];
+                    const int wl = (t * (RT / 2) + pr) * HP + pc;          // pooled pixel inside the image
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int co = 4 * cq + q;
+                        const size_t g = ((size_t)b * COUT + co) * (HP * HP) + wl;
+                        outv[q] = fmaxf(bv[q] + bias_s[co], 0.f);
+                        a.y[g] = outv[q];
+                        a.amax[g] = (uint8_t)bi[q];
+                    }
+                    __nv_bfloat162 p01 = __floats2bfloat162_rn(outv[0], outv[1]), p23 = __floats2bfloat162_rn(outv[2], outv[3]);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p01); pk.y = *reinterpret_cast<uint32_t*>(&p23);
+                    if constexpr (C::OUT_P8)   // [c/8][pooled pixel of the tile][8]
+                        *reinterpret_cast<uint2*>(P_ + ((cq >> 1) * NPP + pp) * 8 + (cq & 1) * 4) = pk;
+                    else                       // NHWC: [pooled pixel of the tile][COUT]
+                        *reinterpret_cast<uint2*>(P_ + pp * COUT + 4 * cq) = pk;
+                }
+            }
+            if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (a.ybf) {
+                constexpr int NV = C::P_BYTES / 16;
+                for (int i = te; i < NV; i += 128) {
+                    size_t dst;
+                    if constexpr (C::OUT_P8) {
+                        const int cg = i / NPP, pp = i % NPP;                // one uint4 = one pixel of one 8-channel group
+                        dst = (((size_t)b * (COUT / 8) + cg) * (HP * HP) + t * NPP + pp);
+                    } else {
+                        dst = ((size_t)b * (HP * HP) + t * NPP) * (COUT / 8) + i;
+                    }
+                    reinterpret_cast<uint4*>(a.ybf)[dst] = reinterpret_cast<const uint4*>(P_)[i];
+                }
+            }
+            // S_ / P_ are rewritten only after the next tile's first barrier, which every thread reaches after these stores
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
+}
+
+// ================================================================================================ dgrad
+template <int CIN_, int COUT_, int KS_, int HIN_, int HP_>
+struct DCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, HIN = HIN_, HP = HP_;
+    static constexpr int N = CIN;                           // GEMM N = input channels
+    static constexpr int CG = COUT / 8, CB = COUT / 16, NSTEP = KS * KS * CB;
+    static constexpr int WP = HIN + KS - 1;                 // padded routed-gradient image, square: conv output + (KS-1) zeros on every side
+    static constexpr int PLANE = WP * WP * 16, IMG = CG * PLANE;
+    static constexpr int MROWS = HIN * WP;                  // GEMM rows per image: (iy, ix') with ix' < WP, valid ix' < HIN
+    static constexpr int TPI = (MROWS + 127) / 128;
+    static constexpr int B_STEP = N * 32, B_BYTES = NSTEP * B_STEP;
+    static constexpr int NIMG = 2;
+    static constexpr int NACC = cmin(8, 512 / (N < 32 ? 32 : N));
+    static constexpr int ACCW = N < 32 ? 32 : N;            // TMEM columns per accumulator
+    static constexpr int OFF_B = 0;
+    static constexpr int OFF_IMG = (B_BYTES + 127) / 128 * 128;
+    static constexpr int OVER = ((TPI * 128 + (KS - 1) * WP + KS) * 16 > PLANE ? (TPI * 128 + (KS - 1) * WP + KS) * 16 - PLANE : 0);
+    static constexpr int OFF_BAR = (OFF_IMG + NIMG * IMG + OVER + 127) / 128 * 128;
+    static constexpr int NBAR = 1 + 2 * NIMG + 2 * NACC;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+    static_assert(WP >= 2 * HP + 2 * (KS - 1), "the pooled region plus the zero border must fit");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct DgradArgs {
+    const float* gP; const float* aP; const uint8_t* amax;   // pooled gradient, pooled activation, argmax of THIS layer's output
+    const __nv_bfloat16* wpk;                                // dgrad operand image: step (tap, co/16): CIN rows x 16 k
+    float* gin;                                              // (B, CIN, HIN, HIN) f32
+    int B; int* err;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a) {
+    constexpr int N = C::N, COUT = C::COUT, HP = C::HP, WP = C::WP, HIN = C::HIN, KS = C::KS, NIMG = C::NIMG, NACC = C::NACC;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* b_full = bars;
+    uint64_t* img_full = bars + 1;               // [NIMG]  8 builder warps
+    uint64_t* img_empty = bars + 1 + NIMG;       // [NIMG]  4 issuers
+    uint64_t* t_full = bars + 1 + 2 * NIMG;      // [NACC]
+    uint64_t* t_empty = t_full + NACC;           // [NACC]  4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* err = a.err;
+
+    if (threadIdx.x == 0) {
+        tc05::mbar_init(b_full, 1);
+        for (int i = 0; i < NIMG; ++i) { tc05::mbar_init(img_full + i, 8); tc05::mbar_init(img_empty + i, 4); }
+        for (int i = 0; i < NACC; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < C::OVER / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_IMG + NIMG * C::IMG)[i] = make_uint4(0, 0, 0, 0);
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc05::mbar_expect_tx(b_full, C::B_BYTES);
+            tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
+        }
+    } else if (warp <= 3 || warp == 12) {
+        // ------------------------------------------------------------------ 4 MMA issuers
+        const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_IMG), C::PLANE, 128, tc05::SW_NONE);
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_B), 128, 256, tc05::SW_NONE);
+        bool ok = tc05::mbar_wait(b_full, 0, err);
+        TileRange it(a.B, C::TPI);
+        int b, t, lastb = -1;
+        uint32_t k = 0, use = 0, cnt = 0;
+        while (ok && it.next(b, t)) {
+            if (b != lastb) {
+                if (lastb >= 0) {
+                    if (tc05::elect_one()) tc05::mma_commit(img_empty + (k - 1) % NIMG);
+                    __syncwarp();
+                }
+                lastb = b;
+                ok = tc05::mbar_wait(img_full + k % NIMG, (k / NIMG) & 1, err);
+                ++k;
+            }
+            const uint32_t c = cnt++;
+            if ((c & 3) != w) continue;
+            const uint32_t acc = c % NACC, slot = (k - 1) % NIMG;
+            ok = ok && tc05::mbar_wait(t_empty + acc, ((use >> acc) & 1) ^ 1, err);
+            tc05::tc_fence_after();
+            if (ok && tc05::elect_one()) {
+                const uint64_t a0 = ad0 + (uint64_t)((slot * C::IMG + t * 128 * 16) >> 4);
+                const uint32_t d_tmem = tmem_base + acc * C::ACCW;
+#pragma unroll
+                for (int s = 0; s < C::NSTEP; ++s) {
+                    // window shift (ky', kx') pairs with the FLIPPED kernel tap (K-1-ky', K-1-kx')
+                    const int tp = s / C::CB, cb = s % C::CB;
+                    const int wstep = (KS * KS - 1 - tp) * C::CB + cb;
+                    tc05::mma_bf16(d_tmem, a0 + (uint64_t)(((tp / KS) * WP + tp % KS) + 2 * cb * (C::PLANE >> 4)),
+                                   bd0 + (uint64_t)(wstep * (C::B_STEP >> 4)), idesc, s > 0);
+                }
+                tc05::mma_commit(t_full + acc);
+            }
+            __syncwarp();
+            use ^= 1u << acc;
+        }
+        if (lastb >= 0) {
+            if (tc05::elect_one()) tc05::mma_commit(img_empty + (k - 1) % NIMG);
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ warps 4-11: build dYp of every image, warps 4-7 then drain the tiles
+        // Building is interleaved with the epilogue in program order: before the epilogue of the first tile of image
+        // k the builders have already produced image k+1 (NIMG = 2), so the issuers never wait for a gradient image.
+        const int tb = threadIdx.x - 128;                     // 0..255
+        const int ew = warp & 3;
+        auto build = [&](int bimg, uint32_t kimg) -> bool {
+            const uint32_t slot = kimg % NIMG;
+            if (!tc05::mbar_wait(img_empty + slot, ((kimg / NIMG) & 1) ^ 1, err)) return false;
+            uint8_t* img = smem + C::OFF_IMG + slot * C::IMG;
+            for (int i = tb; i < C::IMG / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            // routed, ReLU-masked gradient: one pooled element -> one position of the padded image
+            for (int i = tb; i < COUT * HP * HP; i += 256) {
+                const int wl = i % (HP * HP), co = i / (HP * HP);
+                const size_t g = ((size_t)bimg * COUT + co) * (HP * HP) + wl;
+                const float gv = a.aP[g] > 0.f ? a.gP[g] : 0.f;
+                const int pos = a.amax[g];
+                const int y = 2 * (wl / HP) + (pos >> 1) + (KS - 1), x = 2 * (wl % HP) + (pos & 1) + (KS - 1);
+                *reinterpret_cast<__nv_bfloat16*>(img + (co >> 3) * C::PLANE + (y * WP + x) * 16 + (co & 7) * 2) = __float2bfloat16_rn(gv);
+            }
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(img_full + slot);
+            return true;
+        };
+        TileRange it(a.B, C::TPI);
+        int b, t, lastb = -1, built_upto = -1;
+        const int b_first = it.i / C::TPI, b_last = it.hi > it.i ? (it.hi - 1) / C::TPI : -1;
+        uint32_t use = 0, cnt = 0;
+        bool ok = true;
+        while (ok && it.next(b, t)) {
+            if (b != lastb) {
+                lastb = b;
+                // keep one image ahead of the consumers
+                while (ok && built_upto < b + 1 && built_upto < b_last) {
+                    const int nb = built_upto < 0 ? b_first : built_upto + 1;
+                    ok = build(nb, (uint32_t)(nb - b_first));
+                    built_upto = nb;
+                }
+            }
+            const uint32_t c = cnt++;
+            const uint32_t acc = c % NACC, par = (use >> acc) & 1;
+            use ^= 1u << acc;
+            if (warp >= 8) continue;                          // warps 8-11 only build
+            ok = ok && tc05::mbar_wait(t_full + acc, par, err);
+            if (!ok) break;
+            tc05::tc_fence_after();
+            const int m = t * 128 + ew * 32 + lane;           // GEMM row inside the image
+            const int iy = m / WP, ix = m % WP;
+            const bool valid = m < C::MROWS && ix < HIN;
+#pragma unroll
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW + c0, v);
+                tc05::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a.gin[(((size_t)b * N + c0 + j) * HIN + iy) * HIN + ix] = v[j];
+                }
+            }
+            tc05::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(t_empty + acc);
+        }
+    }
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
+}
+
+using F2 = FCfg<16, 32, 5, 28, 12, 4, true>;      // conv2 forward: 6 tiles of 4 conv rows per image, P8 output for conv3
+using F3 = FCfg<32, 64, 4, 12, 4, 8, false>;      // conv3 forward: one tile per image, NHWC output for conv4's gather
+using D2 = DCfg<16, 32, 5, 28, 12>;
+using D3 = DCfg<32, 64, 4, 12, 4>;
+
+template <typename C>
+int launch_fwd(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
+    auto kern = sw_fwd_kernel<C>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
+    const int ntiles = c->batch * C::TPI;
+    int grid = bc::num_sms();
+    if (grid > ntiles) grid = ntiles;
+    FwdArgs args{(const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)wpk, c->params + ar.b[layer],
+                 c->act[layer], c->amax[layer], (__nv_bfloat16*)c->act_bf16[layer], c->batch, c->err_flag};
+    kern<<<grid, NTHREADS, C::SMEM_BYTES, s>>>(args);
+    BC_CUDA_LAUNCH_CHECK(name);
+    return BC_OK;
+}
+
+template <typename C>
+int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
+    auto kern = sw_dgrad_kernel<C>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const int ntiles = c->batch * C::TPI;
+    int grid = bc::num_sms();
+    if (grid > ntiles) grid = ntiles;
+    DgradArgs args{c->gact[layer], c->act[layer], c->amax[layer], (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag};
+    kern<<<grid, NTHREADS, C::SMEM_BYTES, s>>>(args);
+    BC_CUDA_LAUNCH_CHECK(name);
+    return BC_OK;
+}
+
+}  // namespace csw
+
+// layer 1 = conv2, layer 2 = conv3 (conv4 keeps the gather kernels of conv_tc.cu)
+int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream) {
+    return layer == 1 ? csw::launch_fwd<csw::F2>(c, 1, wpk, (cudaStream_t)stream, "conv2_sw_fwd_kernel")
+                      : csw::launch_fwd<csw::F3>(c, 2, wpk, (cudaStream_t)stream, "conv3_sw_fwd_kernel");
+}
+int bc_conv_sw_dgrad_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream) {
+    return layer == 1 ? csw::launch_dgrad<csw::D2>(c, 1, wpk, (cudaStream_t)stream, "conv2_sw_dgrad_kernel")
+                      : csw::launch_dgrad<csw::D3>(c, 2, wpk, (cudaStream_t)stream, "conv3_sw_dgrad_kernel");
+}

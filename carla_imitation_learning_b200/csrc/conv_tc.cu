@@ -421,7 +421,8 @@ struct WCfg {
     static constexpr int TMEM_COLS = N < 32 ? 32 : N;
 };
 
-template <typename C>
+// P8IN: `act` is stored [b][c/8][pixel][8] (the layout of the shifted-window kernels, conv_sw.cu) instead of NHWC
+template <typename C, bool P8IN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ dY, float* __restrict__ part,
                 int64_t seg_len, int64_t w_off, int64_t b_off, int B, int* err) {
@@ -521,8 +522,14 @@ wgrad_tc_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __re
                 if (pg < npix) {
                     if (step < NSTEP) {
                         const int b = pg / PPF, pl = pg % PPF;
-                        const uint4* p = reinterpret_cast<const uint4*>(act + (((size_t)b * HIN + pl / HD) * HIN + pl % HD) * CIN + toff);
-                        v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                        if constexpr (P8IN) {
+                            const size_t px = (size_t)(pl / HD + tap / KS) * HIN + (pl % HD + tap % KS);
+                            const uint4* p = reinterpret_cast<const uint4*>(act) + ((size_t)b * (CIN / 8) + 2 * cb) * (HIN * HIN) + px;
+                            v[q][0] = __ldg(p); v[q][1] = __ldg(p + HIN * HIN);
+                        } else {
+                            const uint4* p = reinterpret_cast<const uint4*>(act + (((size_t)b * HIN + pl / HD) * HIN + pl % HD) * CIN + toff);
+                            v[q][0] = __ldg(p); v[q][1] = __ldg(p + 1);
+                        }
                     } else if (step == NSTEP) {
                         v[q][0] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // bf16 1.0 x8
                         v[q][1] = v[q][0];
@@ -703,10 +710,10 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
 }  // namespace ctc
 
 namespace ctc {
-template <typename C>
+template <typename C, bool P8IN>
 int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
     using W = WCfg<C>;
-    auto kern = wgrad_tc_kernel<C>;
+    auto kern = wgrad_tc_kernel<C, P8IN>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W::SMEM_BYTES);
@@ -731,9 +738,9 @@ int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
                  "conv%d wgrad (tcgen05): null buffer", layer + 1);
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch_wgrad<ctc::L2>(c, 1, s, "conv2_wgrad_tc_kernel");
-    case 2: return ctc::launch_wgrad<ctc::L3>(c, 2, s, "conv3_wgrad_tc_kernel");
-    default: return ctc::launch_wgrad<ctc::L4>(c, 3, s, "conv4_wgrad_tc_kernel");
+    case 1: return ctc::launch_wgrad<ctc::L2, true>(c, 1, s, "conv2_wgrad_tc_kernel");    // act_bf16[0], [1] are P8 (conv_sw.cu)
+    case 2: return ctc::launch_wgrad<ctc::L3, true>(c, 2, s, "conv3_wgrad_tc_kernel");
+    default: return ctc::launch_wgrad<ctc::L4, false>(c, 3, s, "conv4_wgrad_tc_kernel");  // act_bf16[2] is NHWC
     }
 }
 
@@ -744,8 +751,8 @@ int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
     const uint8_t* base = (const uint8_t*)c->w_packed;
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch_dgrad<ctc::L2, 8, 3>(c, 1, base + kPackD2, s, "conv2_dgrad_tc_kernel");
-    case 2: return ctc::launch_dgrad<ctc::L3, 8, 3>(c, 2, base + kPackD3, s, "conv3_dgrad_tc_kernel");
+    case 1: return bc_conv_sw_dgrad_launch(c, 1, base + kPackD2, stream);   // shifted-window kernels build dY themselves
+    case 2: return bc_conv_sw_dgrad_launch(c, 2, base + kPackD3, stream);
     default: return ctc::launch_dgrad<ctc::L4, 4, 4>(c, 3, base + kPackD4, s, "conv4_dgrad_tc_kernel");
     }
 }
@@ -758,8 +765,8 @@ int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream) {
     const uint8_t* base = (const uint8_t*)c->w_packed;
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch<ctc::L2, 8, 3>(c, 1, base + kPackOff2, s, "conv2_tc_kernel");
-    case 2: return ctc::launch<ctc::L3, 8, 3>(c, 2, base + kPackOff3, s, "conv3_tc_kernel");
+    case 1: return bc_conv_sw_fwd_launch(c, 1, base + kPackOff2, stream);
+    case 2: return bc_conv_sw_fwd_launch(c, 2, base + kPackOff3, stream);
     default: return ctc::launch<ctc::L4, 4, 4>(c, 3, base + kPackOff4, s, "conv4_tc_kernel");
     }
 }

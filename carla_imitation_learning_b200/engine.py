@@ -119,7 +119,7 @@ class StepBuffers:
     loss: torch.Tensor
     ghead: Optional[torch.Tensor] = None
     gact: List[torch.Tensor] = field(default_factory=list)
-    act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: NHWC copies feeding the next layer's MMA
+    act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: bf16 copies feeding the next layer's MMA
     dy_bf16: Optional[torch.Tensor] = None                       # bf16 mode: un-pooled conv-output gradient scratch
     x_tp: Optional[torch.Tensor] = None                          # bf16 mode: the input as Toeplitz-ready planes
     x_tp_strides: tuple = (0, 0)                                 # (sample, channel) element strides into x_tp
@@ -168,7 +168,11 @@ class BCEngine:
         elif (self.conv_mode & 1) and self.obs_size == 4 and batch:
             bufs.x_tp, bufs.x_tp_strides = self.to_tp(x)
         if self.conv_mode & 1:
-            bufs.act_bf16 = [torch.empty((batch, s[1], s[2], s[0]), dtype=torch.bfloat16, device=dev) for s in ACT_SHAPES[:3]]
+            # bf16 copies feeding the next layer's MMAs: act1, act2 as P8 = (B, C/8, H*W, 8) for the shifted-window
+            # kernels (csrc/conv_sw.cu), act3 as NHWC for conv4's gather
+            bufs.act_bf16 = [torch.empty((batch, 2, 784, 8), dtype=torch.bfloat16, device=dev),
+                             torch.empty((batch, 4, 144, 8), dtype=torch.bfloat16, device=dev),
+                             torch.empty((batch, 4, 4, 64), dtype=torch.bfloat16, device=dev)]
         if backward:
             self._alloc_bwd(bufs)
         return bufs

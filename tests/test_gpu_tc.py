@@ -89,9 +89,24 @@ def test_bf16_mode_training_step_within_tolerance():
     assert rel(eng.grads, g32) <= 0.1      # includes pool-routing flips caused by the bf16 rounding
 
 
+def _to_act_bf16(x_nchw, idx):
+    """NCHW -> the layout of bufs.act_bf16[idx]: P8 (B, C/8, H*W, 8) for act1/act2, NHWC for act3."""
+    B, Cc, Hh, Ww = x_nchw.shape
+    if idx == 2:
+        return x_nchw.permute(0, 2, 3, 1).contiguous()
+    return x_nchw.reshape(B, Cc // 8, 8, Hh * Ww).permute(0, 1, 3, 2).contiguous()
+
+
+def _from_act_bf16(t, idx, shape):
+    B, Cc, Hh, Ww = shape
+    if idx == 2:
+        return t.permute(0, 3, 1, 2)
+    return t.permute(0, 1, 3, 2).reshape(B, Cc, Hh, Ww)
+
+
 @pytest.mark.parametrize("layer,B", [(1, 3), (1, 37), (2, 5), (2, 1), (3, 33), (3, 1), (3, 70)])
 def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
-    """conv2/3/4 + ReLU + pool as tcgen05 implicit GEMMs over NHWC bf16 activations."""
+    """conv2/3 + ReLU + pool as shifted-window tcgen05 GEMMs over P8 bf16 activations, conv4 as a gathered implicit GEMM."""
     import ctypes as C
     from carla_imitation_learning_b200 import _lib
     from oracle import bc_oracle as O
@@ -110,7 +125,7 @@ def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
     gen = torch.Generator().manual_seed(7 * layer + B)
     xin = (torch.rand((B, cin, hin, hin), generator=gen) - 0.3).to(torch.bfloat16)
     bufs = eng.alloc(B, torch.zeros(B, 4, 256, 256, device=dev, dtype=torch.bfloat16), None, False)
-    bufs.act_bf16[layer - 1].copy_(xin.permute(0, 2, 3, 1).contiguous().to(dev))
+    bufs.act_bf16[layer - 1].copy_(_to_act_bf16(xin, layer - 1).to(dev))
     c = eng.ctx(bufs)
     _lib.check(eng.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, torch.cuda.current_stream().cuda_stream), "conv tc")
     torch.cuda.synchronize()
@@ -123,8 +138,8 @@ def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
     assert err <= 1e-5, err
     _check_routing(z, bufs.amax[layer].cpu(), got, 2)
     if layer < 3:   # the NHWC bf16 copy handed to the next layer
-        nhwc = bufs.act_bf16[layer].float().cpu().permute(0, 3, 1, 2)
-        assert torch.equal(nhwc, bufs.act[layer].cpu().to(torch.bfloat16).float())
+        back = _from_act_bf16(bufs.act_bf16[layer].float().cpu(), layer, bufs.act[layer].shape)
+        assert torch.equal(back, bufs.act[layer].cpu().to(torch.bfloat16).float())
 
 
 @pytest.mark.parametrize("B", [2, 37])
@@ -318,7 +333,7 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
             xin = x.double().cpu()
             stride = 3
         else:
-            xin = bufs.act_bf16[layer - 1].double().cpu().permute(0, 3, 1, 2)
+            xin = _from_act_bf16(bufs.act_bf16[layer - 1].double().cpu(), layer - 1, bufs.act[layer - 1].shape)
             stride = 1
         k = w.shape[-1]
         cols = F.unfold(xin, kernel_size=k, stride=stride)                       # (B, Cin*k*k, L) over the full conv map
