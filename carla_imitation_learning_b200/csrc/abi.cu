@@ -110,7 +110,7 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
     if (rc) return rc;
     const bool tc = (c->conv_mode & 6) && c->dy_bf16 && c->act_bf16[0];
     for (int l = 3; l >= 1; --l) {
-        if (tc) {   // one unpool feeds both the tensor-core wgrad and dgrad of the layer
+        if (tc && l == 3) {   // conv4: one unpool feeds both the gathered wgrad and dgrad (conv2/conv3 build dY inside their kernels)
             if ((rc = bc_unpool_launch(c, l, stream))) return rc;
             bc_tc_set_dy_ready(true);
         }

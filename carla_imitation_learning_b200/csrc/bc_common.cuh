@@ -16,6 +16,7 @@ int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 int bc_unpool_launch(const bc_ctx* c, int layer, void* stream);
 int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);     // conv_sw.cu (layers 1, 2)
 int bc_conv_sw_dgrad_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);
+int bc_conv_sw_wgrad_launch(const bc_ctx* c, int layer, void* stream);
 void bc_tc_set_dy_ready(bool v);
 size_t bc_conv_tc_pack_total();
 
@@ -72,7 +73,7 @@ __host__ inline Arena arena_layout(int obs, int na) {
 
 // partial-sum workspace: per segment, NPART[seg] copies of seg_len floats, then loss partials
 constexpr int kHeadBlocks = 128;    // partial copies of the head segment (= head CTAs: 2 samples each at B=256)
-constexpr int kWgradParts[4] = {296, 37, 36, 8};  // conv1..conv4: partial-sum slots = grid.x of the wgrad kernels
+constexpr int kWgradParts[4] = {296, 29, 37, 8};  // conv1..conv4: partial-sum slots = grid.x of the wgrad kernels (conv2: x 5 kernel rows = 145 CTAs, conv3: x 4 = 148)
 struct Partials { int64_t off[5]; int nparts[5]; int64_t loss_off; int64_t total; };
 __host__ inline Partials partials_layout(const Arena& a) {
     Partials p{};

@@ -45,6 +45,40 @@ struct TileRange {
     }
 };
 
+
+// The routed gradient of one image, fetched into registers first (all loads of an image in flight at once, and issued
+// one image ahead of its use) and scattered into a shared-memory image later: NE elements per thread of 256.
+template <int COUT, int HP>
+struct PooledGrad {
+    static constexpr int TOTAL = COUT * HP * HP, NE = (TOTAL + 255) / 256;
+    float g[NE]; uint8_t pos[NE];
+    __device__ __forceinline__ void load(const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax, int b, int tb) {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            const int i = tb + 256 * j;
+            if (TOTAL % 256 == 0 || i < TOTAL) {
+                const size_t o = (size_t)b * TOTAL + i;          // (co, pooled pixel) in memory order
+                const float av = __ldg(aP + o), gv = __ldg(gP + o);
+                pos[j] = __ldg(amax + o);
+                g[j] = av > 0.f ? gv : 0.f;
+            }
+        }
+    }
+    // pix(py, px, dy, dx) -> pixel index inside one 8-channel plane of the target image; plane = bytes per plane
+    template <typename F>
+    __device__ __forceinline__ void scatter(uint8_t* img, int plane, int tb, F&& pix) const {
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            const int i = tb + 256 * j;
+            if (TOTAL % 256 == 0 || i < TOTAL) {
+                const int wl = i % (HP * HP), co = i / (HP * HP);
+                const int m = pix(wl / HP, wl % HP, pos[j] >> 1, pos[j] & 1);
+                *reinterpret_cast<__nv_bfloat16*>(img + (co >> 3) * plane + m * 16 + (co & 7) * 2) = __float2bfloat16_rn(g[j]);
+            }
+        }
+    }
+};
+
 // ================================================================================================ forward
 template <int CIN_, int COUT_, int KS_, int HIN_, int HP_, int RT_, bool OUT_P8_>
 struct FCfg {
@@ -384,24 +418,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
         // k the builders have already produced image k+1 (NIMG = 2), so the issuers never wait for a gradient image.
         const int tb = threadIdx.x - 128;                     // 0..255
         const int ew = warp & 3;
-        auto build = [&](int bimg, uint32_t kimg) -> bool {
+        PooledGrad<COUT, HP> pg;
+        auto build = [&](int bimg, uint32_t kimg, int bnext) -> bool {      // pg holds image bimg; fetches bnext (if >= 0) afterwards
             const uint32_t slot = kimg % NIMG;
             if (!tc05::mbar_wait(img_empty + slot, ((kimg / NIMG) & 1) ^ 1, err)) return false;
             uint8_t* img = smem + C::OFF_IMG + slot * C::IMG;
             for (int i = tb; i < C::IMG / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
             asm volatile("bar.sync 3, 256;" ::: "memory");
             // routed, ReLU-masked gradient: one pooled element -> one position of the padded image
-            for (int i = tb; i < COUT * HP * HP; i += 256) {
-                const int wl = i % (HP * HP), co = i / (HP * HP);
-                const size_t g = ((size_t)bimg * COUT + co) * (HP * HP) + wl;
-                const float gv = a.aP[g] > 0.f ? a.gP[g] : 0.f;
-                const int pos = a.amax[g];
-                const int y = 2 * (wl / HP) + (pos >> 1) + (KS - 1), x = 2 * (wl % HP) + (pos & 1) + (KS - 1);
-                *reinterpret_cast<__nv_bfloat16*>(img + (co >> 3) * C::PLANE + (y * WP + x) * 16 + (co & 7) * 2) = __float2bfloat16_rn(gv);
-            }
+            pg.scatter(img, C::PLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy + (KS - 1)) * WP + 2 * px + dx + (KS - 1); });
             tc05::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc05::mbar_arrive(img_full + slot);
+            if (bnext >= 0) pg.load(a.gP, a.aP, a.amax, bnext, tb);
             return true;
         };
         TileRange it(a.B, C::TPI);
@@ -409,13 +438,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
         const int b_first = it.i / C::TPI, b_last = it.hi > it.i ? (it.hi - 1) / C::TPI : -1;
         uint32_t use = 0, cnt = 0;
         bool ok = true;
+        if (b_last >= 0) pg.load(a.gP, a.aP, a.amax, b_first, tb);
         while (ok && it.next(b, t)) {
             if (b != lastb) {
                 lastb = b;
                 // keep one image ahead of the consumers
                 while (ok && built_upto < b + 1 && built_upto < b_last) {
                     const int nb = built_upto < 0 ? b_first : built_upto + 1;
-                    ok = build(nb, (uint32_t)(nb - b_first));
+                    ok = build(nb, (uint32_t)(nb - b_first), nb < b_last ? nb + 1 : -1);
                     built_upto = nb;
                 }
             }
@@ -449,10 +479,213 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
     if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
 }
 
+// ================================================================================================ wgrad
+//   dW[co][ci][ky][kx] = sum_{b, m = oy*W_in + ox}  X[b][m + ky*W_in + kx][ci] * dY[b][m][co]
+// Both operands MN-major, K = pixels m (16 per instruction). The A operand of (ky, 8-channel group cg) is the input
+// image of plane cg seen through a descriptor whose M-cores are 16 B apart: core kx' = the same pixels shifted by kx'
+// (SBO = 16 B, LBO = 128 B) -- 16 horizontal taps per instruction, of which KS are real (rows (kx' >= KS) are ignored).
+// B = the routed gradient in the SAME linear pixel order, [co/8][m][8], built in shared memory per image; its columns
+// ox >= W_out are zero, so the wrapped pixels of A meet zeros. One accumulator per (ky, cg) lives in TMEM for the whole
+// kernel: grid = (partial-sum slots, KS): CTA (p, ky) owns kernel row ky for the images of slot p. Class ky = 0 also
+// produces the bias gradient: its builder threads keep a running f32 sum per (co, pooled pixel) and fold the pixels
+// in a fixed order at the end (deterministic; the f32 values are summed before their bf16 rounding).
+template <int CIN_, int COUT_, int KS_, int HIN_, int HP_>
+struct WCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, HIN = HIN_, HP = HP_;
+    static constexpr int CG = CIN / 8, CGO = COUT / 8;
+    static constexpr int MPIX = 2 * HP * HIN;               // linear pixels of the pooled conv region (pitch W_in)
+    static constexpr int NKS = MPIX / 16;                   // K-steps per image
+    static constexpr int XPLANE = HIN * HIN * 16, XIMG = CG * XPLANE;
+    static constexpr int DPLANE = MPIX * 16, DIMG = CGO * DPLANE;
+    static constexpr int NIMG = 2;
+    static constexpr int ACCW = COUT < 32 ? 32 : COUT;
+    static constexpr int NACC = CG;
+    static constexpr int OFF_X = 0;
+    static constexpr int XSLOT = (XIMG + 1023) / 1024 * 1024;
+    static constexpr int OFF_XPAD = OFF_X + NIMG * XSLOT;   // over-read of the shifted windows of the last plane
+    static constexpr int OFF_D = OFF_XPAD + 1024;
+    static constexpr int DSLOT = (DIMG + 1023) / 1024 * 1024;
+    static constexpr int OFF_BAR = OFF_D + NIMG * DSLOT;
+    static constexpr int NBAR = 4 * NIMG + 1;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+    static_assert(MPIX % 16 == 0, "K-steps of 16 pixels");
+    static_assert(NACC * ACCW <= 512, "TMEM columns");
+    static_assert((MPIX + (KS - 1) * HIN + 16) * 16 <= XPLANE + 1024, "over-read pad");
+    static_assert(COUT * HP * HP * 4 <= NIMG * DSLOT, "the bias fold reuses the gradient slots");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+};
+
+struct WgradArgs {
+    const __nv_bfloat16* x;                                  // P8 bf16 input activations of the layer
+    const float* gP; const float* aP; const uint8_t* amax;   // pooled gradient, pooled activation, argmax of the layer's output
+    float* part; int64_t seg_len, w_off, b_off;              // partial-sum slots (one per blockIdx.x), arena offsets inside a slot
+    int B; int* err;
+};
+
+template <typename C>
+__global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a) {
+    constexpr int CIN = C::CIN, COUT = C::COUT, KS = C::KS, HIN = C::HIN, HP = C::HP, NIMG = C::NIMG, CG = C::CG, NKS = C::NKS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* x_full = bars;                     // [NIMG]
+    uint64_t* x_empty = bars + NIMG;             // [NIMG]  4 issuers
+    uint64_t* d_full = bars + 2 * NIMG;          // [NIMG]  8 builder warps
+    uint64_t* d_empty = bars + 3 * NIMG;         // [NIMG]  4 issuers
+    uint64_t* done = bars + 4 * NIMG;            //         4 issuers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ky = blockIdx.y;
+    int* err = a.err;
+    // images of this partial-sum slot: a contiguous balanced range
+    const int b_lo = (int)((long long)a.B * blockIdx.x / gridDim.x), b_hi = (int)((long long)a.B * (blockIdx.x + 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NIMG; ++i) {
+            tc05::mbar_init(x_full + i, 1); tc05::mbar_init(x_empty + i, 4);
+            tc05::mbar_init(d_full + i, 8); tc05::mbar_init(d_empty + i, 4);
+        }
+        tc05::mbar_init(done, 4);
+        tc05::mbar_fence_init();
+    }
+    if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
+    // the shifted windows of valid rows run up to KS-1 pixels past the last plane of an image; those pixels meet zero
+    // columns of dY, so they only have to be finite: start from an all-zero input region (slots, gaps and pad)
+    for (int i = threadIdx.x; i < (C::OFF_D - C::OFF_X) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_X)[i] = make_uint4(0, 0, 0, 0);
+    tc05::fence_async_smem();
+    tc05::tc_fence_before();
+    __syncthreads();
+    tc05::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ loader: the input image, one bulk copy
+        if (lane == 0) {
+            uint32_t k = 0;
+            for (int b = b_lo; b < b_hi; ++b, ++k) {
+                const uint32_t slot = k % NIMG;
+                if (!tc05::mbar_wait(x_empty + slot, ((k / NIMG) & 1) ^ 1, err)) break;
+                tc05::mbar_expect_tx(x_full + slot, C::XIMG);
+                tc05::bulk_g2s(smem + C::OFF_X + slot * C::XSLOT, reinterpret_cast<const uint8_t*>(a.x) + (size_t)b * C::XIMG, C::XIMG, x_full + slot);
+            }
+        }
+    } else if (warp <= 3 || warp == 12) {
+        // ------------------------------------------------------------------ issuer w owns the accumulators acc % 4 == w (acc = cg)
+        const int w = warp == 12 ? 0 : warp;
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, COUT, 1, 1);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_X), 128, 16, tc05::SW_NONE);       // M-cores = pixel shifts
+        const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_D), 128, C::DPLANE, tc05::SW_NONE);
+        bool ok = true, first = true;
+        uint32_t k = 0;
+        for (int b = b_lo; ok && b < b_hi; ++b, ++k) {
+            const uint32_t slot = k % NIMG, ph = (k / NIMG) & 1;
+            ok = tc05::mbar_wait(x_full + slot, ph, err) && tc05::mbar_wait(d_full + slot, ph, err);
+            tc05::tc_fence_after();
+            if (ok && tc05::elect_one()) {
+                const uint64_t bs = bd0 + (uint64_t)((slot * C::DSLOT) >> 4);
+                for (int acc = w; acc < C::NACC; acc += 4) {
+                    const uint64_t as = ad0 + (uint64_t)((slot * C::XSLOT + acc * C::XPLANE + ky * HIN * 16) >> 4);
+                    const uint32_t d_tmem = tmem_base + acc * C::ACCW;
+#pragma unroll 1
+                    for (int u0 = 0; u0 < NKS; u0 += 6) {
+#pragma unroll
+                        for (int u = 0; u < 6; ++u)
+                            if (u0 + u < NKS)
+                                tc05::mma_bf16(d_tmem, as + (uint64_t)((u0 + u) * 16), bs + (uint64_t)((u0 + u) * 16), idesc, (first && u0 + u == 0) ? 0u : 1u);
+                    }
+                }
+                tc05::mma_commit(x_empty + slot);
+                tc05::mma_commit(d_empty + slot);
+            }
+            __syncwarp();
+            first = false;
+        }
+        if (tc05::elect_one()) tc05::mma_commit(done);
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ warps 4-11: build the routed gradient of every image; warps 4-7 then write the partial
+        const int tb = threadIdx.x - 128;
+        const int ew = warp & 3;
+        bool ok = true;
+        uint32_t k = 0;
+        PooledGrad<COUT, HP> pg;
+        float bsum[PooledGrad<COUT, HP>::NE];                 // class 0: running sum of every (co, pooled pixel) this thread owns
+#pragma unroll
+        for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j) bsum[j] = 0.f;
+        if (b_lo < b_hi) pg.load(a.gP, a.aP, a.amax, b_lo, tb);
+        for (int b = b_lo; ok && b < b_hi; ++b, ++k) {
+            const uint32_t slot = k % NIMG;
+            ok = tc05::mbar_wait(d_empty + slot, ((k / NIMG) & 1) ^ 1, err);
+            if (!ok) break;
+            uint8_t* img = smem + C::OFF_D + slot * C::DSLOT;
+            for (int i = tb; i < C::DIMG / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            pg.scatter(img, C::DPLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy) * HIN + 2 * px + dx; });
+            if (ky == 0) {
+#pragma unroll
+                for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j)
+                    if (PooledGrad<COUT, HP>::TOTAL % 256 == 0 || tb + 256 * j < PooledGrad<COUT, HP>::TOTAL) bsum[j] += pg.g[j];
+            }
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(d_full + slot);
+            if (b + 1 < b_hi) pg.load(a.gP, a.aP, a.amax, b + 1, tb);
+        }
+        const bool okd = ok && tc05::mbar_wait(done, 0, err);   // every MMA has completed: the gradient slots are free
+        tc05::tc_fence_after();
+        float* dst = a.part + (size_t)blockIdx.x * a.seg_len;
+        if (ky == 0) {
+            // ---- bias gradient: element sums -> smem in (co, pooled pixel) order -> one thread per channel folds its pixels
+            float* bs = reinterpret_cast<float*>(smem + C::OFF_D);
+#pragma unroll
+            for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j)
+                if (PooledGrad<COUT, HP>::TOTAL % 256 == 0 || tb + 256 * j < PooledGrad<COUT, HP>::TOTAL) bs[tb + 256 * j] = bsum[j];
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (tb < COUT) {
+                float acc = 0.f;
+                for (int i = 0; i < HP * HP; ++i) acc += bs[tb * (HP * HP) + i];
+                dst[a.b_off + tb] = acc;
+            }
+        }
+        if (warp >= 8) goto fin;
+        // ---- epilogue: D[cg] row (kx', ci8), column co -> dW[co][8 cg + ci8][ky][kx']
+        {
+            const bool any = b_hi > b_lo;
+            if (okd) {
+                const int row = ew * 32 + lane, kx = row >> 3, ci8 = row & 7;
+#pragma unroll 1
+                for (int acc = 0; acc < C::NACC; ++acc) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < COUT; c0 += 16) {
+                        float v[16];
+                        if (any) {
+                            tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW + c0, v);
+                            tc05::tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = 0.f;      // a slot without images contributes zeros
+                        }
+                        if (kx < KS) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                dst[a.w_off + (((size_t)(c0 + j) * CIN + acc * 8 + ci8) * KS + ky) * KS + kx] = v[j];
+                        }
+                    }
+                }
+            }
+        }
+    }
+fin:
+    tc05::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
+}
+
 using F2 = FCfg<16, 32, 5, 28, 12, 4, true>;      // conv2 forward: 6 tiles of 4 conv rows per image, P8 output for conv3
 using F3 = FCfg<32, 64, 4, 12, 4, 8, false>;      // conv3 forward: one tile per image, NHWC output for conv4's gather
 using D2 = DCfg<16, 32, 5, 28, 12>;
 using D3 = DCfg<32, 64, 4, 12, 4>;
+using W2 = WCfg<16, 32, 5, 28, 12>;
+using W3 = WCfg<32, 64, 4, 12, 4>;
 
 template <typename C>
 int launch_fwd(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
@@ -492,7 +725,31 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
     return BC_OK;
 }
 
+template <typename C>
+int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
+    auto kern = sw_wgrad_kernel<C>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
+        configured = true;
+    }
+    const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
+    const bc::Partials pl = bc::partials_layout(ar);
+    const int seg = 4 - layer;
+    WgradArgs args{(const __nv_bfloat16*)c->act_bf16[layer - 1], c->gact[layer], c->act[layer], c->amax[layer],
+                   c->partials + pl.off[seg], ar.seg_len[seg], ar.w[layer] - ar.seg_off[seg], ar.b[layer] - ar.seg_off[seg], c->batch, c->err_flag};
+    kern<<<dim3(bc::kWgradParts[layer], C::KS), NTHREADS, C::SMEM_BYTES, s>>>(args);
+    BC_CUDA_LAUNCH_CHECK(name);
+    return BC_OK;
+}
+
 }  // namespace csw
+
+int bc_conv_sw_wgrad_launch(const bc_ctx* c, int layer, void* stream) {
+    return layer == 1 ? csw::launch_wgrad<csw::W2>(c, 1, (cudaStream_t)stream, "conv2_sw_wgrad_kernel")
+                      : csw::launch_wgrad<csw::W3>(c, 2, (cudaStream_t)stream, "conv3_sw_wgrad_kernel");
+}
 
 // layer 1 = conv2, layer 2 = conv3 (conv4 keeps the gather kernels of conv_tc.cu)
 int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream) {

@@ -738,8 +738,8 @@ int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream) {
                  "conv%d wgrad (tcgen05): null buffer", layer + 1);
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
-    case 1: return ctc::launch_wgrad<ctc::L2, true>(c, 1, s, "conv2_wgrad_tc_kernel");    // act_bf16[0], [1] are P8 (conv_sw.cu)
-    case 2: return ctc::launch_wgrad<ctc::L3, true>(c, 2, s, "conv3_wgrad_tc_kernel");
+    case 1: return bc_conv_sw_wgrad_launch(c, 1, stream);    // shifted-window kernels (conv_sw.cu) build dY themselves
+    case 2: return bc_conv_sw_wgrad_launch(c, 2, stream);
     default: return ctc::launch_wgrad<ctc::L4, false>(c, 3, s, "conv4_wgrad_tc_kernel");  // act_bf16[2] is NHWC
     }
 }

@@ -284,13 +284,13 @@ def test_bf16_module_path_trains_like_the_reference(golden_dir):
 
 
 def _dense_dy(gP, aP, amax, p, hc):
-    """Routed, ReLU-masked conv-output gradient (f64), rounded to bf16 like unpool_kernel / the conv1 dY builder."""
+    """Routed, ReLU-masked conv-output gradient (f64): rounded to bf16 like the dY builders of the kernels, and unrounded."""
     B, Cc, Hp, Wp = gP.shape
     g = torch.where(aP > 0, gP, torch.zeros_like(gP)).double()
     oh = torch.nn.functional.one_hot(amax.long(), p * p).double() * g[..., None]
     dy = torch.zeros(B, Cc, hc, hc, dtype=torch.float64)
     dy[..., :Hp * p, :Wp * p] = oh.reshape(B, Cc, Hp, Wp, p, p).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, Hp * p, Wp * p)
-    return dy.to(torch.bfloat16).double()
+    return dy.to(torch.bfloat16).double(), dy
 
 
 @pytest.mark.parametrize("B", [3, 37])
@@ -327,7 +327,7 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
         if layer > 0:
             _lib.check(eng.lib.bc_conv_bwd_dgrad(C.byref(c), layer, s), "dgrad")
         torch.cuda.synchronize()
-        dy = _dense_dy(gP.cpu(), bufs.act[layer].cpu(), bufs.amax[layer].cpu(), pool[layer], hc[layer])
+        dy, dy_f32 = _dense_dy(gP.cpu(), bufs.act[layer].cpu(), bufs.amax[layer].cpu(), pool[layer], hc[layer])
         w = params[f"{names[layer]}.weight"].detach().cpu()
         if layer == 0:
             xin = x.double().cpu()
@@ -339,7 +339,8 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
         cols = F.unfold(xin, kernel_size=k, stride=stride)                       # (B, Cin*k*k, L) over the full conv map
         L_used = dy.shape[-1]
         ref_w = torch.einsum("bol,bkl->ok", dy.reshape(B, dy.shape[1], -1), cols).reshape(w.shape)
-        ref_b = dy.sum(dim=(0, 2, 3))
+        # conv2/conv3 (shifted-window wgrad) fold the f32 gradient before its bf16 rounding; conv1/conv4 use a ones row of the GEMM
+        ref_b = (dy_f32 if layer in (1, 2) else dy).sum(dim=(0, 2, 3))
         pw, pb = params[f"{names[layer]}.weight"], params[f"{names[layer]}.bias"]
         got_w = eng.grads[pw._bc_offset:pw._bc_offset + pw.numel()].view(w.shape).cpu().double()
         got_b = eng.grads[pb._bc_offset:pb._bc_offset + pb.numel()].cpu().double()
