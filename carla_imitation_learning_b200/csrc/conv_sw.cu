@@ -46,34 +46,52 @@ struct TileRange {
 };
 
 
-// The routed gradient of one image, fetched into registers first (all loads of an image in flight at once, and issued
-// one image ahead of its use) and scattered into a shared-memory image later: NE elements per thread of 256.
+// The routed gradient of one image, fetched into registers first (all loads of an image in flight at once, issued one
+// image ahead of its use) and written into a shared-memory image later. One unit = (pool window, 8-channel group): its
+// 2x2 conv pixels x 8 channels are four full 16 B stores (zeros except the routed position of each channel), so the
+// pooled region of the image is REWRITTEN completely for every image and only needs zeroing once per kernel; pixels
+// outside the pooled region (zero border / unused columns) are never written and stay zero.
 template <int COUT, int HP>
 struct PooledGrad {
-    static constexpr int TOTAL = COUT * HP * HP, NE = (TOTAL + 255) / 256;
-    float g[NE]; uint8_t pos[NE];
+    static constexpr int NU = HP * HP * (COUT / 8), NE = (NU + 255) / 256;     // units per image, per thread of 256
+    float g[NE][8]; uint32_t pos[NE];                                          // 8 x 2-bit window positions per unit
+    __device__ __forceinline__ static bool has(int j, int tb) { return NU % 256 == 0 || tb + 256 * j < NU; }
     __device__ __forceinline__ void load(const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax, int b, int tb) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
-            const int i = tb + 256 * j;
-            if (TOTAL % 256 == 0 || i < TOTAL) {
-                const size_t o = (size_t)b * TOTAL + i;          // (co, pooled pixel) in memory order
-                const float av = __ldg(aP + o), gv = __ldg(gP + o);
-                pos[j] = __ldg(amax + o);
-                g[j] = av > 0.f ? gv : 0.f;
+            if (has(j, tb)) {
+                const int i = tb + 256 * j, wl = i % (HP * HP), cg = i / (HP * HP);
+                const size_t o = ((size_t)b * COUT + cg * 8) * (HP * HP) + wl;   // lanes run along the pooled pixels: coalesced per channel
+                uint32_t pk = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float av = __ldg(aP + o + k * (HP * HP)), gv = __ldg(gP + o + k * (HP * HP));
+                    pk |= (uint32_t)__ldg(amax + o + k * (HP * HP)) << (2 * k);
+                    g[j][k] = av > 0.f ? gv : 0.f;
+                }
+                pos[j] = pk;
             }
         }
     }
     // pix(py, px, dy, dx) -> pixel index inside one 8-channel plane of the target image; plane = bytes per plane
     template <typename F>
-    __device__ __forceinline__ void scatter(uint8_t* img, int plane, int tb, F&& pix) const {
+    __device__ __forceinline__ void store(uint8_t* img, int plane, int tb, F&& pix) const {
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
-            const int i = tb + 256 * j;
-            if (TOTAL % 256 == 0 || i < TOTAL) {
-                const int wl = i % (HP * HP), co = i / (HP * HP);
-                const int m = pix(wl / HP, wl % HP, pos[j] >> 1, pos[j] & 1);
-                *reinterpret_cast<__nv_bfloat16*>(img + (co >> 3) * plane + m * 16 + (co & 7) * 2) = __float2bfloat16_rn(g[j]);
+            if (has(j, tb)) {
+                const int i = tb + 256 * j, wl = i % (HP * HP), cg = i / (HP * HP);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float lo = ((pos[j] >> (4 * k)) & 3u) == (uint32_t)p ? g[j][2 * k] : 0.f;
+                        const float hi = ((pos[j] >> (4 * k + 2)) & 3u) == (uint32_t)p ? g[j][2 * k + 1] : 0.f;
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                        w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(img + cg * plane + pix(wl / HP, wl % HP, p >> 1, p & 1) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             }
         }
     }
@@ -355,7 +373,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
         tc05::mbar_fence_init();
     }
     if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
-    for (int i = threadIdx.x; i < C::OVER / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_IMG + NIMG * C::IMG)[i] = make_uint4(0, 0, 0, 0);
+    // gradient slots start as zeros: the builders rewrite the pooled region of a slot for every image, the zero border never changes
+    for (int i = threadIdx.x; i < (NIMG * C::IMG + C::OVER) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_IMG)[i] = make_uint4(0, 0, 0, 0);
     tc05::fence_async_smem();
     tc05::tc_fence_before();
     __syncthreads();
@@ -423,10 +442,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
             const uint32_t slot = kimg % NIMG;
             if (!tc05::mbar_wait(img_empty + slot, ((kimg / NIMG) & 1) ^ 1, err)) return false;
             uint8_t* img = smem + C::OFF_IMG + slot * C::IMG;
-            for (int i = tb; i < C::IMG / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            // routed, ReLU-masked gradient: one pooled element -> one position of the padded image
-            pg.scatter(img, C::PLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy + (KS - 1)) * WP + 2 * px + dx + (KS - 1); });
+            // routed, ReLU-masked gradient: one pool window x 8 channels -> its four pixels of the padded image
+            pg.store(img, C::PLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy + (KS - 1)) * WP + 2 * px + dx + (KS - 1); });
             tc05::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc05::mbar_arrive(img_full + slot);
@@ -550,7 +567,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
     if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
     // the shifted windows of valid rows run up to KS-1 pixels past the last plane of an image; those pixels meet zero
     // columns of dY, so they only have to be finite: start from an all-zero input region (slots, gaps and pad)
-    for (int i = threadIdx.x; i < (C::OFF_D - C::OFF_X) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_X)[i] = make_uint4(0, 0, 0, 0);
+    // (the gradient slots too: their pooled region is rewritten for every image, the unused columns stay zero)
+    for (int i = threadIdx.x; i < C::OFF_BAR / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     tc05::fence_async_smem();
     tc05::tc_fence_before();
     __syncthreads();
@@ -608,22 +626,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
         bool ok = true;
         uint32_t k = 0;
         PooledGrad<COUT, HP> pg;
-        float bsum[PooledGrad<COUT, HP>::NE];                 // class 0: running sum of every (co, pooled pixel) this thread owns
+        float bsum[PooledGrad<COUT, HP>::NE][8];              // class 0: running sum of every (co, pooled pixel) this thread owns
 #pragma unroll
-        for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j) bsum[j] = 0.f;
+        for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) bsum[j][q] = 0.f;
         if (b_lo < b_hi) pg.load(a.gP, a.aP, a.amax, b_lo, tb);
         for (int b = b_lo; ok && b < b_hi; ++b, ++k) {
             const uint32_t slot = k % NIMG;
             ok = tc05::mbar_wait(d_empty + slot, ((k / NIMG) & 1) ^ 1, err);
             if (!ok) break;
             uint8_t* img = smem + C::OFF_D + slot * C::DSLOT;
-            for (int i = tb; i < C::DIMG / 16; i += 256) reinterpret_cast<uint4*>(img)[i] = make_uint4(0, 0, 0, 0);
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            pg.scatter(img, C::DPLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy) * HIN + 2 * px + dx; });
+            pg.store(img, C::DPLANE, tb, [](int py, int px, int dy, int dx) { return (2 * py + dy) * HIN + 2 * px + dx; });
             if (ky == 0) {
 #pragma unroll
                 for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j)
-                    if (PooledGrad<COUT, HP>::TOTAL % 256 == 0 || tb + 256 * j < PooledGrad<COUT, HP>::TOTAL) bsum[j] += pg.g[j];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bsum[j][q] += pg.g[j][q];
             }
             tc05::fence_async_smem();
             __syncwarp();
@@ -638,7 +657,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
             float* bs = reinterpret_cast<float*>(smem + C::OFF_D);
 #pragma unroll
             for (int j = 0; j < PooledGrad<COUT, HP>::NE; ++j)
-                if (PooledGrad<COUT, HP>::TOTAL % 256 == 0 || tb + 256 * j < PooledGrad<COUT, HP>::TOTAL) bs[tb + 256 * j] = bsum[j];
+                if (PooledGrad<COUT, HP>::has(j, tb)) {
+                    const int i = tb + 256 * j, wl = i % (HP * HP), cg = i / (HP * HP);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) bs[(cg * 8 + q) * (HP * HP) + wl] = bsum[j][q];
+                }
             asm volatile("bar.sync 3, 256;" ::: "memory");
             if (tb < COUT) {
                 float acc = 0.f;
