@@ -27,6 +27,7 @@ UNIT = "frames/s"
 FLOPS_FWD = (44255232, 14745600, 5308416, 589824)          # SURVEY 8(d), per frame, conv1..4
 FLOPS_TRAIN = 150505152
 FRAME_BYTES = 256 * 256 * 3
+TRAFFIC_CONV1_TP = 45412864        # dram__bytes_read.sum + dram__bytes_write.sum of conv1_tp_kernel at B=256 (profiles/r1e_ncu_full_conv1_fwd_wgrad_stage_raw.csv)
 
 
 def load_peaks():
@@ -389,13 +390,16 @@ def run_b200(args):
                                     else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_burst"],
-                         "traffic": (35465472 if (args.mode == "bf16" and B == 256) else None),   # ncu dram read+write of this kernel, profiles/r1d
+                         "traffic": (TRAFFIC_CONV1_TP if (args.mode == "bf16" and B == 256) else None),   # ncu dram read+write of this kernel, profiles/r1e
                          "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
                          "kernel_ms": k_ms, "flops_per_launch": FLOPS_FWD[0] * B,
                          "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
             "roofline_hbm": {"kernel": ("stage_gray_tp_kernel" if args.mode == "bf16" else "stage_gray_kernel"), "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": stage_bytes / (stage_ms * 1e-3) / 1e9 / peaks["hbm"],
                              "bytes_per_launch": stage_bytes, "kernel_ms": stage_ms},
+            # every conv kernel against the tensor roofline: algorithmic FLOPs (fwd = dgrad = wgrad per layer) / live time
+            "roofline_conv_tflops": {k: round(FLOPS_FWD[int(k[4]) - 1] * B / (v * 1e-6) / 1e12, 1)
+                                     for k, v in breakdown.items() if k.startswith("conv")},
             "breakdown_us": breakdown,
             "clocks": clocks,
         }
