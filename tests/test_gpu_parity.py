@@ -411,3 +411,65 @@ def test_loss_curve_1k_steps_within_one_percent(golden_dir):
     # bare 1 % band around ONE reference run is not a property the reference itself has)
     from tests.curve_check import check_curve
     check_curve(got, golden_dir, tol=1e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_inference_sweep_batches_match_oracle(mode):
+    """BASELINE configs[4]: inference-only policy forward + greedy action over a batch sweep (1..1024; the closed-loop
+    rollout of src/data/stat.py:41 uses B=1). Logits vs the oracle forward on the same weights: rel 1e-5 (fp32 mode) /
+    2e-2 (bf16 mode); actions equal wherever the oracle's top-2 margin exceeds the tolerance."""
+    from carla_imitation_learning_b200 import stage_frames, stage_gray, sliding_window
+    from src.architectures.nets import ConvNet1
+    dev = _dev()
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": mode}).to(dev)
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    tol = REL_F32 if mode == "fp32" else 2e-2
+    frames, _ = O.synth_frames(4242, 1024 + 4)
+    fr = torch.from_numpy(frames).to(dev)
+    gray = stage_gray(fr)
+    ref_all = O.forward(params, torch.from_numpy(O.gray_stack(frames[:132])).unfold(0, 4, 1).permute(0, 3, 1, 2)[:128])
+    for B in (1, 2, 31, 128, 1024):
+        if mode == "bf16":
+            x = stage_frames(fr[:B + 4])
+        else:
+            x = sliding_window(gray[:B + 4])
+        with torch.no_grad():
+            logits = net(x)
+            actions = net.act(x)
+        assert logits.shape == (B, 9) and actions.shape == (B,) and actions.dtype == torch.int64
+        n = min(B, 128)
+        got, ref = logits[:n].cpu().double(), ref_all[:n].double()
+        assert float((got - ref).abs().max() / ref.abs().max()) <= tol, (mode, B)
+        top2 = ref.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 2 * tol * ref.abs().max()
+        assert torch.equal(actions[:n].cpu()[clear], ref.argmax(1)[clear])
+        assert torch.equal(actions.cpu(), logits.argmax(1).cpu())
+    net.engine().check_device_errors()
+
+
+def test_stacked_12_channel_variant_matches_oracle():
+    """BASELINE configs[3]: obs_size = 12 (3 cameras x 4 frames channel-stacked) at the 256x256 the architecture
+    hard-codes (nets.py:14); forward, loss and all 14 gradients vs the f64 oracle given the device's routing.
+    (precision='bf16' falls back to the exact kernels for obs_size != 4: the Toeplitz operand is built for 4 planes.)"""
+    from src.architectures.nets import ConvNet1
+    dev = _dev()
+    torch.manual_seed(7)
+    net = ConvNet1({"obs_size": 12, "n_actions": 9, "precision": "bf16"}).to(dev)
+    assert net.engine().conv_mode == 0
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    assert params["cnn_base.0.weight"].shape == (16, 12, 7, 7)
+    gen = torch.Generator().manual_seed(3)
+    B = 3
+    x = torch.rand((B, 12, 256, 256), generator=gen)
+    y = torch.randint(0, 9, (B,), generator=gen)
+    eng = net.engine()
+    bufs = eng.train_forward_backward(x.to(dev), y.to(dev))
+    torch.cuda.synchronize()
+    amax = [a.cpu().long() for a in bufs.amax]
+    ref_loss, ref_logits, ref, _ = O.explicit_backward(params, x, y, dtype=torch.float64, argmax_override=amax)
+    assert _relerr(bufs.logits.cpu(), ref_logits) <= REL_F32
+    assert abs(float(bufs.loss) - float(ref_loss)) <= REL_F32 * float(ref_loss)
+    for k, p in net.named_parameters():
+        g = eng.grads[p._bc_offset:p._bc_offset + p.numel()].view(p.shape).cpu()
+        assert _relerr(g, ref[k]) <= REL_F32, k
