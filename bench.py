@@ -197,8 +197,9 @@ def run_b200(args):
         def stage(frames_u8):
             stage_gray(frames_u8, out=gray)
 
-    from carla_imitation_learning_b200.parallel import DataParallelStep
-    dp = DataParallelStep(eng, opt) if world > 1 else None   # 2-bucket exchange overlapped with conv1 wgrad
+    from carla_imitation_learning_b200.parallel import DataParallelStep, PeerExchangeStep
+    # N > 1: gradient exchange fused into the Adam kernel over NVLink peer memory (default), or the 2-bucket NCCL all-reduce
+    dp = None if world == 1 else (PeerExchangeStep(eng, opt) if args.dp == "peer" else DataParallelStep(eng, opt))
 
     def train(b):
         if dp is not None:
@@ -380,6 +381,7 @@ def run_b200(args):
             "config": {"workload": f"ConvNet1 BC train step (BASELINE configs[1]), obs 4x256x256, 9 actions, batch {B}/GPU, "
                                    f"u8 RGB frames staged to {args.staged} gray planes, sliding 4-frame window",
                        "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graphs is not None,
+                       "exchange": (None if world == 1 else ("adam kernel reads peer gradient arenas over NVLink" if args.dp == "peer" else "nccl 2-bucket all-reduce")),
                        "l2": f"inputs rotate over {NBUF} x {(B + 4) * FRAME_BYTES / 1e6:.0f} MB device buffers (> 126 MB L2)",
                        "final_loss": loss_dev},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -420,6 +422,7 @@ def main():
     ap.add_argument("--staged", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="N>1 gradient exchange: fused peer-memory Adam, or NCCL buckets")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

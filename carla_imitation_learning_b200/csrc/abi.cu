@@ -64,6 +64,101 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     }
 }
 
+// ---- K11 + K10 fused: the data-parallel gradient exchange inside the Adam step, over NVLink peer memory -------------
+// Every rank's gradient arena lives in a symmetric allocation that all ranks map (torch symmetric memory, i.e.
+// cudaIpc / fabric handles: plumbing). One kernel per step and rank:
+//   A  announce "my gradients of epoch e are complete" in every peer's signal pad, wait for every peer's announcement;
+//   B  read all `world` arenas straight from peer memory, add them in RANK ORDER (so every rank computes bitwise the same
+//      sum and the replicas never drift), scale by grad_scale = 1/world, apply the Adam update to the local replica;
+//   C  the last CTA announces "done reading" and waits for the peers' same flag, so that when this kernel has finished
+//      on a rank, nobody is still reading that rank's gradients and the next backward may overwrite them.
+// 533 KB per arena: the whole exchange is (world-1) x 533 KB of NVLink reads per rank and two flag round trips -- no
+// separate all-reduce launch, no host involvement, CUDA-graph capturable. Waits are bounded by wall-clock time.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ bool wait_epoch(const uint32_t* flag, uint32_t epoch, int* err) {
+    const uint64_t t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (globaltimer_ns() - t0 > 20000000000ull) {       // 20 s: a peer died or the ranks disagree on the step count
+            if (err) atomicExch(err, 2);
+            return false;
+        }
+        __nanosleep(100);
+    }
+    return true;
+}
+
+constexpr int kSigReady = 256, kSigDone = 320;               // u32 word offsets inside a rank's signal pad (64 ranks each)
+
+__global__ void __launch_bounds__(256) adam_exchange_kernel(float4* __restrict__ p, const float4* const* __restrict__ peer_grads,
+                                                            uint32_t* const* __restrict__ peer_signals, float4* __restrict__ m,
+                                                            float4* __restrict__ v, const double* __restrict__ st,
+                                                            uint32_t* __restrict__ sync, int64_t n4, int rank, int world, int* err) {
+    __shared__ int s_last;
+    const uint32_t epoch = sync[0] + 1;
+    uint32_t* my_sig = peer_signals[rank];
+    // ---- A
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peer_signals[threadIdx.x] + kSigReady + rank, epoch);
+    }
+    if (threadIdx.x < world) wait_epoch(my_sig + kSigReady + threadIdx.x, epoch, err);
+    __syncthreads();
+    // ---- B
+    const float w1 = (float)(1.0 - st[1]), b2 = (float)st[2], w2 = (float)(1.0 - st[2]), eps = (float)st[3];
+    const float gs = (float)st[5], neg_step = (float)(-st[6]), bc2s = (float)st[7];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 gg = ld_relaxed_sys_f4(peer_grads[0] + i);
+        for (int r = 1; r < world; ++r) {
+            const float4 o = ld_relaxed_sys_f4(peer_grads[r] + i);
+            gg.x = __fadd_rn(gg.x, o.x); gg.y = __fadd_rn(gg.y, o.y); gg.z = __fadd_rn(gg.z, o.z); gg.w = __fadd_rn(gg.w, o.w);
+        }
+        float4 pp = p[i], mm = m[i], vv = v[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = G[k] * gs;
+            M[k] = __fmaf_rn(w1, gk - M[k], M[k]);
+            V[k] = __fmaf_rn(w2 * gk, gk, V[k] * b2);
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V[k]), bc2s), eps);
+            P[k] = __fmaf_rn(neg_step, __fdiv_rn(M[k], denom), P[k]);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+    // ---- C
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(sync + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < world) {
+            st_release_sys(peer_signals[threadIdx.x] + kSigDone + rank, epoch);
+            wait_epoch(my_sig + kSigDone + threadIdx.x, epoch, err);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { sync[1] = 0; sync[0] = epoch; }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -143,6 +238,21 @@ int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (const float4*)grads, (float4*)exp_avg,
                                                         (float4*)exp_avg_sq, state, n4);
     BC_CUDA_LAUNCH_CHECK("adam_kernel");
+    return BC_OK;
+}
+
+int bc_adam_step_exchange(float* params, const void* peer_grads_dev, const void* peer_signals_dev, float* exp_avg, float* exp_avg_sq,
+                          const double* state, uint32_t* sync_state, int64_t n, int rank, int world, int* err_flag, void* stream) {
+    BC_CHECK_ARG(params && peer_grads_dev && peer_signals_dev && exp_avg && exp_avg_sq && state && sync_state, "bc_adam_step_exchange: null pointer");
+    BC_CHECK_ARG(n > 0 && n % 4 == 0, "bc_adam_step_exchange: n=%lld must be a positive multiple of 4", (long long)n);
+    BC_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bc_adam_step_exchange: rank %d of %d", rank, world);
+    const int64_t n4 = n / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 64) blocks = 64;                              // every CTA spins on the flags: keep them all resident
+    adam_exchange_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (const float4* const*)peer_grads_dev,
+                                                                 (uint32_t* const*)peer_signals_dev, (float4*)exp_avg, (float4*)exp_avg_sq,
+                                                                 state, sync_state, n4, rank, world, err_flag);
+    BC_CUDA_LAUNCH_CHECK("adam_exchange_kernel");
     return BC_OK;
 }
 

@@ -115,6 +115,18 @@ class FusedAdam(torch.optim.Optimizer):
             _lib.check(lib.bc_adam_step(arena.data_ptr(), flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
                                         st.data_ptr(), arena.numel(), s), "bc_adam_step")
 
+    def step_exchange(self, peer) -> None:
+        """Data-parallel step: tick + ONE kernel that sums every rank's gradient arena straight from NVLink peer memory
+        (rank order), folds the 1/world mean and applies Adam (bc_adam_step_exchange; `peer` = parallel.PeerGrads)."""
+        arena, m, v, st, _ = self._bind()
+        self._sync_scalars(st)
+        lib, s = _lib.lib(), _stream_ptr()
+        with torch.cuda.device(arena.device):
+            _lib.check(lib.bc_adam_tick(st.data_ptr(), s), "bc_adam_tick")
+            _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), peer.grads_dev, peer.signals_dev, m.data_ptr(), v.data_ptr(),
+                                                 st.data_ptr(), peer.sync.data_ptr(), arena.numel(), peer.rank, peer.world,
+                                                 peer.err.data_ptr(), s), "bc_adam_step_exchange")
+
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict):
         """Accepts a torch.optim.Adam state_dict (reference checkpoints, train.py:198-201)."""

@@ -73,8 +73,60 @@ class GradExchange:
         self.finish()
 
 
+class PeerGrads:
+    """The gradient arena of this rank in a symmetric allocation every rank maps (torch symmetric memory = cudaIpc /
+    fabric handles; plumbing), plus the per-rank signal pad and the private sync words of bc_adam_step_exchange."""
+
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        n = engine.arena.numel()
+        self.buf = symm.empty(n, dtype=torch.float32, device=engine.device)
+        self.hdl = symm.rendezvous(self.buf, group.group_name)
+        self.buf.zero_()
+        self.hdl.get_signal_pad(self.rank).zero_()
+        self.grads_dev, self.signals_dev = int(self.hdl.buffer_ptrs_dev), int(self.hdl.signal_pad_ptrs_dev)
+        self.sync = torch.zeros(2, dtype=torch.int32, device=engine.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        engine.grads = self.buf                       # backward now reduces its partial sums straight into peer-visible memory
+        torch.cuda.synchronize(engine.device)
+        dist.barrier(group)                           # every pad is zero before anybody signals
+
+    def check(self) -> None:
+        if int(self.err.item()) != 0:
+            raise RuntimeError("bc_adam_step_exchange: a peer rank never signalled (rank died, or the ranks ran different step counts)")
+
+
+class PeerExchangeStep:
+    """One optimisation step on this rank's shard with the gradient exchange FUSED into the Adam kernel over NVLink
+    peer memory: forward, backward, then one kernel that reads all ranks' arenas, sums in rank order, updates.
+    No NCCL call and no host round trip inside the step, so the whole step is one CUDA graph."""
+
+    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None):
+        self.eng, self.opt = engine, optimizer
+        self.peer = PeerGrads(engine, group)
+        optimizer.set_grad_scale(1.0 / self.peer.world)
+
+    def __call__(self, bufs, loss_scale: Optional[float] = None) -> None:
+        self.eng.enqueue_train(bufs, loss_scale)
+        self.opt.step_exchange(self.peer)
+
+    def capture(self, bufs, pre=None):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if pre is not None:
+                pre()
+            self(bufs)
+        return g
+
+    def replay(self, graph) -> None:
+        graph.replay()
+
+
 class DataParallelStep:
-    """One optimisation step on this rank's shard: forward, backward with the exchange overlapped, Adam."""
+    """One optimisation step on this rank's shard: forward, backward with the NCCL exchange overlapped, Adam.
+    (The baseline exchange; PeerExchangeStep above is the fused one.)"""
 
     def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None):
         self.eng, self.opt = engine, optimizer
