@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "conv_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
 
@@ -32,7 +32,7 @@ class BcCtx(C.Structure):
         ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p),
         ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
         ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
-        ("dy_bf16", C.c_void_p),
+        ("reserved0", C.c_void_p),
         ("x_tp", C.c_void_p), ("x_tp_stride_n", C.c_int64), ("x_tp_stride_c", C.c_int64),
     ]
 

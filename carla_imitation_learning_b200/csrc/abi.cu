@@ -203,15 +203,9 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
     // head: (CE from labels when with_loss, else the caller's dlogits) + MLP backward -> ghead
     int rc = bc_head(c, with_loss ? 3 : 2, stream);
     if (rc) return rc;
-    const bool tc = (c->conv_mode & 6) && c->dy_bf16 && c->act_bf16[0];
     for (int l = 3; l >= 1; --l) {
-        if (tc && l == 3) {   // conv4: one unpool feeds both the gathered wgrad and dgrad (conv2/conv3 build dY inside their kernels)
-            if ((rc = bc_unpool_launch(c, l, stream))) return rc;
-            bc_tc_set_dy_ready(true);
-        }
         rc = bc_conv_bwd_wgrad(c, l, stream);
         if (!rc) rc = bc_conv_bwd_dgrad(c, l, stream);
-        bc_tc_set_dy_ready(false);
         if (rc) return rc;
     }
     if ((rc = bc_conv_bwd_wgrad(c, 0, stream))) return rc;

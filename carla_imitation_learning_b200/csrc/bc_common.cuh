@@ -13,11 +13,12 @@ int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream);  // conv_tc.cu 
 int bc_conv_tc_pack(const bc_ctx* c, void* stream);
 int bc_dgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
 int bc_wgrad_tc_launch(const bc_ctx* c, int layer, void* stream);
-int bc_unpool_launch(const bc_ctx* c, int layer, void* stream);
 int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);     // conv_sw.cu (layers 1, 2)
 int bc_conv_sw_dgrad_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream);
 int bc_conv_sw_wgrad_launch(const bc_ctx* c, int layer, void* stream);
-void bc_tc_set_dy_ready(bool v);
+int bc_conv4_sw_fwd_launch(const bc_ctx* c, const uint8_t* wpk, void* stream);               // conv4_sw.cu (layer 3)
+int bc_conv4_sw_dgrad_launch(const bc_ctx* c, const uint8_t* wpk, void* stream);
+int bc_conv4_sw_wgrad_launch(const bc_ctx* c, void* stream);
 size_t bc_conv_tc_pack_total();
 
 namespace bc {

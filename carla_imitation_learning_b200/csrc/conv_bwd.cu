@@ -323,7 +323,7 @@ extern "C" int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream) {
     const int64_t w_off = ar.w[layer] - ar.seg_off[seg], b_off = ar.b[layer] - ar.seg_off[seg];
     const float* gP = layer == 3 ? c->ghead : c->gact[layer];
     BC_CHECK_ARG(gP, "bc_conv_bwd_wgrad: gradient buffer for layer %d is null", layer);
-    if ((c->conv_mode & 4) && layer >= 1 && c->dy_bf16 && c->act_bf16[layer - 1]) return bc_wgrad_tc_launch(c, layer, stream);
+    if ((c->conv_mode & 4) && layer >= 1 && c->act_bf16[layer - 1]) return bc_wgrad_tc_launch(c, layer, stream);
     if ((c->conv_mode & 8) && layer == 0 && c->x_tp && c->obs_size == 4 && c->err_flag) return bc_conv1_wgrad_tc_launch(c, stream);
     cudaStream_t s = (cudaStream_t)stream;
     const int B = c->batch, np = bc::kWgradParts[layer];
@@ -354,7 +354,7 @@ extern "C" int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream) {
     const float* w = c->params + ar.w[layer];
     const float* gP = layer == 3 ? c->ghead : c->gact[layer];
     BC_CHECK_ARG(gP, "bc_conv_bwd_dgrad: gradient buffer for layer %d is null", layer);
-    if ((c->conv_mode & 2) && c->dy_bf16) return bc_dgrad_tc_launch(c, layer, stream);
+    if ((c->conv_mode & 2) && c->act_bf16[0]) return bc_dgrad_tc_launch(c, layer, stream);
     cudaStream_t s = (cudaStream_t)stream;
     switch (layer) {
     case 1:

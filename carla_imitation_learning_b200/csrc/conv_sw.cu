@@ -98,10 +98,11 @@ struct PooledGrad {
 };
 
 // ================================================================================================ forward
-template <int CIN_, int COUT_, int KS_, int HIN_, int HP_, int RT_, bool OUT_P8_>
+// OUT_: layout of the bf16 copy for the next layer: 1 = P8 [b][c/8][pixel][8], 2 = P8B [c/8][b][pixel][8] (conv4_sw.cu)
+template <int CIN_, int COUT_, int KS_, int HIN_, int HP_, int RT_, int OUT_>
 struct FCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, HIN = HIN_, HP = HP_, RT = RT_;
-    static constexpr bool OUT_P8 = OUT_P8_;
+    static constexpr int OUT = OUT_;
     static constexpr int CG = CIN / 8, CB = CIN / 16, NSTEP = KS * KS * CB;
     static constexpr int PLANE = HIN * HIN * 16;            // bytes of one 8-channel plane of one image
     static constexpr int IMG = CG * PLANE;
@@ -293,23 +294,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_fwd_kernel(const FwdArgs a) {
                     __nv_bfloat162 p01 = __floats2bfloat162_rn(outv[0], outv[1]), p23 = __floats2bfloat162_rn(outv[2], outv[3]);
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&p01); pk.y = *reinterpret_cast<uint32_t*>(&p23);
-                    if constexpr (C::OUT_P8)   // [c/8][pooled pixel of the tile][8]
-                        *reinterpret_cast<uint2*>(P_ + ((cq >> 1) * NPP + pp) * 8 + (cq & 1) * 4) = pk;
-                    else                       // NHWC: [pooled pixel of the tile][COUT]
-                        *reinterpret_cast<uint2*>(P_ + pp * COUT + 4 * cq) = pk;
+                    *reinterpret_cast<uint2*>(P_ + ((cq >> 1) * NPP + pp) * 8 + (cq & 1) * 4) = pk;   // [c/8][pooled pixel of the tile][8]
                 }
             }
             if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
             if (a.ybf) {
                 constexpr int NV = C::P_BYTES / 16;
                 for (int i = te; i < NV; i += 128) {
-                    size_t dst;
-                    if constexpr (C::OUT_P8) {
-                        const int cg = i / NPP, pp = i % NPP;                // one uint4 = one pixel of one 8-channel group
-                        dst = (((size_t)b * (COUT / 8) + cg) * (HP * HP) + t * NPP + pp);
-                    } else {
-                        dst = ((size_t)b * (HP * HP) + t * NPP) * (COUT / 8) + i;
-                    }
+                    const int cg = i / NPP, pp = i % NPP;                    // one uint4 = one pixel of one 8-channel group
+                    const size_t dst = C::OUT == 1 ? (((size_t)b * (COUT / 8) + cg) * (HP * HP) + t * NPP + pp)
+                                                   : (((size_t)cg * a.B + b) * (HP * HP) + t * NPP + pp);
                     reinterpret_cast<uint4*>(a.ybf)[dst] = reinterpret_cast<const uint4*>(P_)[i];
                 }
             }
@@ -703,8 +697,8 @@ fin:
     if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
 }
 
-using F2 = FCfg<16, 32, 5, 28, 12, 4, true>;      // conv2 forward: 6 tiles of 4 conv rows per image, P8 output for conv3
-using F3 = FCfg<32, 64, 4, 12, 4, 8, false>;      // conv3 forward: one tile per image, NHWC output for conv4's gather
+using F2 = FCfg<16, 32, 5, 28, 12, 4, 1>;         // conv2 forward: 6 tiles of 4 conv rows per image, P8 output for conv3
+using F3 = FCfg<32, 64, 4, 12, 4, 8, 2>;          // conv3 forward: one tile per image, P8B output (batch inside the plane) for conv4
 using D2 = DCfg<16, 32, 5, 28, 12>;
 using D3 = DCfg<32, 64, 4, 12, 4>;
 using W2 = WCfg<16, 32, 5, 28, 12>;
@@ -774,7 +768,7 @@ int bc_conv_sw_wgrad_launch(const bc_ctx* c, int layer, void* stream) {
                       : csw::launch_wgrad<csw::W3>(c, 2, (cudaStream_t)stream, "conv3_sw_wgrad_kernel");
 }
 
-// layer 1 = conv2, layer 2 = conv3 (conv4 keeps the gather kernels of conv_tc.cu)
+// layer 1 = conv2, layer 2 = conv3 (conv4: conv4_sw.cu)
 int bc_conv_sw_fwd_launch(const bc_ctx* c, int layer, const uint8_t* wpk, void* stream) {
     return layer == 1 ? csw::launch_fwd<csw::F2>(c, 1, wpk, (cudaStream_t)stream, "conv2_sw_fwd_kernel")
                       : csw::launch_fwd<csw::F3>(c, 2, wpk, (cudaStream_t)stream, "conv3_sw_fwd_kernel");

@@ -120,7 +120,6 @@ class StepBuffers:
     ghead: Optional[torch.Tensor] = None
     gact: List[torch.Tensor] = field(default_factory=list)
     act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: bf16 copies feeding the next layer's MMA
-    dy_bf16: Optional[torch.Tensor] = None                       # bf16 mode: un-pooled conv-output gradient scratch
     x_tp: Optional[torch.Tensor] = None                          # bf16 mode: the input as Toeplitz-ready planes
     x_tp_strides: tuple = (0, 0)                                 # (sample, channel) element strides into x_tp
 
@@ -169,10 +168,10 @@ class BCEngine:
             bufs.x_tp, bufs.x_tp_strides = self.to_tp(x)
         if self.conv_mode & 1:
             # bf16 copies feeding the next layer's MMAs: act1, act2 as P8 = (B, C/8, H*W, 8) for the shifted-window
-            # kernels (csrc/conv_sw.cu), act3 as NHWC for conv4's gather
+            # kernels (csrc/conv_sw.cu), act3 as P8B = (C/8, B, H*W, 8) for conv4 (csrc/conv4_sw.cu)
             bufs.act_bf16 = [torch.empty((batch, 2, 784, 8), dtype=torch.bfloat16, device=dev),
                              torch.empty((batch, 4, 144, 8), dtype=torch.bfloat16, device=dev),
-                             torch.empty((batch, 4, 4, 64), dtype=torch.bfloat16, device=dev)]
+                             torch.empty((8, batch, 16, 8), dtype=torch.bfloat16, device=dev)]
         if backward:
             self._alloc_bwd(bufs)
         return bufs
@@ -182,8 +181,6 @@ class BCEngine:
             e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
             bufs.ghead = e(bufs.batch, 128)
             bufs.gact = [e(bufs.batch, *s) for s in ACT_SHAPES[:3]]
-            if self.conv_mode and bufs.act_bf16:
-                bufs.dy_bf16 = torch.empty((bufs.batch, 24, 24, 32), dtype=torch.bfloat16, device=self.device)
 
     def to_tp(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
         """(B,4,256,256) f32/bf16 batch -> Toeplitz-ready bf16 planes (include/bc_b200.h BC_BF16_TP) + strides.
@@ -242,7 +239,6 @@ class BCEngine:
         c.conv_mode = self.conv_mode
         for i in range(3):
             c.act_bf16[i] = b.act_bf16[i].data_ptr() if b.act_bf16 else None
-        c.dy_bf16 = b.dy_bf16.data_ptr() if b.dy_bf16 is not None else None
         c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
         if b.x_tp is not None:
             c.x_tp, (c.x_tp_stride_n, c.x_tp_stride_c) = b.x_tp.data_ptr(), b.x_tp_strides

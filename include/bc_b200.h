@@ -74,10 +74,10 @@ typedef struct {
     int32_t conv_mode;       /* bit mask of tcgen05 (bf16) kernels: 1 forward, 2 dgrad, 4 wgrad conv2-4, 8 wgrad conv1; 0 = exact f32 */
     void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
     int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
-    void* act_bf16[3];       /* bf16 mode: NHWC bf16 copies of act[0..2] (B,28,28,16) (B,12,12,32) (B,4,4,64),
-                                written by the conv epilogues, read by the next layer's tcgen05 gather   */
-    void* dy_bf16;           /* bf16 mode: scratch for the un-pooled conv-output gradient, NHWC bf16,
-                                batch*24*24*32 elements (the largest layer); one layer at a time          */
+    void* act_bf16[3];       /* bf16 mode: bf16 copies of act[0..2] in the layouts the shifted-window kernels read
+                                (csrc/conv_sw.cu, conv4_sw.cu): act1 P8 (B,2,784,8), act2 P8 (B,4,144,8),
+                                act3 P8B (8,B,16,8) = [c/8][b][pixel][8]; written by the conv epilogues     */
+    void* reserved0;         /* (was: dense dY scratch; the routed gradients are now built in shared memory)  */
     const void* x_tp;        /* bf16 mode: the input as BC_BF16_TP planes (bc_stage_gray / bc_planes_to_tp); sample n,
                                 channel c is the plane at x_tp + n*x_tp_stride_n + c*x_tp_stride_c (elements).
                                 stride_n == stride_c is the sliding window: consecutive samples share 3 of 4 planes

@@ -90,17 +90,16 @@ def test_bf16_mode_training_step_within_tolerance():
 
 
 def _to_act_bf16(x_nchw, idx):
-    """NCHW -> the layout of bufs.act_bf16[idx]: P8 (B, C/8, H*W, 8) for act1/act2, NHWC for act3."""
+    """NCHW -> the layout of bufs.act_bf16[idx]: P8 (B, C/8, H*W, 8) for act1/act2, P8B (C/8, B, H*W, 8) for act3."""
     B, Cc, Hh, Ww = x_nchw.shape
-    if idx == 2:
-        return x_nchw.permute(0, 2, 3, 1).contiguous()
-    return x_nchw.reshape(B, Cc // 8, 8, Hh * Ww).permute(0, 1, 3, 2).contiguous()
+    p8 = x_nchw.reshape(B, Cc // 8, 8, Hh * Ww).permute(0, 1, 3, 2)
+    return (p8.permute(1, 0, 2, 3) if idx == 2 else p8).contiguous()
 
 
 def _from_act_bf16(t, idx, shape):
     B, Cc, Hh, Ww = shape
     if idx == 2:
-        return t.permute(0, 3, 1, 2)
+        t = t.permute(1, 0, 2, 3)
     return t.permute(0, 1, 3, 2).reshape(B, Cc, Hh, Ww)
 
 
@@ -339,8 +338,8 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
         cols = F.unfold(xin, kernel_size=k, stride=stride)                       # (B, Cin*k*k, L) over the full conv map
         L_used = dy.shape[-1]
         ref_w = torch.einsum("bol,bkl->ok", dy.reshape(B, dy.shape[1], -1), cols).reshape(w.shape)
-        # conv2/conv3 (shifted-window wgrad) fold the f32 gradient before its bf16 rounding; conv1/conv4 use a ones row of the GEMM
-        ref_b = (dy_f32 if layer in (1, 2) else dy).sum(dim=(0, 2, 3))
+        # conv2-4 (shifted-window wgrad) fold the f32 gradient before its bf16 rounding; conv1 uses a ones row of the GEMM
+        ref_b = (dy_f32 if layer >= 1 else dy).sum(dim=(0, 2, 3))
         pw, pb = params[f"{names[layer]}.weight"], params[f"{names[layer]}.bias"]
         got_w = eng.grads[pw._bc_offset:pw._bc_offset + pw.numel()].view(w.shape).cpu().double()
         got_b = eng.grads[pb._bc_offset:pb._bc_offset + pb.numel()].cpu().double()
