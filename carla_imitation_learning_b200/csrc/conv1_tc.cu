@@ -573,6 +573,15 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
     return conv1_tp_launch(c, stream);
 }
 
+int bc_conv1_wgrad_tp_grid(const bc_ctx* c) {
+    const bool sliding = c->x_tp_stride_n == c->x_tp_stride_c;
+    const int njobs = (sliding ? c->batch + 3 : 4 * c->batch) * c1tc::TILES_PER_FRAME;
+    int grid = bc::num_sms();
+    if (grid > bc::kWgradParts[0]) grid = bc::kWgradParts[0];
+    if (grid > njobs) grid = njobs;
+    return grid < 1 ? 1 : grid;
+}
+
 static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05, TP): null buffer");
     BC_CHECK_ARG(c->obs_size == 4, "conv1 wgrad (tcgen05, TP): obs_size 4 only");
@@ -586,15 +595,10 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     }
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
-    const int nparts = bc::kWgradParts[0];
-    const bool sliding = c->x_tp_stride_n == c->x_tp_stride_c;
-    const int njobs = (sliding ? c->batch + 3 : 4 * c->batch) * c1tc::TILES_PER_FRAME;
-    int grid = bc::num_sms();
-    if (grid > nparts) grid = nparts;
-    if (grid > njobs) grid = njobs;
+    const int grid = bc_conv1_wgrad_tp_grid(c);      // = the slots bc_reduce_partials reads for conv1 in this mode
     c1wg2::conv1_wgrad_tp_kernel<<<grid, c1wg2::NTHREADS, c1wg2::SMEM_BYTES, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
-        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], nparts, c->batch, c->err_flag);
+        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
     return BC_OK;
 }

@@ -272,11 +272,17 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
         const float* p = a.part + a.poff[s] + (i - a.seg_off[s]);
         const int64_t stride = a.seg_len[s];
         const int n = a.nparts[s];
-        float s0 = 0.f, s1 = 0.f;
+        // 4 independent chains per thread (fixed association order): 4 loads in flight instead of 2
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int q = g;
-        for (; q + 8 < n; q += 16) { s0 += p[(int64_t)q * stride]; s1 += p[(int64_t)(q + 8) * stride]; }
+        for (; q + 24 < n; q += 32) {
+            s0 += p[(int64_t)q * stride]; s1 += p[(int64_t)(q + 8) * stride];
+            s2 += p[(int64_t)(q + 16) * stride]; s3 += p[(int64_t)(q + 24) * stride];
+        }
         if (q < n) s0 += p[(int64_t)q * stride];
-        acc = s0 + s1;
+        if (q + 8 < n) s1 += p[(int64_t)(q + 8) * stride];
+        if (q + 16 < n) s2 += p[(int64_t)(q + 16) * stride];
+        acc = (s0 + s1) + (s2 + s3);
     }
     red[g][e] = acc;
     __syncthreads();
@@ -378,6 +384,8 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     ReduceArgs a{};
     a.part = c->partials; a.grads = c->grads; a.loss = c->loss;
     for (int k = 0; k < 5; ++k) { a.seg_off[k] = ar.seg_off[k]; a.seg_len[k] = ar.seg_len[k]; a.poff[k] = pl.off[k]; a.nparts[k] = pl.nparts[k]; }
+    // the tcgen05 conv1 wgrad writes one partial per CTA, i.e. fewer slots than the layout reserves: read only those
+    if ((c->conv_mode & 8) && c->x_tp && c->obs_size == 4 && c->err_flag) a.nparts[4] = bc_conv1_wgrad_tp_grid(c);
     a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
     a.begin = ar.seg_off[seg_lo];
     a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];
