@@ -34,6 +34,8 @@ namespace {
 // state (doubles, like the Python scalars torch.optim.Adam works with):
 //   [0] lr [1] beta1 [2] beta2 [3] eps [4] step [5] grad_scale [6] step_size (out) [7] bc2_sqrt (out)
 __global__ void adam_tick_kernel(double* st) {
+    bc::pdl_wait();
+    bc::pdl_trigger();
     // torch/optim/adam.py (single-tensor path): bias_correction1 = 1 - beta1 ** step;
     // step_size = lr / bias_correction1; bias_correction2_sqrt = sqrt(1 - beta2 ** step) -- all in f64.
     const double step = st[4] + 1.0;
@@ -45,6 +47,8 @@ __global__ void adam_tick_kernel(double* st) {
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                    const double* __restrict__ st, int64_t n4) {
+    bc::pdl_wait();
+    bc::pdl_trigger();
     // the f64 scalars are rounded to f32 exactly where ATen rounds its Scalar arguments
     const float w1 = (float)(1.0 - st[1]), b2 = (float)st[2], w2 = (float)(1.0 - st[2]), eps = (float)st[3];
     const float gs = (float)st[5], neg_step = (float)(-st[6]), bc2s = (float)st[7];
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(float4* __restrict__
                                                             float4* __restrict__ v, const double* __restrict__ st,
                                                             uint32_t* __restrict__ sync, int64_t n4, int rank, int world, int* err) {
     __shared__ int s_last;
+    bc::pdl_wait();
+    bc::pdl_trigger();
     const uint32_t epoch = sync[0] + 1;
     uint32_t* my_sig = peer_signals[rank];
     // ---- A
@@ -214,7 +220,7 @@ int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
 
 int bc_adam_tick(double* state, void* stream) {
     BC_CHECK_ARG(state, "bc_adam_tick: null state");
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+    bc::launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, state);
     BC_CUDA_LAUNCH_CHECK("adam_tick_kernel");
     return BC_OK;
 }
@@ -229,8 +235,8 @@ int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     int blocks = (int)((n4 + 255) / 256);
     const int cap = bc::num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (const float4*)grads, (float4*)exp_avg,
-                                                        (float4*)exp_avg_sq, state, n4);
+    bc::launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (float4*)params, (const float4*)grads, (float4*)exp_avg,
+                   (float4*)exp_avg_sq, state, n4);
     BC_CUDA_LAUNCH_CHECK("adam_kernel");
     return BC_OK;
 }
@@ -243,9 +249,8 @@ int bc_adam_step_exchange(float* params, const void* peer_grads_dev, const void*
     const int64_t n4 = n / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 64) blocks = 64;                              // every CTA spins on the flags: keep them all resident
-    adam_exchange_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float4*)params, (const float4* const*)peer_grads_dev,
-                                                                 (uint32_t* const*)peer_signals_dev, (float4*)exp_avg, (float4*)exp_avg_sq,
-                                                                 state, sync_state, n4, rank, world, err_flag);
+    bc::launch_pdl(adam_exchange_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (float4*)params, (const float4* const*)peer_grads_dev,
+                   (uint32_t* const*)peer_signals_dev, (float4*)exp_avg, (float4*)exp_avg_sq, state, sync_state, n4, rank, world, err_flag);
     BC_CUDA_LAUNCH_CHECK("adam_exchange_kernel");
     return BC_OK;
 }

@@ -111,12 +111,15 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     }
     if (warp == 0) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
     if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(smem + OFF_RING + NSLOT * SLOT_BYTES)[threadIdx.x] = 0u;   // over-read pad
-    if (threadIdx.x < 16) reinterpret_cast<float*>(smem + OFF_BIAS)[threadIdx.x] = bias[threadIdx.x];
     tc05::fence_async_smem();
     tc05::tc_fence_before();
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
+    if (threadIdx.x >= 128 && threadIdx.x < 144) reinterpret_cast<float*>(smem + OFF_BIAS)[threadIdx.x - 128] = bias[threadIdx.x - 128];
+    if (warp >= 4 && warp < 12) asm volatile("bar.sync 3, 256;" ::: "memory");   // the epilogue warps read the bias from smem
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: 6 bulk copies per plane, one per lane
@@ -379,6 +382,8 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: 14 bulk copies per job, one per lane
@@ -561,7 +566,7 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
     const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
-    c1tp::conv1_tp_kernel<<<grid, c1tp::NTHREADS, c1tp::SMEM_BYTES, (cudaStream_t)stream>>>(
+    bc::launch_pdl(c1tp::conv1_tp_kernel, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
         c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
@@ -596,7 +601,7 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
     const int grid = bc_conv1_wgrad_tp_grid(c);      // = the slots bc_reduce_partials reads for conv1 in this mode
-    c1wg2::conv1_wgrad_tp_kernel<<<grid, c1wg2::NTHREADS, c1wg2::SMEM_BYTES, (cudaStream_t)stream>>>(
+    bc::launch_pdl(c1wg2::conv1_wgrad_tp_kernel, dim3(grid), dim3(c1wg2::NTHREADS), c1wg2::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
         c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");

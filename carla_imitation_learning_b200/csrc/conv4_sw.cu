@@ -55,6 +55,8 @@ conv4_fwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __re
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -204,6 +206,8 @@ conv4_dgrad_kernel(const float* __restrict__ gP, const float* __restrict__ aP, c
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -319,6 +323,8 @@ conv4_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         for (int c = 0; c < nchunk; ++c) {
@@ -446,7 +452,7 @@ int bc_conv4_sw_fwd_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) {
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const int ntiles = (c->batch + 7) / 8;
     const int grid = ntiles < bc::num_sms() ? ntiles : bc::num_sms();
-    c4::conv4_fwd_kernel<<<grid, c4::fw::NTHREADS, c4::fw::SMEM_BYTES, (cudaStream_t)stream>>>(
+    bc::launch_pdl(c4::conv4_fwd_kernel, dim3(grid), dim3(c4::fw::NTHREADS), c4::fw::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->act_bf16[2], (const __nv_bfloat16*)wpk, c->params + ar.b[3], c->act[3], c->amax[3], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv4_fwd_kernel");
     return BC_OK;
@@ -457,7 +463,7 @@ int bc_conv4_sw_dgrad_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) 
     if (!configured) { int rc = c4::opt_in(c4::conv4_dgrad_kernel, c4::dg::SMEM_BYTES, "conv4_dgrad_kernel"); if (rc) return rc; configured = true; }
     const int ntiles = (c->batch + 1) / 2;
     const int grid = ntiles < bc::num_sms() ? ntiles : bc::num_sms();
-    c4::conv4_dgrad_kernel<<<grid, c4::dg::NTHREADS, c4::dg::SMEM_BYTES, (cudaStream_t)stream>>>(
+    bc::launch_pdl(c4::conv4_dgrad_kernel, dim3(grid), dim3(c4::dg::NTHREADS), c4::dg::SMEM_BYTES, (cudaStream_t)stream,
         c->ghead, c->act[3], c->amax[3], (const __nv_bfloat16*)wpk, c->gact[2], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv4_dgrad_kernel");
     return BC_OK;
@@ -468,7 +474,7 @@ int bc_conv4_sw_wgrad_launch(const bc_ctx* c, void* stream) {
     if (!configured) { int rc = c4::opt_in(c4::conv4_wgrad_kernel, c4::wg::SMEM_BYTES, "conv4_wgrad_kernel"); if (rc) return rc; configured = true; }
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
-    c4::conv4_wgrad_kernel<<<dim3(bc::kWgradParts[3], c4::wg::NCLS), c4::wg::NTHREADS, c4::wg::SMEM_BYTES, (cudaStream_t)stream>>>(
+    bc::launch_pdl(c4::conv4_wgrad_kernel, dim3(bc::kWgradParts[3], c4::wg::NCLS), dim3(c4::wg::NTHREADS), c4::wg::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->act_bf16[2], c->ghead, c->act[3], c->amax[3], c->partials + pl.off[1], ar.seg_len[1],
         ar.w[3] - ar.seg_off[1], ar.b[3] - ar.seg_off[1], c->batch, c->err_flag);
     BC_CUDA_LAUNCH_CHECK("conv4_wgrad_kernel");

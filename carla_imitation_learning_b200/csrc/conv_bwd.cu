@@ -262,6 +262,8 @@ struct ReduceArgs {
 // a one-thread-per-element walk over up to 296 copies.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
     __shared__ float red[8][33];
+    bc::pdl_wait();
+    bc::pdl_trigger();
     const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int64_t i = a.begin + (int64_t)blockIdx.x * 32 + e;
     float acc = 0.f;
@@ -389,7 +391,7 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
     a.begin = ar.seg_off[seg_lo];
     a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];
-    reduce_partials_kernel<<<(int)((a.end - a.begin + 31) / 32), 256, 0, (cudaStream_t)stream>>>(a);
+    bc::launch_pdl(reduce_partials_kernel, dim3((unsigned)((a.end - a.begin + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return BC_OK;
 }

@@ -157,12 +157,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_fwd_kernel(const FwdArgs a) {
     }
     if (warp == 0) tc05::tmem_alloc(tmem_slot, 512);
     for (int i = threadIdx.x; i < 4096 / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + C::OFF_IMG + NIMG * C::IMG)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x < COUT) reinterpret_cast<float*>(smem + C::OFF_BIAS)[threadIdx.x] = a.bias[threadIdx.x];
     tc05::fence_async_smem();
     tc05::tc_fence_before();
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + COUT) reinterpret_cast<float*>(smem + C::OFF_BIAS)[threadIdx.x - 128] = a.bias[threadIdx.x - 128];
+    if (warp >= 4 && warp < 12) asm volatile("bar.sync 3, 256;" ::: "memory");   // the epilogue warps read the bias from smem
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: one bulk copy per image
@@ -374,6 +377,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -568,6 +573,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tc05::pdl_trigger();
+    tc05::pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: the input image, one bulk copy
@@ -719,7 +726,7 @@ int launch_fwd(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, c
     if (grid > ntiles) grid = ntiles;
     FwdArgs args{(const __nv_bfloat16*)c->act_bf16[layer - 1], (const __nv_bfloat16*)wpk, c->params + ar.b[layer],
                  c->act[layer], c->amax[layer], (__nv_bfloat16*)c->act_bf16[layer], c->batch, c->err_flag};
-    kern<<<grid, NTHREADS, C::SMEM_BYTES, s>>>(args);
+    bc::launch_pdl(kern, dim3(grid), dim3(NTHREADS), C::SMEM_BYTES, s, args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;
 }
@@ -737,7 +744,7 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
     DgradArgs args{c->gact[layer], c->act[layer], c->amax[layer], (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag};
-    kern<<<grid, NTHREADS, C::SMEM_BYTES, s>>>(args);
+    bc::launch_pdl(kern, dim3(grid), dim3(NTHREADS), C::SMEM_BYTES, s, args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;
 }
@@ -756,7 +763,7 @@ int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
     const int seg = 4 - layer;
     WgradArgs args{(const __nv_bfloat16*)c->act_bf16[layer - 1], c->gact[layer], c->act[layer], c->amax[layer],
                    c->partials + pl.off[seg], ar.seg_len[seg], ar.w[layer] - ar.seg_off[seg], ar.b[layer] - ar.seg_off[seg], c->batch, c->err_flag};
-    kern<<<dim3(bc::kWgradParts[layer], C::KS), NTHREADS, C::SMEM_BYTES, s>>>(args);
+    bc::launch_pdl(kern, dim3(bc::kWgradParts[layer], C::KS), dim3(NTHREADS), C::SMEM_BYTES, s, args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;
 }

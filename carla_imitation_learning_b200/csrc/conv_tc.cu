@@ -59,6 +59,8 @@ constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz i
 constexpr int kPackElems = kNC1 + kNW2 + kNW3 + kNW4;
 // all seven operand images (conv1 Toeplitz, conv2-4 forward + dgrad) in one launch
 __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
+    bc::pdl_wait();
+    bc::pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kNC1) {
         // step s = (ci,ky): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu)
@@ -79,7 +81,7 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
 int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
     ctc::PackArgs pa{c->params + a.w[0], c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed};
-    ctc::pack_all_kernel<<<(ctc::kPackElems + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
+    bc::launch_pdl(ctc::pack_all_kernel, dim3((ctc::kPackElems + 255) / 256), dim3(256), 0, (cudaStream_t)stream, pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
     BC_CUDA_LAUNCH_CHECK("pack_all_kernel");
     return BC_OK;
 }

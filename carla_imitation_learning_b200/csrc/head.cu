@@ -26,6 +26,8 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
+    bc::pdl_wait();
+    bc::pdl_trigger();
     __shared__ float s_w0[64 * 128];
     __shared__ float s_w2[32 * 64];
     __shared__ float s_w4[MAXA * 32];
@@ -184,7 +186,7 @@ extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) {
     a.ow0 = ar.w[4]; a.ob0 = ar.b[4]; a.ow2 = ar.w[5]; a.ob2 = ar.b[5]; a.ow4 = ar.w[6]; a.ob4 = ar.b[6];
     a.B = c->batch; a.NA = c->n_actions; a.mode = head_mode; a.loss_scale = c->loss_scale;
     // the partial layout has a fixed number of copies, so the grid is fixed as well
-    head_kernel<<<bc::kHeadBlocks, NT, 0, (cudaStream_t)stream>>>(a);
+    bc::launch_pdl(head_kernel, dim3(bc::kHeadBlocks), dim3(NT), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("head_kernel");
     return BC_OK;
 }

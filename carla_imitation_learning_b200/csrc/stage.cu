@@ -90,6 +90,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // `plain` (optional): the same frames also as plain (n,256,256) bf16 planes; unit (R,g) owns pixels [12g, 12g+12) (g = 20: 16)
 __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ plain, int64_t n_units) {
+    bc::pdl_wait();          // the previous step's kernels still read the planes this one overwrites
+    bc::pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride)
         tp_write([&](int64_t plane, int R, int px0, uint32_t (&pk)[8]) {
@@ -168,7 +170,7 @@ extern "C" int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, 
     const int64_t units = n_frames * 3 * TP_NQ * TP_NG;
     const int64_t cap = (int64_t)bc::num_sms() * 16;
     const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
-    stage_gray_tp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
+    bc::launch_pdl(stage_gray_tp_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
     BC_CUDA_LAUNCH_CHECK("stage_gray_tp_kernel");
     return BC_OK;
 }

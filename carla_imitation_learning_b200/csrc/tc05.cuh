@@ -108,6 +108,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization (bc::launch_pdl) may start while their
+// predecessor in the stream is still running: pdl_trigger() in the predecessor allows it, pdl_wait() in the dependent
+// blocks until the predecessor grid has completed and its memory is visible. Everything before pdl_wait() -- barrier
+// init, TMEM allocation, shared-memory zeroing -- overlaps the predecessor's tail; nothing there may touch global
+// memory written inside the step. Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
