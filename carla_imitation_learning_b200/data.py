@@ -16,7 +16,8 @@ from typing import Iterator, Optional, Tuple
 import numpy as np
 import torch
 
-from .engine import sliding_window, stage_gray
+from . import _lib
+from .engine import StagedBatch, sliding_window, stage_frames, stage_gray
 
 
 def synthetic_sequence(seed: int, n_frames: int, h: int = 256, w: int = 256, n_actions: int = 9,
@@ -57,14 +58,15 @@ def continous_to_discreet(steer, throttle, brake, steer_threshold: float = 0.05)
 class SequentialFrames:
     """Iterable of (x, y) batches over one frame sequence, staged on the device.
 
-    x is a (b, frame_skip, H, W) strided view into the staged gray planes (f32 or bf16),
-    y the (b,) int64 labels of the frames that follow each window. The last batch may be
+    x is a (b, frame_skip, H, W) strided view into the staged gray planes (f32 or bf16) or, with
+    layout='tp' (the bf16 tensor-core mode), a StagedBatch of Toeplitz-ready planes written by the same
+    single staging pass; y the (b,) int64 labels of the frames that follow each window. The last batch may be
     short (the reference's DataLoader has no drop_last). Host frames are pinned; chunk k+1's
     H2D copy and staging run on a side stream while the trainer consumes chunk k.
     """
 
     def __init__(self, frames_u8: np.ndarray, labels: np.ndarray, batch_size: int = 64, frame_skip: int = 4,
-                 device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32):
+                 device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32, layout: str = "plain"):
         if frames_u8.dtype != np.uint8 or frames_u8.ndim != 4 or frames_u8.shape[-1] != 3:
             raise ValueError("frames must be (N,H,W,3) uint8")
         if len(labels) != len(frames_u8):
@@ -82,7 +84,15 @@ class SequentialFrames:
         n, h, w, _ = frames_u8.shape
         rows = self.batch_size + frame_skip
         self._raw = [torch.empty((rows, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
-        self._gray = [torch.empty((rows, h, w), dtype=dtype, device=self.device) for _ in range(2)]
+        if layout not in ("plain", "tp"):
+            raise ValueError("layout is 'plain' (gray planes) or 'tp' (Toeplitz-ready bf16 planes for precision='bf16')")
+        if layout == "tp" and (h, w, frame_skip) != (256, 256, 4):
+            raise ValueError("the Toeplitz-ready layout is defined for 256x256 frames and frame_skip 4")
+        self.layout = layout
+        if layout == "tp":
+            self._gray = [torch.empty((rows, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=self.device) for _ in range(2)]
+        else:
+            self._gray = [torch.empty((rows, h, w), dtype=dtype, device=self.device) for _ in range(2)]
 
     def __len__(self) -> int:
         return (self.n_samples + self.batch_size - 1) // self.batch_size
@@ -92,7 +102,10 @@ class SequentialFrames:
         hi = min(lo + self.batch_size, self.n_samples) + self.frame_skip
         with torch.cuda.stream(self._copy_stream):
             self._raw[slot][:hi - lo].copy_(self.frames[lo:hi], non_blocking=True)
-            stage_gray(self._raw[slot][:hi - lo], out=self._gray[slot][:hi - lo])
+            if self.layout == "tp":
+                stage_frames(self._raw[slot][:hi - lo], out=StagedBatch(self._gray[slot][:hi - lo], None, self.frame_skip))
+            else:
+                stage_gray(self._raw[slot][:hi - lo], out=self._gray[slot][:hi - lo])
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return ev
@@ -110,7 +123,10 @@ class SequentialFrames:
                 ev = self._produce(k + 1, slot ^ 1)
             lo = k * self.batch_size
             b = min(self.batch_size, self.n_samples - lo)
-            x = sliding_window(self._gray[slot][:b + self.frame_skip], self.frame_skip)
+            if self.layout == "tp":
+                x = StagedBatch(self._gray[slot][:b + self.frame_skip], None, self.frame_skip)
+            else:
+                x = sliding_window(self._gray[slot][:b + self.frame_skip], self.frame_skip)
             y = self.labels[lo + self.frame_skip: lo + self.frame_skip + b]
             yield x, y
 
@@ -129,5 +145,6 @@ def sequential_train_val_test_iterator(hparams, frames_by_split=None):
         else:
             frames, labels = synthetic_sequence(i, (8 if split == "train" else 2) * bs + fs,
                                                 n_actions=int(hparams['n_actions']))
-        out[f"{split}_dataloader"] = SequentialFrames(frames, labels, bs, fs)
+        bf16 = (hparams.get('precision', 'fp32') if hasattr(hparams, 'get') else 'fp32') == 'bf16'
+        out[f"{split}_dataloader"] = SequentialFrames(frames, labels, bs, fs, layout="tp" if bf16 else "plain")
     return out

@@ -447,3 +447,30 @@ def test_stage_frames_feeds_both_layouts_and_matches_the_plain_path():
     assert torch.equal(net(sb), b2.logits)
     with pytest.raises(ValueError):
         ConvNet1({"obs_size": 4, "n_actions": 9}).to(dev).engine().forward(sb)      # fp32 mode reads plain f32/bf16 planes
+
+
+def test_sequential_loader_feeds_the_bf16_mode_with_staged_batches():
+    """SequentialFrames(layout='tp') (the device-side SequentialTorchDataset for precision='bf16') yields StagedBatch
+    windows, short last batch included; a training step on them is bitwise the step on the plain-plane loader's batch."""
+    from carla_imitation_learning_b200 import StagedBatch
+    from carla_imitation_learning_b200.data import SequentialFrames, synthetic_sequence
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    frames, labels = synthetic_sequence(3, 23)                       # 19 samples: batches of 8, 8, 3
+    tp = SequentialFrames(frames, labels, batch_size=8, layout="tp")
+    plain = SequentialFrames(frames, labels, batch_size=8, dtype=torch.bfloat16)
+    assert len(tp) == 3
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
+    eng = net.engine()
+    sizes = []
+    for (xa, ya), (xb, yb) in zip(tp, plain):
+        assert isinstance(xa, StagedBatch) and torch.equal(ya, yb) and tuple(xa.shape) == tuple(xb.shape)
+        la = eng.train_forward_backward(xa, ya).loss.clone()
+        ga = eng.grads.clone()
+        lb = eng.train_forward_backward(xb, yb).loss.clone()
+        assert torch.equal(la, lb) and torch.equal(ga, eng.grads)
+        sizes.append(xa.shape[0])
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    assert sizes == [8, 8, 3]
