@@ -414,8 +414,8 @@ def run_b200(args):
                        "final_loss": loss_dev},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (B + 4) * FRAME_BYTES + 8 * B, "d2h_bytes_per_step": 4},
-            # per step: stage, [pack], 4 conv fwd, head, 3 x ([unpool,] wgrad, dgrad), conv1 wgrad, reduce, adam tick, adam
-            "gpu_launches": (20 if args.mode == "bf16" else 16) * args.steps,
+            # per step: stage, [pack], 4 conv fwd, head, 3 x (wgrad, dgrad), conv1 wgrad, reduce, adam (tick folded in)
+            "gpu_launches": (16 if args.mode == "bf16" else 15) * args.steps,
             "roofline": {"kernel": ("conv1_tp_kernel (tcgen05 Toeplitz implicit GEMM on Toeplitz-ready planes, bf16)" if args.mode == "bf16"
                                     else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",

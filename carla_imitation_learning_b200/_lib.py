@@ -57,6 +57,7 @@ EXPORTS = {
     "bc_loss_reduce": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_adam_tick": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bc_adam_tick_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bc_adam_step_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bc_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

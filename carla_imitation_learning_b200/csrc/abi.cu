@@ -44,6 +44,52 @@ __global__ void adam_tick_kernel(double* st) {
     st[7] = sqrt(1.0 - pow(st[2], step));
 }
 
+// tick folded into the update: every CTA derives the step's scalars from st[4] + 1 itself (same f64 formulas as
+// adam_tick_kernel), the last CTA to finish publishes them and the new step count. st has 9 doubles here: [8] is the
+// CTA counter (as u32). Saves one launch per step.
+__device__ __forceinline__ void adam_scalars(const double* st, double* s_sc) {
+    const double step = st[4] + 1.0;
+    s_sc[0] = step;
+    s_sc[1] = st[0] / (1.0 - pow(st[1], step));
+    s_sc[2] = sqrt(1.0 - pow(st[2], step));
+}
+__device__ __forceinline__ void adam_publish(double* st, const double* s_sc) {   // called by thread 0 of every CTA after its work
+    __threadfence();
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(st + 8);
+    if (atomicAdd(ctr, 1u) == gridDim.x - 1) {
+        st[4] = s_sc[0]; st[6] = s_sc[1]; st[7] = s_sc[2];
+        *ctr = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) adam_tick_step_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                             float4* __restrict__ m, float4* __restrict__ v,
+                                                             double* __restrict__ st, int64_t n4) {
+    __shared__ double s_sc[3];
+    bc::pdl_wait();
+    bc::pdl_trigger();
+    if (threadIdx.x == 0) adam_scalars(st, s_sc);
+    __syncthreads();
+    const float w1 = (float)(1.0 - st[1]), b2 = (float)st[2], w2 = (float)(1.0 - st[2]), eps = (float)st[3];
+    const float gs = (float)st[5], neg_step = (float)(-s_sc[1]), bc2s = (float)s_sc[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = G[k] * gs;
+            M[k] = __fmaf_rn(w1, gk - M[k], M[k]);
+            V[k] = __fmaf_rn(w2 * gk, gk, V[k] * b2);
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V[k]), bc2s), eps);
+            P[k] = __fmaf_rn(neg_step, __fdiv_rn(M[k], denom), P[k]);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) adam_publish(st, s_sc);
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                    const double* __restrict__ st, int64_t n4) {
@@ -112,11 +158,13 @@ constexpr int kSigReady = 256, kSigDone = 320;               // u32 word offsets
 
 __global__ void __launch_bounds__(256) adam_exchange_kernel(float4* __restrict__ p, const float4* const* __restrict__ peer_grads,
                                                             uint32_t* const* __restrict__ peer_signals, float4* __restrict__ m,
-                                                            float4* __restrict__ v, const double* __restrict__ st,
+                                                            float4* __restrict__ v, double* __restrict__ st,
                                                             uint32_t* __restrict__ sync, int64_t n4, int rank, int world, int* err) {
     __shared__ int s_last;
+    __shared__ double s_sc[3];
     bc::pdl_wait();
     bc::pdl_trigger();
+    if (threadIdx.x == 0) adam_scalars(st, s_sc);          // the tick is folded in (published by the last CTA, phase C)
     const uint32_t epoch = sync[0] + 1;
     uint32_t* my_sig = peer_signals[rank];
     // ---- A
@@ -128,7 +176,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(float4* __restrict__
     __syncthreads();
     // ---- B
     const float w1 = (float)(1.0 - st[1]), b2 = (float)st[2], w2 = (float)(1.0 - st[2]), eps = (float)st[3];
-    const float gs = (float)st[5], neg_step = (float)(-st[6]), bc2s = (float)st[7];
+    const float gs = (float)st[5], neg_step = (float)(-s_sc[1]), bc2s = (float)s_sc[2];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 gg = ld_relaxed_sys_f4(peer_grads[0] + i);
@@ -161,7 +209,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(float4* __restrict__
             wait_epoch(my_sig + kSigDone + threadIdx.x, epoch, err);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { sync[1] = 0; sync[0] = epoch; }
+        if (threadIdx.x == 0) { sync[1] = 0; sync[0] = epoch; st[4] = s_sc[0]; st[6] = s_sc[1]; st[7] = s_sc[2]; }
     }
 }
 
@@ -241,8 +289,23 @@ int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
     return BC_OK;
 }
 
+int bc_adam_tick_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double* state9, int64_t n, void* stream) {
+    BC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state9, "bc_adam_tick_step: null pointer");
+    BC_CHECK_ARG(n >= 0 && n % 4 == 0, "bc_adam_tick_step: n=%lld must be a multiple of 4 (the arena is padded)", (long long)n);
+    BC_CHECK_ARG(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "bc_adam_tick_step: 16 B alignment");
+    const int64_t n4 = n / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    const int cap = bc::num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;                               // n == 0 still ticks
+    bc::launch_pdl(adam_tick_step_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (float4*)params, (const float4*)grads,
+                   (float4*)exp_avg, (float4*)exp_avg_sq, state9, n4);
+    BC_CUDA_LAUNCH_CHECK("adam_tick_step_kernel");
+    return BC_OK;
+}
+
 int bc_adam_step_exchange(float* params, const void* peer_grads_dev, const void* peer_signals_dev, float* exp_avg, float* exp_avg_sq,
-                          const double* state, uint32_t* sync_state, int64_t n, int rank, int world, int* err_flag, void* stream) {
+                          double* state, uint32_t* sync_state, int64_t n, int rank, int world, int* err_flag, void* stream) {
     BC_CHECK_ARG(params && peer_grads_dev && peer_signals_dev && exp_avg && exp_avg_sq && state && sync_state, "bc_adam_step_exchange: null pointer");
     BC_CHECK_ARG(n > 0 && n % 4 == 0, "bc_adam_step_exchange: n=%lld must be a positive multiple of 4", (long long)n);
     BC_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bc_adam_step_exchange: rank %d of %d", rank, world);

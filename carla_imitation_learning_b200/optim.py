@@ -48,7 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
         old = self._bound
         m = torch.zeros_like(arena)
         v = torch.zeros_like(arena)
-        st = torch.zeros(8, dtype=torch.float64, device=arena.device)
+        st = torch.zeros(9, dtype=torch.float64, device=arena.device)     # 8 scalars (csrc/abi.cu) + the CTA counter of the fused tick
         if old is not None:  # the arena moved: carry the moments over
             m.copy_(old[1]); v.copy_(old[2]); st.copy_(old[3])
         g = self.param_groups[0]
@@ -106,14 +106,13 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
     def step_flat(self, flat_grads: torch.Tensor) -> None:
-        """One tick + one fused update, gradients given as an arena-shaped tensor (the engine's grads)."""
+        """Tick and fused update in one launch, gradients given as an arena-shaped tensor (the engine's grads)."""
         arena, m, v, st, _ = self._bind()
         self._sync_scalars(st)
         lib, s = _lib.lib(), _stream_ptr()
         with torch.cuda.device(arena.device):
-            _lib.check(lib.bc_adam_tick(st.data_ptr(), s), "bc_adam_tick")
-            _lib.check(lib.bc_adam_step(arena.data_ptr(), flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                        st.data_ptr(), arena.numel(), s), "bc_adam_step")
+            _lib.check(lib.bc_adam_tick_step(arena.data_ptr(), flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                             st.data_ptr(), arena.numel(), s), "bc_adam_tick_step")
 
     def step_exchange(self, peer) -> None:
         """Data-parallel step: tick + ONE kernel that sums every rank's gradient arena straight from NVLink peer memory
@@ -122,7 +121,6 @@ class FusedAdam(torch.optim.Optimizer):
         self._sync_scalars(st)
         lib, s = _lib.lib(), _stream_ptr()
         with torch.cuda.device(arena.device):
-            _lib.check(lib.bc_adam_tick(st.data_ptr(), s), "bc_adam_tick")
             _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), peer.grads_dev, peer.signals_dev, m.data_ptr(), v.data_ptr(),
                                                  st.data_ptr(), peer.sync.data_ptr(), arena.numel(), peer.rank, peer.world,
                                                  peer.err.data_ptr(), s), "bc_adam_step_exchange")

@@ -133,15 +133,18 @@ int bc_loss_reduce(const bc_ctx* c, void* stream);                 /* head CTAs'
 int bc_adam_tick(double* state, void* stream);
 int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                  const double* state, int64_t n, void* stream);
+/* tick + step in ONE launch (what the training step uses): state9 = the 8 doubles above + one more word used as a CTA counter */
+int bc_adam_tick_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double* state9, int64_t n, void* stream);
 
 /* ---- a12 folded into a11: the DDP gradient mean (train.py:125 `pl.Trainer(gpus=[...])`, utils.py:60-64) inside the Adam step.
  * peer_grads_dev / peer_signals_dev: DEVICE arrays of `world` pointers -- rank r's gradient arena and signal pad mapped into
  * this process (peer memory over NVLink; torch symmetric memory provides both). Each rank launches this once per step after its
  * own gradients are complete: flag exchange, sum of the `world` arenas in rank order read straight from peer memory, Adam update
- * with state[5] = grad_scale = 1/world, second flag exchange (nobody still reads this rank's gradients when the kernel ends).
+ * with state[5] = grad_scale = 1/world (the tick is folded in: do NOT call bc_adam_tick before it), second flag exchange (nobody
+ * still reads this rank's gradients when the kernel ends).
  * sync_state: 2 device u32 {epoch, CTA counter}, zero-initialised, private to the rank. *err_flag = 2 if a peer never arrived. */
 int bc_adam_step_exchange(float* params, const void* peer_grads_dev, const void* peer_signals_dev, float* exp_avg, float* exp_avg_sq,
-                          const double* state, uint32_t* sync_state, int64_t n, int rank, int world, int32_t* err_flag, void* stream);
+                          double* state, uint32_t* sync_state, int64_t n, int rank, int world, int32_t* err_flag, void* stream);
 
 /* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
 int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);
