@@ -87,21 +87,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// `plain` (optional): the same frames also as plain (n,256,256) bf16 planes; unit (R,g) owns pixels [12g, 12g+12) (g = 20: 16)
+// Every pixel is converted ONCE: unit (R, g'), g' = 0..21, owns the 12 pixels [12g', 12g'+12) of image row R (g' = 21: the
+// last 4) and writes them where they belong -- pixels 0..7 as the h=0 chunk and 8..11 as the first half of the h=1 chunk of
+// segment g', pixels 0..3 also as the second half of the h=1 chunk of segment g'-1 (the 4-pixel overlap of neighbouring
+// segments). The FP64 gray arithmetic is the limiter of this kernel, so 12 instead of 16 conversions per thread matters.
+// `plain` (optional): the same gray values also as plain (n,256,256) bf16 planes.
+constexpr int TP_NU = TP_NG + 1;
 __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ plain, int64_t n_units) {
     bc::pdl_wait();          // the previous step's kernels still read the planes this one overwrites
     bc::pdl_trigger();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride)
-        tp_write([&](int64_t plane, int R, int px0, uint32_t (&pk)[8]) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + ((plane * BC_H + R) * BC_W + px0) * 3);
-            uint32_t w[12];
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {
+        const int g = (int)(u % TP_NU), q = (int)((u / TP_NU) % TP_NQ), c = (int)((u / (TP_NU * TP_NQ)) % 3);
+        const int64_t plane = u / (TP_NU * TP_NQ * 3);
+        const int R = 3 * q + c;
+        uint32_t pk[6] = {0, 0, 0, 0, 0, 0};                 // 12 gray values as bf16 pairs; rows R >= 256 stay zero
+        if (R < BC_H) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + ((plane * BC_H + R) * BC_W + 12 * g) * 3);
+            uint32_t w[9];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) w[i] = __ldg(src + i);
-            float v[16];
+            for (int i = 0; i < 9; ++i) w[i] = (g < TP_NG || i < 3) ? __ldg(src + i) : 0u;     // g' = 21 has 4 pixels = 12 bytes left
+            float v[12];
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
+            for (int p = 0; p < 12; ++p) {
                 uint32_t ch[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -111,13 +120,21 @@ __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __res
                 v[p] = gray_px(ch[0], ch[1], ch[2]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+            for (int i = 0; i < 6; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             if (plain) {
-                uint2* dst = reinterpret_cast<uint2*>(plain + (plane * BC_H + R) * BC_W + px0);
-                dst[0] = make_uint2(pk[0], pk[1]); dst[1] = make_uint2(pk[2], pk[3]); dst[2] = make_uint2(pk[4], pk[5]);
-                if (px0 == 240) dst[3] = make_uint2(pk[6], pk[7]);
+                uint2* dst = reinterpret_cast<uint2*>(plain + (plane * BC_H + R) * BC_W + 12 * g);
+                dst[0] = make_uint2(pk[0], pk[1]);
+                if (g < TP_NG) { dst[1] = make_uint2(pk[2], pk[3]); dst[2] = make_uint2(pk[4], pk[5]); }
             }
-        }, out, u);
+        }
+        __nv_bfloat16* row0 = out + plane * BC_TP_PLANE_ELEMS + ((int64_t)(c * 2) * TP_NQ + q) * (TP_NG * 8);   // (c, h=0, q)
+        __nv_bfloat16* row1 = row0 + TP_NQ * TP_NG * 8;                                                          // (c, h=1, q)
+        if (g < TP_NG) {
+            *reinterpret_cast<uint4*>(row0 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint2*>(row1 + g * 8) = make_uint2(pk[4], pk[5]);
+        }
+        if (g > 0) *reinterpret_cast<uint2*>(row1 + (g - 1) * 8 + 4) = make_uint2(pk[0], pk[1]);
+    }
 }
 
 // plain planes (f32 or bf16, rows contiguous, `plane_stride` elements apart) -> TP planes
@@ -167,7 +184,7 @@ extern "C" int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, 
     BC_CHECK_ARG(rgb && tp && n_frames >= 0, "bc_stage_gray_tp: null pointer");
     BC_CHECK_ARG(((uintptr_t)rgb % 4 == 0) && ((uintptr_t)tp % 16 == 0) && ((uintptr_t)plain_bf16 % 8 == 0), "bc_stage_gray_tp: alignment");
     if (n_frames == 0) return BC_OK;
-    const int64_t units = n_frames * 3 * TP_NQ * TP_NG;
+    const int64_t units = n_frames * 3 * TP_NQ * TP_NU;
     const int64_t cap = (int64_t)bc::num_sms() * 16;
     const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
     bc::launch_pdl(stage_gray_tp_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
@@ -185,7 +202,7 @@ extern "C" int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, i
     const int sms = bc::num_sms();
     if (out_dtype == BC_BF16_TP) {
         BC_CHECK_ARG(n_pixels % (BC_H * BC_W) == 0, "bc_stage_gray: the TP layout is defined for whole 256x256 frames");
-        const int64_t units = n_pixels / (BC_H * BC_W) * 3 * TP_NQ * TP_NG;
+        const int64_t units = n_pixels / (BC_H * BC_W) * 3 * TP_NQ * TP_NU;
         int blocks = (int)((units + 255) / 256 < (int64_t)sms * 16 ? (units + 255) / 256 : (int64_t)sms * 16);
         stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, nullptr, units);
     } else if (out_dtype == BC_F32) {
