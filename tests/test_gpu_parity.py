@@ -415,7 +415,7 @@ def test_loss_curve_1k_steps_within_one_percent(golden_dir):
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_inference_sweep_batches_match_oracle(mode):
-    """BASELINE configs[4]: inference-only policy forward + greedy action over a batch sweep (1..1024; the closed-loop
+    """BASELINE configs[4]: inference-only policy forward + greedy action over a batch sweep (1..4096; the closed-loop
     rollout of src/data/stat.py:41 uses B=1). Logits vs the oracle forward on the same weights: rel 1e-5 (fp32 mode) /
     2e-2 (bf16 mode); actions equal wherever the oracle's top-2 margin exceeds the tolerance."""
     from carla_imitation_learning_b200 import stage_frames, stage_gray, sliding_window
@@ -425,11 +425,11 @@ def test_inference_sweep_batches_match_oracle(mode):
     net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": mode}).to(dev)
     params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     tol = REL_F32 if mode == "fp32" else 2e-2
-    frames, _ = O.synth_frames(4242, 1024 + 4)
+    frames, _ = O.synth_frames(4242, 4096 + 4)
     fr = torch.from_numpy(frames).to(dev)
     gray = stage_gray(fr)
     ref_all = O.forward(params, torch.from_numpy(O.gray_stack(frames[:132])).unfold(0, 4, 1).permute(0, 3, 1, 2)[:128])
-    for B in (1, 2, 31, 128, 1024):
+    for B in (1, 2, 31, 128, 1024, 4096):
         if mode == "bf16":
             x = stage_frames(fr[:B + 4])
         else:
