@@ -75,7 +75,7 @@ __host__ inline Arena arena_layout(int obs, int na) {
 
 // partial-sum workspace: per segment, NPART[seg] copies of seg_len floats, then loss partials
 constexpr int kHeadBlocks = 128;    // partial copies of the head segment (= head CTAs: 2 samples each at B=256)
-constexpr int kWgradParts[4] = {296, 29, 37, 8};  // conv1..conv4: partial-sum slots = grid.x of the wgrad kernels (conv2: x 5 kernel rows = 145 CTAs, conv3: x 4 = 148)
+constexpr int kWgradParts[4] = {296, 29, 37, 16};  // conv1..conv4: partial-sum slots = grid.x of the wgrad kernels (conv2: x 5 kernel rows = 145 CTAs, conv3: x 4 = 148, conv4: x 6 classes = 96)
 struct Partials { int64_t off[5]; int nparts[5]; int64_t loss_off; int64_t total; };
 __host__ inline Partials partials_layout(const Arena& a) {
     Partials p{};

@@ -8,7 +8,7 @@
 //             are the 2x2 conv outputs, pooled through shared memory.
 //   dgrad   : per image a 6x6 zero-padded routed gradient (pitch 64 pixels, 2 images per tile) built in smem.
 //   wgrad   : K = pixels (one 16-pixel K-step = one image), A = the input through a descriptor whose M-cores are pixel
-//             shifts (kx'), B = the routed gradient [co/8][pixel][8] built in smem; grid = (8 partial-sum slots, 6 classes
+//             shifts (kx'), B = the routed gradient [co/8][pixel][8] built in smem; grid = (16 partial-sum slots, 6 classes
 //             = kernel row ky x half of the input-channel groups), 4 accumulators of 128 columns per CTA.
 #include "bc_common.cuh"
 #include "tc05.cuh"
