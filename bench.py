@@ -211,7 +211,7 @@ def run_b200(args):
         host_frames.append(hf); host_labels.append(hl)
         dev_frames.append(hf.to(dev)); dev_labels.append(hl.to(dev))
     if args.mode == "bf16":
-        eng.set_mode("bf16")           # before alloc(): bf16 mode adds the NHWC bf16 activation copies
+        eng.set_mode("bf16")           # before alloc(): bf16 mode adds the bf16 activation copies (P8 / P8B layouts)
         staged = stage_frames(dev_frames[0])          # Toeplitz-ready bf16 planes, rewritten in place every step
         bufs = eng.alloc(B, staged, dev_labels[0], True)
 

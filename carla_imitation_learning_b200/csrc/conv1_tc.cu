@@ -62,7 +62,7 @@ constexpr int SMAX = 4;
 constexpr int OFF_B = 0;
 constexpr int OFF_RING = OFF_B + B_BYTES;
 constexpr int OFF_S = (OFF_RING + NSLOT * SLOT_BYTES + 64 + 127) / 128 * 128;   // 64 B: the over-read of the last slice
-constexpr int P_BYTES = 2 * 28 * 16 * 2;                  // one tile's pooled outputs as NHWC bf16
+constexpr int P_BYTES = 2 * 28 * 16 * 2;                  // one tile's pooled outputs as bf16, P8 order [c/8][pixel][8]
 constexpr int OFF_P = OFF_S + 2 * S_BYTES;
 constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;
 constexpr int OFF_BAR = (OFF_BIAS + 64 + 127) / 128 * 128;

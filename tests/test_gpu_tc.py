@@ -105,7 +105,7 @@ def _from_act_bf16(t, idx, shape):
 
 @pytest.mark.parametrize("layer,B", [(1, 3), (1, 37), (2, 5), (2, 1), (3, 33), (3, 1), (3, 70)])
 def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
-    """conv2/3 + ReLU + pool as shifted-window tcgen05 GEMMs over P8 bf16 activations, conv4 as a gathered implicit GEMM."""
+    """conv2/3/4 + ReLU + pool as shifted-window tcgen05 GEMMs over P8 / P8B bf16 activations."""
     import ctypes as C
     from carla_imitation_learning_b200 import _lib
     from oracle import bc_oracle as O
@@ -136,14 +136,14 @@ def test_conv234_tcgen05_matches_bf16_rounded_oracle(layer, B):
     err = float((got - ref).abs().max() / ref.abs().max())
     assert err <= 1e-5, err
     _check_routing(z, bufs.amax[layer].cpu(), got, 2)
-    if layer < 3:   # the NHWC bf16 copy handed to the next layer
+    if layer < 3:   # the bf16 copy handed to the next layer (P8 / P8B)
         back = _from_act_bf16(bufs.act_bf16[layer].float().cpu(), layer, bufs.act[layer].shape)
         assert torch.equal(back, bufs.act[layer].cpu().to(torch.bfloat16).float())
 
 
 @pytest.mark.parametrize("B", [2, 37])
 def test_dgrad_tcgen05_matches_exact_f32_dgrad(B):
-    """Dense tensor-core dgrad (unpool -> implicit GEMM) vs the exact routing-sparse f32 kernel, same inputs."""
+    """Dense tensor-core dgrad (routed gradient built in smem -> shifted-window GEMM) vs the exact routing-sparse f32 kernel, same inputs."""
     import ctypes as C
     from carla_imitation_learning_b200 import _lib, stage_gray, sliding_window
     from oracle import bc_oracle as O
