@@ -1,0 +1,117 @@
+"""CPU models of the operand layouts the tcgen05 kernels rely on (include/bc_b200.h BC_BF16_TP, csrc/conv1_tc.cu,
+csrc/conv_sw.cu): the descriptor arithmetic written out in numpy must reproduce the convolution's operands exactly.
+Pure index identities -- no GPU, no oracle numerics -- so a layout change that breaks a kernel's assumption fails here first."""
+import numpy as np
+import pytest
+
+ROWB_ELEMS = 21 * 8            # one (q) row of a TP piece: 21 groups x 8 pixels
+
+
+def tp_plane(img):
+    """(256,256) -> (3,2,86,21,8): TP[c][h][q][g][i] = img[3q+c][12g+8h+i], zero rows beyond 255."""
+    pad = np.zeros((258, 256), img.dtype)
+    pad[:256] = img
+    R = 3 * np.arange(86)[None, :] + np.arange(3)[:, None]
+    px = 12 * np.arange(21)[None, :, None] + 8 * np.arange(2)[:, None, None] + np.arange(8)[None, None, :]
+    return pad[R[:, None, :, None, None], px[None, :, None, :, :]]
+
+
+@pytest.mark.parametrize("ty", [0, 5, 13])
+def test_conv1_a_operand_is_a_strided_view_of_the_tp_tile(ty):
+    """conv1_tp_kernel: the slot holds pieces (c,h) = rows q0..q0+nq(c)-1; kernel row ky = 3d + c reads the 126x16 slice
+    starting d rows in, 16 B row pitch (SBO 128 B per 8 rows), K halves one piece apart (LBO)."""
+    rng = np.random.default_rng(ty)
+    img = rng.integers(1, 1 << 15, size=(256, 256)).astype(np.int32)
+    tp = tp_plane(img)
+    nq = (8, 7, 7)
+    slot, off = [], {}
+    for c in range(3):
+        for h in range(2):
+            off[c, h] = sum(len(p) for p in slot)
+            slot.append(tp[c, h, 6 * ty: 6 * ty + nq[c]].reshape(-1))
+    slot = np.concatenate(slot + [np.zeros(64, np.int32)])          # + the over-read pad
+    for ky in range(7):
+        c, d = ky % 3, ky // 3
+        start, lbo = off[c, 0] + d * ROWB_ELEMS, off[c, 1] - off[c, 0]
+        r, k = np.arange(126)[:, None], np.arange(16)[None, :]
+        A = slot[start + (k // 8) * lbo + r * 8 + k % 8]            # UMMA K-major, no swizzle: row pitch 16 B = 8 elements
+        want = img[3 * (6 * ty + r // 21) + ky, 12 * (r % 21) + k]
+        assert np.array_equal(A, want), ky
+
+
+def test_conv1_wgrad_slices_have_a_uniform_stride():
+    """conv1_wgrad_tp_kernel: the 14 (ky,h) slices = rows d..d+5 of TP piece (c,h) are contiguous 2016 B runs in HBM, so
+    14 bulk copies can lay them at a uniform stride (the M-direction SBO of the MN-major operand)."""
+    img = np.arange(256 * 256, dtype=np.int32).reshape(256, 256)
+    tp = tp_plane(img)
+    ty = 7
+    for ky in range(7):
+        c, d = ky % 3, ky // 3
+        for h in range(2):
+            piece = tp[c, h].reshape(-1)                              # (q, g, i) contiguous in HBM
+            run = piece[(6 * ty + d) * ROWB_ELEMS: (6 * ty + d + 6) * ROWB_ELEMS]
+            r, i = np.arange(126)[:, None], np.arange(8)[None, :]
+            assert np.array_equal(run.reshape(126, 8), img[3 * (6 * ty + r // 21) + ky, 12 * (r % 21) + 8 * h + i])
+
+
+def p8(x):
+    """(C,H,W) -> (C/8, H*W, 8): the shifted-window kernels' activation layout."""
+    C, H, W = x.shape
+    return x.reshape(C // 8, 8, H * W).transpose(0, 2, 1)
+
+
+def test_shifted_window_forward_operand():
+    """conv_sw.cu forward: row m = oy*W_in + ox; tap (ky,kx), channel block cb = the same image shifted by ky*W_in + kx
+    pixels, planes 2cb and 2cb+1 (LBO = one plane)."""
+    rng = np.random.default_rng(0)
+    C, H, K = 16, 28, 5
+    x = rng.integers(1, 1 << 15, size=(C, H, H)).astype(np.int32)
+    img = np.concatenate([p8(x).reshape(-1), np.zeros(4096, np.int32)])
+    plane = H * H * 8
+    m = np.arange(24 * H)[:, None]                                    # all conv rows, pitch W_in
+    k = np.arange(16)[None, :]
+    oy, ox = m // H, m % H
+    for ky, kx, cb in ((0, 0, 0), (4, 4, 0), (2, 3, 0)):
+        A = img[(2 * cb + k // 8) * plane + (m + ky * H + kx) * 8 + k % 8]
+        valid = (ox < H - K + 1)[:, 0]
+        want = x[16 * cb + k, oy + ky, np.minimum(ox + kx, H - 1)]
+        assert np.array_equal(A[valid], want[valid])
+
+
+def test_shifted_window_dgrad_is_a_correlation_of_the_padded_gradient():
+    """dX[iy][ix] = sum dYp[iy+ky'][ix+kx'] * W[K-1-ky'][K-1-kx'] with dYp = dY zero-padded by K-1 (size H_in + K - 1)."""
+    rng = np.random.default_rng(1)
+    H, K = 12, 4
+    Ho = H - K + 1
+    dy = rng.standard_normal((Ho, Ho))
+    w = rng.standard_normal((K, K))
+    dx = np.zeros((H, H))
+    for oy in range(Ho):
+        for ox in range(Ho):
+            dx[oy:oy + K, ox:ox + K] += dy[oy, ox] * w              # transpose of the forward correlation
+    WP = H + K - 1
+    dyp = np.zeros((WP, WP))
+    dyp[K - 1:K - 1 + Ho, K - 1:K - 1 + Ho] = dy
+    got = np.zeros((H, H))
+    for ky in range(K):
+        for kx in range(K):
+            got += dyp[ky:ky + H, kx:kx + H] * w[K - 1 - ky, K - 1 - kx]
+    assert np.allclose(got, dx, atol=1e-12)
+
+
+def test_shifted_window_wgrad_cores_are_pixel_shifts():
+    """conv_sw.cu wgrad: MN-major A with M-cores 16 B apart: row (kx', ci8), K index = pixel m reads
+    plane[m + ky*W_in + kx'][ci8]; with dY zero where ox >= W_out the product is the weight gradient."""
+    rng = np.random.default_rng(2)
+    C, H, K = 8, 12, 4
+    Ho = 8                                                            # pooled conv region
+    x = rng.standard_normal((C, H, H))
+    dy = np.zeros((Ho, H))
+    dy[:, :Ho] = rng.standard_normal((Ho, Ho))                       # linear pitch W_in, zero beyond the conv width
+    plane = np.concatenate([p8(x)[0].reshape(-1), np.zeros(64 * 8)])
+    m = np.arange(Ho * H)
+    for ky in range(K):
+        A = np.stack([plane[(m + ky * H + kx)[:, None] * 8 + np.arange(8)[None, :]] for kx in range(K)])   # (kx', m, ci8)
+        got = np.einsum("kmc,m->kc", A, dy.reshape(-1))
+        want = np.array([[np.sum(dy[:, :Ho] * x[ci, ky:ky + Ho, kx:kx + Ho]) for ci in range(8)] for kx in range(K)])
+        assert np.allclose(got, want, atol=1e-10)
