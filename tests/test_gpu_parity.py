@@ -473,3 +473,55 @@ def test_stacked_12_channel_variant_matches_oracle():
     for k, p in net.named_parameters():
         g = eng.grads[p._bc_offset:p._bc_offset + p.numel()].view(p.shape).cpu()
         assert _relerr(g, ref[k]) <= REL_F32, k
+
+
+def _peer_exchange_world1(_proc, out_path, port):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    try:
+        from carla_imitation_learning_b200 import FusedAdam, stage_frames
+        from carla_imitation_learning_b200.parallel import PeerExchangeStep
+        from src.architectures.nets import ConvNet1
+        frames, labels = O.synth_frames(9, 3 * 6 + 4)
+        res = []
+        for fused in (True, False):
+            torch.manual_seed(12345)
+            net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
+            eng = net.engine()
+            opt = FusedAdam(list(net.parameters()), lr=1e-3)
+            step = PeerExchangeStep(eng, opt) if fused else None
+            for s in range(3):
+                x = stage_frames(torch.from_numpy(frames[6 * s: 6 * s + 10]).to(dev))
+                y = torch.from_numpy(labels[6 * s + 4: 6 * s + 10]).to(dev)
+                eng.pack_weights()
+                bufs = eng.alloc(6, x, y, True)
+                if fused:
+                    step(bufs)
+                else:
+                    eng.enqueue_train(bufs)
+                    opt.step_flat(eng.grads)
+            torch.cuda.synchronize()
+            if fused:
+                step.peer.check()
+            res.append(net._arena.detach().cpu().numpy().copy())
+        np.save(out_path, np.stack(res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_peer_exchange_adam_degenerates_to_adam_on_one_rank(tmp_path):
+    """bc_adam_step_exchange (the data-parallel exchange fused into Adam over peer memory) on a world of ONE rank:
+    flag handshakes with itself, one arena summed, grad_scale 1 -> bitwise the plain fused Adam after 3 steps.
+    (The 2- and 8-GPU behaviour is checked by tools/dp_check.py; the driver's GPU test box has one GPU.)"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "w.npy")
+    mp.spawn(_peer_exchange_world1, args=(out, port), nprocs=1, join=True)
+    w = np.load(out)
+    assert np.array_equal(w[0], w[1])
