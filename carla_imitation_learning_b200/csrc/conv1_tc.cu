@@ -377,6 +377,8 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         const uint32_t v = (i * 16 < NA * A_SLOT && within >= 14 * VIEW) ? 0x3f803f80u : 0u;
         reinterpret_cast<uint4*>(smem + OFF_A)[i] = make_uint4(v, v, v, v);
     }
+    // the dY ring: rows 0..125 of a slot are rewritten for every sample tile, rows 126,127 stay zero
+    for (int i = threadIdx.x; i < NDY * DY_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + OFF_DY)[i] = make_uint4(0, 0, 0, 0);
     tc05::fence_async_smem();
     tc05::tc_fence_before();
     __syncthreads();
@@ -465,6 +467,26 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         const int grp = warp >= 9 ? 1 : 0;
         const int ew = warp - 4;
         const int te = threadIdx.x - (grp ? 288 : 128);
+        // One unit = (pooled pixel of the tile, 8 channels): its 3x3 conv positions x 8 channels are nine full 16 B stores
+        // (zeros except each channel's routed position), so a sample tile REWRITES rows 0..125 of its slot completely: the
+        // ring is zeroed once per kernel (rows 126,127 stay zero) and nothing is scattered 2 bytes at a time. The pooled
+        // gradients of the group's next sample tile are fetched into registers before the wait for its slot.
+        const int upx = te % 28, ucg = (te / 28) & 1, upyl = te / 56;       // units 0..111 of the 128 threads
+        const bool unit = te < 112;
+        float ug[8]; uint32_t upos = 0;
+        int pf_smp = -1, pf_ty = -1;                                        // which sample tile the registers hold
+        auto fetch = [&](int smp, int ty) {
+            pf_smp = smp; pf_ty = ty;
+            if (!unit) return;
+            const size_t g0 = (((size_t)smp * 16 + ucg * 8) * 28 + 2 * ty + upyl) * 28 + upx;
+            upos = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const size_t g = g0 + (size_t)k * 784;
+                ug[k] = aP[g] > 0.f ? gP[g] : 0.f;
+                upos |= (uint32_t)amax[g] << (4 * k);
+            }
+        };
         SegIter it(B, sliding);
         Seg sg;
         uint32_t kb = 0;
@@ -472,27 +494,39 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         while (ok && it.next(sg)) {
             for (int smp = sg.sa; ok && smp <= sg.sb; ++smp, ++kb) {
                 if ((int)(kb & 1) != grp) continue;
+                if (pf_smp != smp || pf_ty != sg.ty) fetch(smp, sg.ty);     // not prefetched (first tile, or a short segment ahead)
                 const uint32_t slot = kb % NDY;
                 ok = tc05::mbar_wait(dy_empty + slot, ((kb / NDY) & 1) ^ 1, err);
                 if (!ok) break;
                 uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
+                if (unit) {
 #pragma unroll
-                for (int q = 0; q < DY_BYTES / 16 / 128; ++q) reinterpret_cast<uint4*>(dy)[te + 128 * q] = make_uint4(0, 0, 0, 0);
-                if (grp) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int p = 0; p < 9; ++p) {
+                        uint32_t w[4];
 #pragma unroll
-                for (int q = 0; q < 7; ++q) {
-                    const int o = te + 128 * q;                      // 2 pooled rows x 16 channels x 28 columns
-                    const int px = o % 28, co = (o / 28) & 15, pyl = o / 448;
-                    const size_t g = (((size_t)smp * 16 + co) * 28 + 2 * sg.ty + pyl) * 28 + px;
-                    const float gv = aP[g] > 0.f ? gP[g] : 0.f;
-                    const int pos = amax[g];
-                    const int oyl = 3 * pyl + pos / 3, ox = 3 * px + pos % 3;
-                    const int r = oyl * NG + (ox >> 2), n = (ox & 3) * 16 + co;
-                    *reinterpret_cast<__nv_bfloat16*>(dy + (n >> 3) * 2048 + r * 16 + (n & 7) * 2) = __float2bfloat16_rn(gv);
+                        for (int k = 0; k < 4; ++k) {
+                            const float lo = ((upos >> (8 * k)) & 15u) == (uint32_t)p ? ug[2 * k] : 0.f;
+                            const float hi = ((upos >> (8 * k + 4)) & 15u) == (uint32_t)p ? ug[2 * k + 1] : 0.f;
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                            w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const int oyl = 3 * upyl + p / 3, ox = 3 * upx + p % 3;
+                        // row r = (oyl, ox / 4), column block = (ox % 4) * 2 + channel half: [n/8][128 rows][16 B]
+                        *reinterpret_cast<uint4*>(dy + ((ox & 3) * 2 + ucg) * 2048 + (oyl * NG + (ox >> 2)) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
                 }
                 tc05::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(dy_full + slot);
+                // prefetch this group's next sample tile (build kb + 2): the next sample of this segment, or the first of the next one
+                if (smp + 2 <= sg.sb) {
+                    fetch(smp + 2, sg.ty);
+                } else {
+                    SegIter itn = it;
+                    Seg sn;
+                    const int skip = smp + 2 - sg.sb - 1;          // 0 or 1 samples of the next segment belong to the other group
+                    if (itn.next(sn) && sn.sa + skip <= sn.sb) fetch(sn.sa + skip, sn.ty);
+                }
             }
         }
         // ---- epilogue (warps 4-7): fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
