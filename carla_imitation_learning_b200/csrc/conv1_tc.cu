@@ -14,6 +14,7 @@
 // no repack warps, no LDS/STS between the copy engine and the tensor core. Two kernels below:
 // conv1_tp_kernel (forward + bias + ReLU + pool3 + argmax) and conv1_wgrad_tp_kernel (weight/bias gradient).
 // All mbarrier waits are bounded and raise a device flag instead of hanging.
+#include <stdlib.h>
 #include "bc_common.cuh"
 #include "tc05.cuh"
 
@@ -91,7 +92,7 @@ struct TileIter {
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
                 const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
-                __nv_bfloat16* __restrict__ ybf, int B, int* err) {
+                __nv_bfloat16* __restrict__ ybf, int B, int* err, int ablate) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* b_full = bars;
@@ -141,6 +142,10 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                     const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
                     ok = tc05::mbar_wait(slot_empty + slot, ph ^ 1, err);
                     if (!ok) break;
+                    if (ablate & 2) {            // timing experiment (BC_C1FW_ABLATE): no plane loads
+                        if (lane == 0) tc05::mbar_arrive(slot_full + slot);
+                        continue;
+                    }
                     if (lane == 0) tc05::mbar_expect_tx(slot_full + slot, SLOT_BYTES);
                     __syncwarp();
                     if (lane < 6)
@@ -182,10 +187,12 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                         const uint64_t so = (uint64_t)((slot * SLOT_BYTES) >> 4);
                         const uint32_t d_tmem = tmem_base + idx * 64;
                         const uint64_t bb = bd0 + (uint64_t)(ci * 7 * (B_STEP >> 4));
+                        if (!(ablate & 1)) {         // timing experiment: bit 0 = no MMAs
 #pragma unroll
-                        for (int ky = 0; ky < 7; ++ky)
-                            tc05::mma_bf16(d_tmem, (ky % 3 == 0 ? ad_c0 : ad_c12) + so + (uint64_t)(a_off(ky) >> 4),
-                                           bb + (uint64_t)(ky * (B_STEP >> 4)), idesc, (ci | ky) > 0);
+                            for (int ky = 0; ky < 7; ++ky)
+                                tc05::mma_bf16(d_tmem, (ky % 3 == 0 ? ad_c0 : ad_c12) + so + (uint64_t)(a_off(ky) >> 4),
+                                               bb + (uint64_t)(ky * (B_STEP >> 4)), idesc, (ci | ky) > 0);
+                        }
                         tc05::mma_commit(slot_empty + slot);
                         if (ci == 3) tc05::mma_commit(t_full + idx);
                     }
@@ -351,7 +358,7 @@ struct SegIter {
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
                       const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
-                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err) {
+                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;                  // [NA]
@@ -404,6 +411,10 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
                     const int64_t pl = sliding ? (int64_t)P * sc : (int64_t)(P >> 2) * sn + (int64_t)(P & 3) * sc;
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(x + pl) + (size_t)(6 * sg.ty) * ROWB;
                     uint8_t* dst = smem + OFF_A + slot * A_SLOT;
+                    if (ablate & 2) {            // timing experiment (BC_C1WG_ABLATE): no plane loads
+                        if (lane == 0) tc05::mbar_arrive(a_full + slot);
+                        continue;
+                    }
                     if (lane == 0) tc05::mbar_expect_tx(a_full + slot, 14 * VIEW);
                     __syncwarp();
                     if (lane < 14) tc05::bulk_g2s(dst + dst_off, src + src_off, VIEW, a_full + slot);
@@ -440,9 +451,11 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
                     if (ok && tc05::elect_one()) {
                         const uint64_t a_st = ad0 + (uint64_t)((slot * A_SLOT) >> 4);
                         const uint64_t b_st = bd0 + (uint64_t)((dslot * DY_BYTES) >> 4);
+                        if (!(ablate & 1)) {         // timing experiment: bit 0 = no MMAs
 #pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            tc05::mma_bf16(d_tmem, a_st + (uint64_t)(u * 16), b_st + (uint64_t)(u * 16), idesc, (first && u == 0) ? 0u : 1u);
+                            for (int u = 0; u < 8; ++u)
+                                tc05::mma_bf16(d_tmem, a_st + (uint64_t)(u * 16), b_st + (uint64_t)(u * 16), idesc, (first && u == 0) ? 0u : 1u);
+                        }
                         tc05::mma_commit(a_empty + slot);
                         tc05::mma_commit(dy_empty + dslot);
                     }
@@ -473,61 +486,69 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         // gradients of the group's next sample tile are fetched into registers before the wait for its slot.
         const int upx = te % 28, ucg = (te / 28) & 1, upyl = te / 56;       // units 0..111 of the 128 threads
         const bool unit = te < 112;
-        float ug[8]; uint32_t upos = 0;
-        int pf_smp = -1, pf_ty = -1;                                        // which sample tile the registers hold
-        auto fetch = [&](int smp, int ty) {
-            pf_smp = smp; pf_ty = ty;
-            if (!unit) return;
-            const size_t g0 = (((size_t)smp * 16 + ucg * 8) * 28 + 2 * ty + upyl) * 28 + upx;
-            upos = 0;
+        // the CTA's builds in order (sample tiles of its segments); this group takes every second one. The global loads
+        // of a build are issued TWO group-builds ahead of its stores (two register sets): measured, the builders'
+        // load latency -- not the plane loads, not the MMAs -- was what bounded this kernel.
+        struct Build {
+            SegIter it; Seg sg; int smp; uint32_t kb; bool valid;
+            __device__ Build(int B_, bool sl) : it(B_, sl), smp(0), kb(0) { valid = it.next(sg); if (valid) smp = sg.sa; }
+            __device__ void step() {                       // next build of the CTA
+                ++kb;
+                if (++smp > sg.sb) { valid = it.next(sg); if (valid) smp = sg.sa; }
+            }
+            __device__ void step_group() { step(); if (valid) step(); }
+        };
+        float ug0[8], ug1[8]; uint32_t up0 = 0u, up1 = 0u;                 // two register sets (named: no dynamic indexing)
+        auto fetch = [&](float (&ug)[8], uint32_t& up, const Build& bd) {
+            if (!unit || !bd.valid) return;
+            const size_t g0 = (((size_t)bd.smp * 16 + ucg * 8) * 28 + 2 * bd.sg.ty + upyl) * 28 + upx;
+            uint32_t pk = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const size_t g = g0 + (size_t)k * 784;
                 ug[k] = aP[g] > 0.f ? gP[g] : 0.f;
-                upos |= (uint32_t)amax[g] << (4 * k);
+                pk |= (uint32_t)amax[g] << (4 * k);
+            }
+            up = pk;
+        };
+        auto store = [&](const float (&ug)[8], uint32_t up, uint8_t* dy) {
+            if (!unit) return;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float lo = ((up >> (8 * k)) & 15u) == (uint32_t)p ? ug[2 * k] : 0.f;
+                    const float hi = ((up >> (8 * k + 4)) & 15u) == (uint32_t)p ? ug[2 * k + 1] : 0.f;
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                    w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                const int oyl = 3 * upyl + p / 3, ox = 3 * upx + p % 3;
+                // row r = (oyl, ox / 4), column block = (ox % 4) * 2 + channel half: [n/8][128 rows][16 B]
+                *reinterpret_cast<uint4*>(dy + ((ox & 3) * 2 + ucg) * 2048 + (oyl * NG + (ox >> 2)) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         };
-        SegIter it(B, sliding);
-        Seg sg;
-        uint32_t kb = 0;
+        Build cur(B, sliding);
+        if (grp && cur.valid) cur.step();                  // group 1 starts at the CTA's second build
+        Build ahead = cur;
+        fetch(ug0, up0, ahead);
+        if (ahead.valid) ahead.step_group();
+        fetch(ug1, up1, ahead);
+        if (ahead.valid) ahead.step_group();               // `ahead` = two group-builds past `cur`
         bool ok = true;
-        while (ok && it.next(sg)) {
-            for (int smp = sg.sa; ok && smp <= sg.sb; ++smp, ++kb) {
-                if ((int)(kb & 1) != grp) continue;
-                if (pf_smp != smp || pf_ty != sg.ty) fetch(smp, sg.ty);     // not prefetched (first tile, or a short segment ahead)
-                const uint32_t slot = kb % NDY;
-                ok = tc05::mbar_wait(dy_empty + slot, ((kb / NDY) & 1) ^ 1, err);
-                if (!ok) break;
-                uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
-                if (unit) {
-#pragma unroll
-                    for (int p = 0; p < 9; ++p) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float lo = ((upos >> (8 * k)) & 15u) == (uint32_t)p ? ug[2 * k] : 0.f;
-                            const float hi = ((upos >> (8 * k + 4)) & 15u) == (uint32_t)p ? ug[2 * k + 1] : 0.f;
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                            w[k] = *reinterpret_cast<uint32_t*>(&h2);
-                        }
-                        const int oyl = 3 * upyl + p / 3, ox = 3 * upx + p % 3;
-                        // row r = (oyl, ox / 4), column block = (ox % 4) * 2 + channel half: [n/8][128 rows][16 B]
-                        *reinterpret_cast<uint4*>(dy + ((ox & 3) * 2 + ucg) * 2048 + (oyl * NG + (ox >> 2)) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-                tc05::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(dy_full + slot);
-                // prefetch this group's next sample tile (build kb + 2): the next sample of this segment, or the first of the next one
-                if (smp + 2 <= sg.sb) {
-                    fetch(smp + 2, sg.ty);
-                } else {
-                    SegIter itn = it;
-                    Seg sn;
-                    const int skip = smp + 2 - sg.sb - 1;          // 0 or 1 samples of the next segment belong to the other group
-                    if (itn.next(sn) && sn.sa + skip <= sn.sb) fetch(sn.sa + skip, sn.ty);
-                }
-            }
+#pragma unroll 1
+        for (uint32_t n = 0; ok && cur.valid; ++n) {
+            const uint32_t slot = cur.kb % NDY;
+            ok = tc05::mbar_wait(dy_empty + slot, ((cur.kb / NDY) & 1) ^ 1, err);
+            if (!ok) break;
+            uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
+            if (n & 1) store(ug1, up1, dy); else store(ug0, up0, dy);
+            tc05::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(dy_full + slot);
+            if (n & 1) fetch(ug1, up1, ahead); else fetch(ug0, up0, ahead);   // the set just stored is free: load two group-builds ahead
+            cur.step_group();
+            if (ahead.valid) ahead.step_group();
         }
         // ---- epilogue (warps 4-7): fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
         if (grp) goto fin;
@@ -600,9 +621,10 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
     const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
+    static const int ablate = getenv("BC_C1FW_ABLATE") ? atoi(getenv("BC_C1FW_ABLATE")) : 0;   // timing experiments only (wrong results)
     bc::launch_pdl(c1tp::conv1_tp_kernel, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
-        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag);
+        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag, ablate);
     BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
     return BC_OK;
 }
@@ -635,9 +657,10 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
     const int grid = bc_conv1_wgrad_tp_grid(c);      // = the slots bc_reduce_partials reads for conv1 in this mode
+    static const int ablate = getenv("BC_C1WG_ABLATE") ? atoi(getenv("BC_C1WG_ABLATE")) : 0;   // timing experiments only (wrong results)
     bc::launch_pdl(c1wg2::conv1_wgrad_tp_kernel, dim3(grid), dim3(c1wg2::NTHREADS), c1wg2::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
-        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag);
+        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
     BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
     return BC_OK;
 }
