@@ -392,6 +392,12 @@ def run_b200(args):
     # algorithmic bytes of the staging kernel: u8 RGB in; gray planes out (bf16 mode: Toeplitz-ready bf16 planes)
     stage_bytes = (B + 4) * (FRAME_BYTES + (2 * _lib.TP_PLANE_ELEMS if args.mode == "bf16" else 65536 * 4))
 
+    # a bounded mbarrier / peer-flag wait that expired would have left wrong results behind: never report such a run
+    eng.check_device_errors()
+    if dp is not None and hasattr(dp, "peer"):
+        dp.peer.check()
+    if not (loss_dev == loss_dev and 0.0 < loss_dev < 20.0):
+        raise RuntimeError(f"training diverged or produced a non-finite loss ({loss_dev}): the timed run is invalid")
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
