@@ -51,7 +51,7 @@ constexpr int TILES_PER_FRAME = 14;      // tile = 6 conv rows x 84 columns of o
 namespace c1tp {
 using c1tc::B_BYTES; using c1tc::B_STEP; using c1tc::MROWS; using c1tc::NG; using c1tc::S_PITCH; using c1tc::S_BYTES;
 using c1tc::TILES_PER_FRAME;
-constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, 1-3 and 12 MMA issuers, 4-7 / 8-11 epilogue groups
+constexpr int NTHREADS = 12 * 32;            // warp 0 loader + TMEM alloc, 1-2 MMA issuers, 3 idle, 4-7 / 8-11 epilogue groups
 constexpr int ROWB = 336;                    // 21 groups x 16 B
 constexpr int PIECE0 = 8 * ROWB, PIECE12 = 7 * ROWB;      // class 0 feeds ky 0,3,6 (8 rows), classes 1,2 feed two ky (7 rows)
 constexpr int SLOT_BYTES = 2 * PIECE0 + 4 * PIECE12;      // 14784
@@ -106,7 +106,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
 
     if (threadIdx.x == 0) {
         tc05::mbar_init(b_full, 1);
-        for (int i = 0; i < NSLOT; ++i) { tc05::mbar_init(slot_full + i, 1); tc05::mbar_init(slot_empty + i, 4); }
+        for (int i = 0; i < NSLOT; ++i) { tc05::mbar_init(slot_full + i, 1); tc05::mbar_init(slot_empty + i, 2); }
         for (int i = 0; i < 8; ++i) { tc05::mbar_init(t_full + i, 1); tc05::mbar_init(t_empty + i, 4); }
         tc05::mbar_fence_init();
     }
@@ -153,15 +153,17 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 }
             }
         }
-    } else if (warp <= 3 || warp == 12) {
-        // ------------------------------------------------------------------ 4 MMA issuers (whole warp loops, one elected lane issues)
-        // Sample tile number c (running count over the CTA's list) belongs to issuer c % 4, accumulator c % 8 and
-        // epilogue group c % 2. One issuer alone leaves the tensor pipe idle between groups of MMAs: a queued
-        // tcgen05.mma holds its uniform registers until it is dispatched, so the warp cannot set up the next group
-        // before the previous one has drained (measured: 470 cycles per 7-MMA group, 224 of them busy). With four
-        // issuers, each with its own uniform register file and its own accumulators, the queue never runs dry.
-        const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0);
+    } else if (warp <= 2) {
+        // ------------------------------------------------------------------ 2 MMA issuers, alternate super-tiles (whole warp loops, one elected lane issues)
+        // Plane j of a super-tile is channel ci = j - s of every sample s in [s_lo, s_hi]: the SAME A chunk meets the weight
+        // blocks of consecutive channels. With the accumulators of a super-tile laid out in descending sample order
+        // (column block 3 - s) and the weight image ordered [ky][ci], those are consecutive accumulator columns and
+        // consecutive B rows, so ONE tcgen05.mma of N = 64 * (number of samples) does what took up to four N = 64
+        // instructions: the A chunk is fetched from shared memory once instead of once per sample (N = 256 costs 128 cycles,
+        // four N = 64 cost 194). Only the first instruction of a sample (ci = 0, ky = 0) must overwrite its accumulator: there
+        // the block is split into [N = 64, overwrite] + [rest, accumulate].
+        constexpr uint32_t idesc64 = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 0, 0), idesc128 = tc05::instr_desc(tc05::FMT_BF16, 128, 128, 0, 0);
+        constexpr uint32_t idesc192 = tc05::instr_desc(tc05::FMT_BF16, 128, 192, 0, 0), idesc256 = tc05::instr_desc(tc05::FMT_BF16, 128, 256, 0, 0);
         const uint32_t ring = tc05::smem_u32(smem + OFF_RING);
         const uint64_t ad_c0 = tc05::smem_desc(ring, PIECE0, 128, tc05::SW_NONE);     // LBO = distance between the K halves
         const uint64_t ad_c12 = tc05::smem_desc(ring, PIECE12, 128, tc05::SW_NONE);
@@ -169,42 +171,60 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
         bool ok = tc05::mbar_wait(b_full, 0, err);
         TileIter it(B, smax);
         int ty, b0, S;
-        uint32_t k = 0, use = 0, cnt = 0;
+        uint32_t k = 0, use = 0, iter = 0;
         while (ok && it.next(ty, b0, S)) {
-            const int s = (int)((w - cnt) & 3);          // the sample of this super-tile this issuer owns (if s < S)
-            const uint32_t idx = (cnt + (uint32_t)s) & 7;
+            const uint32_t set = iter & 1;
+            if (set != (uint32_t)(warp - 1)) {
+                // The other issuer's super-tile. Still observe every plane in ring order and release it (slot_empty counts
+                // both issuers): a waiter that skipped planes could fall a whole ring cycle behind and alias mbarrier phases.
+                for (int j = 0; ok && j < S + 3; ++j, ++k) {
+                    const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
+                    ok = tc05::mbar_wait(slot_full + slot, ph, err);
+                    if (ok && lane == 0) tc05::mbar_arrive(slot_empty + slot);
+                }
+                ++iter;
+                continue;
+            }
             for (int j = 0; ok && j < S + 3; ++j, ++k) {
                 const uint32_t slot = k % NSLOT, ph = (k / NSLOT) & 1;
                 ok = tc05::mbar_wait(slot_full + slot, ph, err);
                 tc05::tc_fence_after();
-                const int ci = j - s;
-                if (s < S && ci >= 0 && ci <= 3) {
-                    if (ci == 0) {
-                        ok = ok && tc05::mbar_wait(t_empty + idx, ((use >> idx) & 1) ^ 1, err);
-                        tc05::tc_fence_after();
-                    }
-                    if (ok && tc05::elect_one()) {
-                        const uint64_t so = (uint64_t)((slot * SLOT_BYTES) >> 4);
-                        const uint32_t d_tmem = tmem_base + idx * 64;
-                        const uint64_t bb = bd0 + (uint64_t)(ci * 7 * (B_STEP >> 4));
-                        if (!(ablate & 1)) {         // timing experiment: bit 0 = no MMAs
-#pragma unroll
-                            for (int ky = 0; ky < 7; ++ky)
-                                tc05::mma_bf16(d_tmem, (ky % 3 == 0 ? ad_c0 : ad_c12) + so + (uint64_t)(a_off(ky) >> 4),
-                                               bb + (uint64_t)(ky * (B_STEP >> 4)), idesc, (ci | ky) > 0);
-                        }
-                        tc05::mma_commit(slot_empty + slot);
-                        if (ci == 3) tc05::mma_commit(t_full + idx);
-                    }
-                    __syncwarp();
-                    if (ci == 3) use ^= 1u << idx;
-                } else if (lane == 0) {
-                    tc05::mbar_arrive(slot_empty + slot);   // nothing of this plane is ours: release our share of the slot
+                const int s_lo = j > 3 ? j - 3 : 0, s_hi = j < S - 1 ? j : S - 1;
+                const bool fresh = j <= S - 1;             // sample s = j = s_hi starts with this plane (its ci = 0)
+                if (fresh) {
+                    const uint32_t idx = set * 4 + j;
+                    ok = ok && tc05::mbar_wait(t_empty + idx, ((use >> idx) & 1) ^ 1, err);
+                    tc05::tc_fence_after();
                 }
+                const int done_s = j - 3;                  // the sample whose last channel this plane is
+                if (ok && tc05::elect_one()) {
+                    const uint64_t so = (uint64_t)((slot * SLOT_BYTES) >> 4);
+                    const int n = s_hi - s_lo + 1, ci_lo = j - s_hi;
+                    const uint32_t d0 = tmem_base + set * 256 + (3 - s_hi) * 64;       // columns ascend with ci = descend with s
+                    const uint32_t idn = n == 1 ? idesc64 : n == 2 ? idesc128 : n == 3 ? idesc192 : idesc256;
+                    const uint32_t idr = n == 2 ? idesc64 : n == 3 ? idesc128 : idesc192;   // the block without its first 64 columns
+                    if (!(ablate & 1)) {         // timing experiment: bit 0 = no MMAs
+#pragma unroll
+                        for (int ky = 0; ky < 7; ++ky) {
+                            const uint64_t ad = (ky % 3 == 0 ? ad_c0 : ad_c12) + so + (uint64_t)(a_off(ky) >> 4);
+                            const uint64_t bd = bd0 + (uint64_t)((ky * 4 + ci_lo) * (B_STEP >> 4));
+                            if (ky == 0 && fresh) {
+                                tc05::mma_bf16(d0, ad, bd, idesc64, 0u);
+                                if (n > 1) tc05::mma_bf16(d0 + 64, ad, bd + (uint64_t)(B_STEP >> 4), idr, 1u);
+                            } else {
+                                tc05::mma_bf16(d0, ad, bd, idn, 1u);
+                            }
+                        }
+                    }
+                    tc05::mma_commit(slot_empty + slot);
+                    if (done_s >= 0 && done_s < S) tc05::mma_commit(t_full + set * 4 + done_s);
+                }
+                __syncwarp();
+                if (done_s >= 0 && done_s < S) use ^= 1u << (set * 4 + done_s);
             }
-            cnt += (uint32_t)S;
+            ++iter;
         }
-    } else {
+    } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (warps 4-11): two groups take alternate sample tiles
         const int eg = (warp - 4) >> 2;          // group
         const int ew = warp & 3;                 // TMEM lane quadrant of this warp
@@ -215,11 +235,13 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
         const float* bias_s = reinterpret_cast<const float*>(smem + OFF_BIAS);
         TileIter it(B, smax);
         int ty, b0, S;
-        uint32_t use = 0, cnt = 0;
+        uint32_t use = 0, cnt = 0, iter = 0;
         bool ok = true;
         while (ok && it.next(ty, b0, S)) {
+            const uint32_t set = (iter++) & 1;
             for (int s = 0; ok && s < S; ++s, ++cnt) {
-                const uint32_t idx = cnt & 7;
+                const uint32_t idx = set * 4 + s;                       // barrier pair of this accumulator
+                const uint32_t col = set * 256 + (3 - s) * 64;          // its TMEM columns (descending sample order, see the issuer)
                 const uint32_t par = (use >> idx) & 1;
                 use ^= 1u << idx;
                 if ((int)(cnt & 1) != eg) continue;
@@ -228,7 +250,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 tc05::tc_fence_after();
                 float v[64];
 #pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + idx * 64 + c0, v + c0);
+                for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + col + c0, v + c0);
                 tc05::tmem_ld_wait();
                 tc05::tc_fence_before();
                 __syncwarp();

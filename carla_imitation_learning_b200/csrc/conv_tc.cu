@@ -63,9 +63,9 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
     bc::pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < kNC1) {
-        // step s = (ci,ky): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu)
+        // step s = (ky,ci): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu)
         const int k = i & 15, n = (i >> 4) & 63, st = i >> 10;
-        const int ci = st / 7, ky = st % 7, j = n >> 4, co = n & 15;
+        const int ky = st >> 2, ci = st & 3, j = n >> 4, co = n & 15;     // steps ordered [ky][ci]: consecutive channels = consecutive B rows
         const int kx = k - 3 * j;
         const float v = (kx >= 0 && kx < 7) ? a.w1[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
         reinterpret_cast<__nv_bfloat16*>(a.base)[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
