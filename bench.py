@@ -27,7 +27,7 @@ UNIT = "frames/s"
 FLOPS_FWD = (44255232, 14745600, 5308416, 589824)          # SURVEY 8(d), per frame, conv1..4
 FLOPS_TRAIN = 150505152
 FRAME_BYTES = 256 * 256 * 3
-TRAFFIC_CONV1_TP = 45782528        # dram__bytes_read.sum + dram__bytes_write.sum of conv1_tp_kernel at B=256 (profiles/r1g_ncu_full_conv1_sw_stage_raw.csv)
+TRAFFIC_CONV1_TP = 45459712        # dram__bytes_read.sum + dram__bytes_write.sum of conv1_tp_kernel at B=256 (profiles/r1i_ncu_full_conv1_tp_raw.csv)
 
 
 def load_peaks():
@@ -426,7 +426,7 @@ def run_b200(args):
                                     else "conv_relu_pool_fwd_kernel<conv1> (exact-f32 FFMA variant)"),
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_burst"],
-                         "traffic": (TRAFFIC_CONV1_TP if (args.mode == "bf16" and B == 256) else None),   # ncu dram read+write of this kernel, profiles/r1g
+                         "traffic": (TRAFFIC_CONV1_TP if (args.mode == "bf16" and B == 256) else None),   # ncu dram read+write of this kernel, profiles/r1i
                          "peak_source": peaks["src"] + " (bf16 cuBLAS burst)",
                          "kernel_ms": k_ms, "flops_per_launch": FLOPS_FWD[0] * B,
                          "step_frac_of_dense_flops": FLOPS_TRAIN * B / (ms / args.steps * 1e-3) / 1e12 / peaks["tf_sust"]},
