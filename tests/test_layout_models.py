@@ -115,3 +115,40 @@ def test_shifted_window_wgrad_cores_are_pixel_shifts():
         got = np.einsum("kmc,m->kc", A, dy.reshape(-1))
         want = np.array([[np.sum(dy[:, :Ho] * x[ci, ky:ky + Ho, kx:kx + Ho]) for ci in range(8)] for kx in range(K)])
         assert np.allclose(got, want, atol=1e-10)
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 4])
+def test_conv1_merged_n_mma_gives_every_sample_its_own_convolution(S):
+    """conv1_tp_kernel issuer: plane j of a super-tile is channel ci = j - s of every sample s in [max(0, j-3), min(j, S-1)].
+    With the weight image ordered [ky][ci][64 rows] and the accumulators of the super-tile in column block 3 - s, ONE
+    instruction per (plane, ky) covers the block of samples: B rows start at (ky, ci_lo = j - s_hi), D columns at block
+    3 - s_hi, N = 64 * n. The first instruction of a sample (ci = 0, ky = 0) overwrites, split off the block.
+    Model: integer operands, the instruction sequence exactly as issued; every sample must end with
+    sum_{ci,ky} A(plane s + ci, ky) @ Wt[ci, ky].T and nothing else (stale accumulator contents must vanish)."""
+    rng = np.random.default_rng(S)
+    M, K, N = 8, 16, 64                                      # rows shrunk (the row dimension plays no role in the mapping)
+    A = rng.integers(-3, 4, size=(S + 3, 7, M, K))           # [plane][ky] operand slices
+    Wt = rng.integers(-3, 4, size=(4, 7, N, K))              # [ci][ky] Toeplitz weight blocks
+    Bimg = Wt.transpose(1, 0, 2, 3).reshape(7 * 4 * N, K)    # packed image: step (ky, ci) -> 64 consecutive rows
+    D = rng.integers(-99, 100, size=(M, 256))                # one accumulator set, stale contents
+    n_instr = 0
+    for j in range(S + 3):
+        s_lo, s_hi = max(0, j - 3), min(j, S - 1)
+        n, ci_lo, fresh = s_hi - s_lo + 1, j - s_hi, j <= S - 1
+        d0 = (3 - s_hi) * 64
+        for ky in range(7):
+            b0 = (ky * 4 + ci_lo) * N
+            if ky == 0 and fresh:
+                assert ci_lo == 0                           # the sample that starts here is the first block of the run
+                D[:, d0:d0 + 64] = A[j, ky] @ Bimg[b0:b0 + 64].T
+                n_instr += 1
+                if n > 1:
+                    D[:, d0 + 64:d0 + 64 * n] += A[j, ky] @ Bimg[b0 + 64:b0 + 64 * n].T
+                    n_instr += 1
+            else:
+                D[:, d0:d0 + 64 * n] += A[j, ky] @ Bimg[b0:b0 + 64 * n].T
+                n_instr += 1
+    for s in range(S):
+        want = sum(A[s + ci, ky] @ Wt[ci, ky].T for ci in range(4) for ky in range(7))
+        assert np.array_equal(D[:, (3 - s) * 64:(4 - s) * 64], want), s
+    assert n_instr == 7 * (S + 3) + S - 1                     # vs 28 * S one-sample instructions
