@@ -14,8 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
 SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+# -cudart shared: the library reuses the libcudart.so.12 torch has already loaded (one CUDA runtime per process)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static")
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", os.environ.get("BC_CUDART", "shared"))
 
 BC_F32, BC_BF16, BC_BF16_TP = 0, 1, 2
 TP_PLANE_ELEMS = 86688
@@ -34,7 +35,14 @@ class BcCtx(C.Structure):
         ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
         ("reserved0", C.c_void_p),
         ("x_tp", C.c_void_p), ("x_tp_stride_n", C.c_int64), ("x_tp_stride_c", C.c_int64),
+        ("grads_epoch", C.c_void_p), ("grads_stride", C.c_int64),
     ]
+
+
+class BcPeer(C.Structure):
+    """Mirror of `bc_peer` (include/bc_b200.h)."""
+    _fields_ = [("peer_grads_dev", C.c_void_p), ("peer_signals_dev", C.c_void_p), ("sync_state", C.c_void_p),
+                ("err_flag", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
 
 
 EXPORTS = {
@@ -57,10 +65,13 @@ EXPORTS = {
     "bc_loss_reduce": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_adam_tick": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bc_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "bc_adam_tick_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "bc_adam_step_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bc_adam_tick_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_adam_step_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(BcPeer),
+                                        C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_backward_overlap": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "bc_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_scale_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "bc_tc_gemm_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bc_tc_mma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bc_last_error_string": (C.c_char_p, []),
@@ -74,7 +85,7 @@ _lib = None
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libbc_b200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "bc_common.cuh"), os.path.join(CSRC, "tc05.cuh"), os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("bc_common.cuh", "tc05.cuh", "pack.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -97,6 +108,7 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c \"import __graft_entry__ as g; g.build()\"`. "
                 "There is no CPU or PyTorch fallback for the BC hot path.")
+        import torch  # noqa: F401  (loads libcudart.so.12, which the library links dynamically)
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(l, name)   # AttributeError here = header/library mismatch

@@ -28,8 +28,18 @@ namespace bc {
 char* err_buf();
 int fail(int code, const char* fmt, ...);
 #define BC_CHECK_ARG(cond, ...) do { if (!(cond)) return bc::fail(BC_ERR_ARG, __VA_ARGS__); } while (0)
-#define BC_CUDA_LAUNCH_CHECK(name) do { cudaError_t e_ = cudaPeekAtLastError(); \
+// the status of the launch just made: launch_pdl's own return value first, then the runtime's sticky-free last error
+// (cudaGetLastError CLEARS it, so one failed launch cannot make every later ABI call report failure)
+cudaError_t& pending_launch_error();
+#define BC_CUDA_LAUNCH_CHECK(name) do { cudaError_t e_ = bc::pending_launch_error(); bc::pending_launch_error() = cudaSuccess; \
+    const cudaError_t g_ = cudaGetLastError(); if (e_ == cudaSuccess) e_ = g_; \
     if (e_ != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: %s", name, cudaGetErrorString(e_)); } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per function AND per device: one flag per device ordinal
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool& operator()() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0; return done[d]; }
+};
 
 int num_sms();
 
@@ -100,7 +110,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    if (e != cudaSuccess) pending_launch_error() = e;
+    return e;
 }
 
 // device side of launch_pdl (same instructions as tc05::pdl_wait / pdl_trigger, for kernels that do not use tc05.cuh)

@@ -633,7 +633,7 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c->obs_size == 4, "conv1 (tcgen05, TP): obs_size 4 only");
     BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
                  "conv1 (tcgen05, TP): x_tp, its strides and w_packed must be 16 B aligned");
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(c1tp::conv1_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tp::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05, TP): smem opt-in %d B failed: %s", c1tp::SMEM_BYTES, cudaGetErrorString(e));
@@ -643,7 +643,11 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
     const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
-    static const int ablate = getenv("BC_C1FW_ABLATE") ? atoi(getenv("BC_C1FW_ABLATE")) : 0;   // timing experiments only (wrong results)
+#ifdef BC_ABLATE   // timing experiments only (knowingly wrong results): compiled out of the shipped library
+    static const int ablate = getenv("BC_C1FW_ABLATE") ? atoi(getenv("BC_C1FW_ABLATE")) : 0;
+#else
+    constexpr int ablate = 0;
+#endif
     bc::launch_pdl(c1tp::conv1_tp_kernel, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
         c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag, ablate);
@@ -670,7 +674,7 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c->obs_size == 4, "conv1 wgrad (tcgen05, TP): obs_size 4 only");
     BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0,
                  "conv1 wgrad (tcgen05, TP): x_tp and its strides must be 16 B aligned");
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(c1wg2::conv1_wgrad_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1wg2::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05, TP): smem opt-in %d B failed: %s", c1wg2::SMEM_BYTES, cudaGetErrorString(e));
@@ -679,7 +683,11 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);
     const int grid = bc_conv1_wgrad_tp_grid(c);      // = the slots bc_reduce_partials reads for conv1 in this mode
-    static const int ablate = getenv("BC_C1WG_ABLATE") ? atoi(getenv("BC_C1WG_ABLATE")) : 0;   // timing experiments only (wrong results)
+#ifdef BC_ABLATE
+    static const int ablate = getenv("BC_C1WG_ABLATE") ? atoi(getenv("BC_C1WG_ABLATE")) : 0;
+#else
+    constexpr int ablate = 0;
+#endif
     bc::launch_pdl(c1wg2::conv1_wgrad_tp_kernel, dim3(grid), dim3(c1wg2::NTHREADS), c1wg2::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
         c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);

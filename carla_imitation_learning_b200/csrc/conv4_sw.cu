@@ -447,7 +447,7 @@ int opt_in(K kern, int bytes, const char* name) {
 }  // namespace c4
 
 int bc_conv4_sw_fwd_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) {
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) { int rc = c4::opt_in(c4::conv4_fwd_kernel, c4::fw::SMEM_BYTES, "conv4_fwd_kernel"); if (rc) return rc; configured = true; }
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const int ntiles = (c->batch + 7) / 8;
@@ -459,7 +459,7 @@ int bc_conv4_sw_fwd_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) {
 }
 
 int bc_conv4_sw_dgrad_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) {
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) { int rc = c4::opt_in(c4::conv4_dgrad_kernel, c4::dg::SMEM_BYTES, "conv4_dgrad_kernel"); if (rc) return rc; configured = true; }
     const int ntiles = (c->batch + 1) / 2;
     const int grid = ntiles < bc::num_sms() ? ntiles : bc::num_sms();
@@ -470,7 +470,7 @@ int bc_conv4_sw_dgrad_launch(const bc_ctx* c, const uint8_t* wpk, void* stream) 
 }
 
 int bc_conv4_sw_wgrad_launch(const bc_ctx* c, void* stream) {
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) { int rc = c4::opt_in(c4::conv4_wgrad_kernel, c4::wg::SMEM_BYTES, "conv4_wgrad_kernel"); if (rc) return rc; configured = true; }
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
     const bc::Partials pl = bc::partials_layout(ar);

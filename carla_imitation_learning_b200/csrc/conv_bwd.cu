@@ -125,7 +125,7 @@ int launch_wgrad(const void* x, int64_t sn, int64_t sc, const float* gP, const f
                  float* part, int64_t seg_len, int64_t w_off, int64_t b_off, int B, int nparts, cudaStream_t s, const char* name) {
     using Cfg = WgradCfg<CIN, COUT, K, S, P, HIN, CO_B, TILED, TIN>;
     auto kern = conv_wgrad_kernel<Cfg, CIN, COUT, K, S, P, HIN, CO_B, TILED, TIN>;
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in failed: %s", name, cudaGetErrorString(e));
@@ -233,7 +233,7 @@ int launch_dgrad(const float* w, const float* gP, const float* aP, const uint8_t
                  int ctas_per_sm, cudaStream_t s, const char* name) {
     using Cfg = DgradCfg<CIN, COUT, K, P, HIN, CI_B, CI_T, NF>;
     auto kern = conv_dgrad_kernel<Cfg, CIN, COUT, K, P, HIN, CI_B, CI_T, NF>;
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in failed: %s", name, cudaGetErrorString(e));
@@ -252,6 +252,7 @@ int launch_dgrad(const float* w, const float* gP, const float* aP, const uint8_t
 // ------------------------------------------------------------------------------------------
 struct ReduceArgs {
     const float* part; float* grads; float* loss;
+    const uint32_t* grads_epoch; int64_t grads_stride;     // peer exchange: double-buffered arena, see bc_ctx.grads_epoch
     int64_t seg_off[5], seg_len[5], poff[5];
     int nparts[5];
     int64_t loss_off; int n_loss; int64_t begin, end; int with_loss;
@@ -292,7 +293,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][e];
-        a.grads[i] = t;
+        const int64_t par = a.grads_epoch ? (int64_t)((*a.grads_epoch + 1u) & 1u) * a.grads_stride : 0;
+        a.grads[par + i] = t;
     }
     if (a.with_loss && blockIdx.x == 0 && threadIdx.x < 32) {
         float v = 0.f;
@@ -385,6 +387,7 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     const bc::Partials pl = bc::partials_layout(ar);
     ReduceArgs a{};
     a.part = c->partials; a.grads = c->grads; a.loss = c->loss;
+    a.grads_epoch = c->grads_epoch; a.grads_stride = c->grads_stride;
     for (int k = 0; k < 5; ++k) { a.seg_off[k] = ar.seg_off[k]; a.seg_len[k] = ar.seg_len[k]; a.poff[k] = pl.off[k]; a.nparts[k] = pl.nparts[k]; }
     // the tcgen05 conv1 wgrad writes one partial per CTA, i.e. fewer slots than the layout reserves: read only those
     if ((c->conv_mode & 8) && c->x_tp && c->obs_size == 4 && c->err_flag) a.nparts[4] = bc_conv1_wgrad_tp_grid(c);

@@ -202,7 +202,7 @@ template <typename Cfg, typename TIN>
 int launch_fwd(const void* x, int64_t sn, int64_t sc, const float* w, const float* b, float* y, uint8_t* amax,
                int B, int ctas_per_sm, cudaStream_t s, const char* name) {
     auto kern = conv_relu_pool_fwd_kernel<Cfg, TIN>;
-    static bool configured = false;  // attribute is per function & device; set once per process
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %zu B failed: %s", name, Cfg::SMEM_BYTES, cudaGetErrorString(e));

@@ -714,7 +714,7 @@ using W3 = WCfg<32, 64, 4, 12, 4>;
 template <typename C>
 int launch_fwd(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
     auto kern = sw_fwd_kernel<C>;
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
@@ -734,7 +734,7 @@ int launch_fwd(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, c
 template <typename C>
 int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s, const char* name) {
     auto kern = sw_dgrad_kernel<C>;
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));
@@ -752,7 +752,7 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
 template <typename C>
 int launch_wgrad(const bc_ctx* c, int layer, cudaStream_t s, const char* name) {
     auto kern = sw_wgrad_kernel<C>;
-    static bool configured = false;
+    static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "%s: smem opt-in %d B failed: %s", name, C::SMEM_BYTES, cudaGetErrorString(e));

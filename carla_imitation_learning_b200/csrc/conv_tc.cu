@@ -2,58 +2,16 @@
 // The kernels themselves: conv_sw.cu (conv2, conv3: shifted-window forward / dgrad / wgrad) and conv4_sw.cu.
 #include "bc_common.cuh"
 #include "tc05.cuh"
+#include "pack.cuh"
 
-namespace ctc {
-
-// UMMA K-major no-swizzle canonical layout of a K=16 slice: byte(r, k) = (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2
-__host__ __device__ constexpr int op_off(int r, int chunk) { return (r >> 3) * 256 + chunk * 128 + (r & 7) * 16; }
-
-template <int CIN_, int COUT_, int KS_>
-struct Cfg {
-    static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_;
-    static constexpr int CB = CIN / 16;                    // forward: 16-channel blocks per tap
-    static constexpr int NSTEP = KS * KS * CB;
-    static constexpr int B_STEP = COUT * 32, B_BYTES = NSTEP * B_STEP;       // forward image: step (tap, ci/16): COUT rows x 16 k
-};
-template <typename C>
-struct DCfg {                                              // dgrad image: step (tap, co/16): CIN rows x 16 k
-    static constexpr int N = C::CIN, CB = C::COUT / 16, NSTEP = C::KS * C::KS * CB;
-    static constexpr int B_STEP = N * 32, B_BYTES = NSTEP * B_STEP;
-};
-using L2 = Cfg<16, 32, 5>;
-using L3 = Cfg<32, 64, 4>;
-using L4 = Cfg<64, 128, 3>;
-}  // namespace ctc
-
-// byte offsets of the per-layer operand images inside w_packed: [conv1 | conv2 | conv3 | conv4]
-static constexpr size_t kPackOff1 = 0, kPackOff2 = 57344;
-static constexpr size_t kPackOff3 = kPackOff2 + ctc::L2::B_BYTES, kPackOff4 = kPackOff3 + ctc::L3::B_BYTES;
-static constexpr size_t kPackD2 = kPackOff4 + ctc::L4::B_BYTES;            // dgrad operand images
-static constexpr size_t kPackD3 = kPackD2 + ctc::DCfg<ctc::L2>::B_BYTES, kPackD4 = kPackD3 + ctc::DCfg<ctc::L3>::B_BYTES;
-static constexpr size_t kPackTotal = kPackD4 + ctc::DCfg<ctc::L4>::B_BYTES;
+using ctc::kPackOff1; using ctc::kPackOff2; using ctc::kPackOff3; using ctc::kPackOff4;
+using ctc::kPackD2; using ctc::kPackD3; using ctc::kPackD4; using ctc::kPackTotal;
 
 size_t bc_conv_tc_pack_total() { return kPackTotal; }
 
 namespace ctc {
 struct PackArgs { const float* w1; const float* w2; const float* w3; const float* w4; uint8_t* base; };
 
-// One source weight W[co][ci][tap] of conv2-4 -> its position in the forward image and in the dgrad image.
-// Threads walk the f32 weights in memory order (coalesced reads); the two bf16 writes are scattered but nothing waits on them.
-template <typename C>
-__device__ __forceinline__ void pack_src_elem(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgr, int i) {
-    using D = DCfg<C>;
-    constexpr int KK = C::KS * C::KS;
-    const int tap = i % KK, ci = (i / KK) % C::CIN, co = i / (KK * C::CIN);
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-    {   // forward: step (tap, ci/16), row co, k = ci%16
-        const int sidx = tap * C::CB + (ci >> 4), k = ci & 15;
-        fwd[(size_t)sidx * (C::B_STEP / 2) + op_off(co, k >> 3) / 2 + (k & 7)] = v;
-    }
-    {   // dgrad: step (tap, co/16), row ci, k = co%16
-        const int sidx = tap * D::CB + (co >> 4), k = co & 15;
-        dgr[(size_t)sidx * (D::B_STEP / 2) + op_off(ci, k >> 3) / 2 + (k & 7)] = v;
-    }
-}
 constexpr int kNW2 = L2::COUT * L2::CIN * L2::KS * L2::KS, kNW3 = L3::COUT * L3::CIN * L3::KS * L3::KS, kNW4 = L4::COUT * L4::CIN * L4::KS * L4::KS;
 constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz image, element-ordered (it has structural zeros)
 constexpr int kPackElems = kNC1 + kNW2 + kNW3 + kNW4;
@@ -72,9 +30,9 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
         return;
     }
     i -= kNC1;
-    if (i < kNW2) { pack_src_elem<L2>(a.w2, (__nv_bfloat16*)(a.base + o2), (__nv_bfloat16*)(a.base + d2), i); return; } i -= kNW2;
-    if (i < kNW3) { pack_src_elem<L3>(a.w3, (__nv_bfloat16*)(a.base + o3), (__nv_bfloat16*)(a.base + d3), i); return; } i -= kNW3;
-    if (i < kNW4) pack_src_elem<L4>(a.w4, (__nv_bfloat16*)(a.base + o4), (__nv_bfloat16*)(a.base + d4), i);
+    if (i < kNW2) { pack_src_elem<L2>(a.w2[i], (__nv_bfloat16*)(a.base + o2), (__nv_bfloat16*)(a.base + d2), i); return; } i -= kNW2;
+    if (i < kNW3) { pack_src_elem<L3>(a.w3[i], (__nv_bfloat16*)(a.base + o3), (__nv_bfloat16*)(a.base + d3), i); return; } i -= kNW3;
+    if (i < kNW4) pack_src_elem<L4>(a.w4[i], (__nv_bfloat16*)(a.base + o4), (__nv_bfloat16*)(a.base + d4), i);
 }
 }  // namespace ctc
 

@@ -23,6 +23,7 @@ struct HeadArgs {
     int64_t ow0, ob0, ow2, ob2, ow4, ob4;  // offsets inside the segment
     int B, NA, mode;
     float loss_scale;
+    int* err;            // device flag: 3 = a label outside [0, n_actions) (nn.CrossEntropyLoss raises there)
 };
 
 __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
@@ -90,7 +91,11 @@ __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
                 const float m = bc::warp_max(z);
                 const float e = lane < NA ? expf(z - m) : 0.f;
                 const float sum = bc::warp_sum(e);
-                const int yb = (int)a.y[b];
+                int yb = (int)a.y[b];
+                if (yb < 0 || yb >= NA) {        // reported through the device flag (checked by the host at epoch end / in tests); the sample contributes class 0
+                    if (lane == 0 && a.err) atomicExch(a.err, 3);
+                    yb = 0;
+                }
                 const float zy = __shfl_sync(0xffffffffu, z, yb & 31);
                 if (lane == 0) block_loss += (logf(sum) + m - zy);
                 const float dl = (e / sum - (lane == yb ? 1.f : 0.f)) * a.loss_scale;
@@ -164,7 +169,30 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int64_t* __restr
     out[b] = idx;
 }
 
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float4* __restrict__ v, int64_t n4, const float* __restrict__ scale) {
+    bc::pdl_wait();
+    bc::pdl_trigger();
+    const float s = *scale;
+    if (s == 1.0f) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 t = v[i];
+        t.x *= s; t.y *= s; t.z *= s; t.w *= s;
+        v[i] = t;
+    }
+}
+
 }  // namespace
+
+extern "C" int bc_scale_inplace(float* v, int64_t n, const float* scale_dev, void* stream) {
+    BC_CHECK_ARG(v && scale_dev && n >= 0 && n % 4 == 0 && (uintptr_t)v % 16 == 0, "bc_scale_inplace: null / unaligned buffer or n not a multiple of 4");
+    if (n == 0) return BC_OK;
+    int blocks = (int)((n / 4 + 255) / 256);
+    if (blocks > bc::num_sms() * 4) blocks = bc::num_sms() * 4;
+    bc::launch_pdl(scale_inplace_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (float4*)v, n / 4, scale_dev);
+    BC_CUDA_LAUNCH_CHECK("scale_inplace_kernel");
+    return BC_OK;
+}
 
 extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) {
     BC_CHECK_ARG(c && c->params && c->act[3] && c->hid1 && c->hid2 && c->logits, "bc_head: null buffer");
@@ -184,7 +212,7 @@ extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) {
     a.loss_part = c->partials ? c->partials + pl.loss_off : nullptr;
     a.seg_len = ar.seg_len[0];
     a.ow0 = ar.w[4]; a.ob0 = ar.b[4]; a.ow2 = ar.w[5]; a.ob2 = ar.b[5]; a.ow4 = ar.w[6]; a.ob4 = ar.b[6];
-    a.B = c->batch; a.NA = c->n_actions; a.mode = head_mode; a.loss_scale = c->loss_scale;
+    a.B = c->batch; a.NA = c->n_actions; a.mode = head_mode; a.loss_scale = c->loss_scale; a.err = c->err_flag;
     // the partial layout has a fixed number of copies, so the grid is fixed as well
     bc::launch_pdl(head_kernel, dim3(bc::kHeadBlocks), dim3(NT), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("head_kernel");

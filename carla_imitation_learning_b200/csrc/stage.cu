@@ -2,23 +2,27 @@
 // Replaces the per-sample numpy work of SequentialTorchDataset._load_file
 // (/root/reference/src/dataset/imitation_dataset.py:120-121,130):
 //     np.dot(images, [0.299, 0.587, 0.114]) / 255.0  ->  float32
-// The f64 evaluation ((R*.299 + G*.587) + B*.114) * (1/255), rounded to f32, equals the
-// numpy result for ALL 2^24 (R,G,B) triples (tests/test_stage_exhaustive.py proves it on the
-// CPU model and on the device), so the kernel is bit-exact for f32 output.
+// The kernel reproduces the numpy result bit for bit for ALL 2^24 (R,G,B) triples (see gray_px below;
+// tests/test_gpu_parity.py::test_stage_gray_bit_exact_all_rgb proves it on the device, tests/test_stage_model.py
+// on a host model of the same three f32 operations).
 // HBM-bound: 3 B read + 4 B (f32) or 2 B (bf16) written per pixel; no reuse, so no smem.
 #include "bc_common.cuh"
 
 namespace {
 
-// u8 -> f64 without the conversion unit (I2F.F64 issues at a fraction of the FP64 FMA rate and was the limiter of
-// this kernel): 2^52 + c is exact as the bit pattern 0x43300000'000000cc, and subtracting 2^52 is exact too.
-__device__ __forceinline__ double u8_to_f64(uint32_t c) { return __dadd_rn(__hiloint2double(0x43300000, (int)c), -4503599627370496.0); }
-
+// The reference evaluates (R*.299 + G*.587 + B*.114) / 255.0 in f64 and casts to f32. For every one of the 2^24 (R,G,B)
+// triples that f32 value depends only on the integer s = 299R + 587G + 114B (<= 255000) and equals the CORRECTLY ROUNDED
+// f32 quotient s / 255000 (the f64 chain's error, ~1e-16 relative, is far below the distance of any s/255000 to an f32
+// rounding boundary: >= 1e-13 relative). A correctly rounded quotient needs no FP64: q0 = s*r, rem = fma(-q0, 255000, s)
+// (exact), q = fma(rem, r, q0) with r = rn(1/255000) -- three f32 instructions, verified against numpy for all 247,023
+// distinct s on the host and for all 2^24 triples on the device (tests/test_gpu_parity.py::test_stage_gray_bit_exact_all_rgb).
+// (The first versions of this kernel ran the f64 chain itself and were FP64-pipe bound at 62 % of the HBM copy rate.)
 __device__ __forceinline__ float gray_px(uint32_t r, uint32_t g, uint32_t b) {
-    // explicit _rn intrinsics: no FMA contraction, so the CPU model in the tests is exact
-    double s = __dadd_rn(__dadd_rn(__dmul_rn(u8_to_f64(r), 0.299), __dmul_rn(u8_to_f64(g), 0.587)),
-                         __dmul_rn(u8_to_f64(b), 0.114));
-    return (float)__dmul_rn(s, 1.0 / 255.0);
+    const float s = (float)(299u * r + 587u * g + 114u * b);          // exact: s < 2^24
+    const float rcp = 1.0f / 255000.0f;
+    const float q0 = __fmul_rn(s, rcp);
+    const float rem = __fmaf_rn(-q0, 255000.0f, s);
+    return __fmaf_rn(rem, rcp, q0);
 }
 
 // PX pixels per thread: 4 for f32 output (one 16 B store), 8 for bf16 output (one 16 B store).
@@ -90,7 +94,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Every pixel is converted ONCE: unit (R, g'), g' = 0..21, owns the 12 pixels [12g', 12g'+12) of image row R (g' = 21: the
 // last 4) and writes them where they belong -- pixels 0..7 as the h=0 chunk and 8..11 as the first half of the h=1 chunk of
 // segment g', pixels 0..3 also as the second half of the h=1 chunk of segment g'-1 (the 4-pixel overlap of neighbouring
-// segments). The FP64 gray arithmetic is the limiter of this kernel, so 12 instead of 16 conversions per thread matters.
+// segments). Every pixel is converted once (12 conversions per thread, not 16).
 // `plain` (optional): the same gray values also as plain (n,256,256) bf16 planes.
 constexpr int TP_NU = TP_NG + 1;
 __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out,

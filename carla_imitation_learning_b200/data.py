@@ -84,6 +84,9 @@ class SequentialFrames:
         n, h, w, _ = frames_u8.shape
         rows = self.batch_size + frame_skip
         self._raw = [torch.empty((rows, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        # labels travel through per-slot buffers too: a batch then has the same (input, label) addresses every time its slot
+        # comes round, which is what lets the training step be a replayed CUDA graph (autograd.FusedStepFunction, trainer.TrainStep)
+        self._lab = [torch.zeros(self.batch_size, dtype=torch.int64, device=self.device) for _ in range(2)]
         if layout not in ("plain", "tp"):
             raise ValueError("layout is 'plain' (gray planes) or 'tp' (Toeplitz-ready bf16 planes for precision='bf16')")
         if layout == "tp" and (h, w, frame_skip) != (256, 256, 4):
@@ -102,6 +105,8 @@ class SequentialFrames:
         hi = min(lo + self.batch_size, self.n_samples) + self.frame_skip
         with torch.cuda.stream(self._copy_stream):
             self._raw[slot][:hi - lo].copy_(self.frames[lo:hi], non_blocking=True)
+            nb = hi - lo - self.frame_skip
+            self._lab[slot][:nb].copy_(self.labels[lo + self.frame_skip: lo + self.frame_skip + nb], non_blocking=True)
             if self.layout == "tp":
                 stage_frames(self._raw[slot][:hi - lo], out=StagedBatch(self._gray[slot][:hi - lo], None, self.frame_skip))
             else:
@@ -127,8 +132,7 @@ class SequentialFrames:
                 x = StagedBatch(self._gray[slot][:b + self.frame_skip], None, self.frame_skip)
             else:
                 x = sliding_window(self._gray[slot][:b + self.frame_skip], self.frame_skip)
-            y = self.labels[lo + self.frame_skip: lo + self.frame_skip + b]
-            yield x, y
+            yield x, self._lab[slot][:b]
 
 
 def sequential_train_val_test_iterator(hparams, frames_by_split=None):

@@ -141,6 +141,8 @@ class BCEngine:
         if arena.numel() != total:
             raise ValueError(f"arena has {arena.numel()} floats, layout needs {total}")
         self.grads = torch.zeros_like(arena)
+        self.grads_epoch: Optional[torch.Tensor] = None    # peer exchange: device word selecting the half of a double-buffered arena (bc_ctx.grads_epoch)
+        self.grads_stride = 0
         # partial-sum workspace: pads are never written, so it must start zeroed
         self.partials = torch.zeros(int(self.lib.bc_partials_floats(self.obs_size, self.n_actions)),
                                     dtype=torch.float32, device=self.device)
@@ -148,6 +150,12 @@ class BCEngine:
         self.w_packed = torch.zeros(int(self.lib.bc_packed_weight_bytes()), dtype=torch.uint8, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.conv_mode = 0            # bit mask, see bc_ctx.conv_mode: 0 = exact f32 FFMA kernels, 15 = all tcgen05 kernels
+        self._packed_version = None   # arena._version the bf16 operand images were last derived from (None = never)
+        self.overlap = False          # backward with the conv4..conv2 weight-gradient kernels on a side stream (bc_backward_overlap)
+        self._side = None             # (side stream, 4 events, ctypes array of their handles)
+        self._static = {}             # batch -> StepBuffers reused by the static-shape paths (no per-step allocation)
+        self.peer = None              # parallel.PeerGrads once the gradients live in peer-visible memory
+        self._slots, self._slot_i = None, 0
 
     # ------------------------------------------------------------------ buffers
     def alloc(self, batch: int, x, y: Optional[torch.Tensor], backward: bool) -> StepBuffers:
@@ -242,30 +250,111 @@ class BCEngine:
         c.w_packed, c.err_flag = self.w_packed.data_ptr(), self.err_flag.data_ptr()
         if b.x_tp is not None:
             c.x_tp, (c.x_tp_stride_n, c.x_tp_stride_c) = b.x_tp.data_ptr(), b.x_tp_strides
+        if self.grads_epoch is not None:
+            c.grads_epoch, c.grads_stride = self.grads_epoch.data_ptr(), self.grads_stride
         return c
+
+    def static_buffers(self, batch: int, x, y: Optional[torch.Tensor]) -> StepBuffers:
+        """One persistent StepBuffers per batch size (training: with the backward buffers); only the input and label
+        pointers are re-pointed. What a fixed-shape training loop uses instead of alloc() every step."""
+        b = self._static.get(batch)
+        if b is None:
+            b = self._static[batch] = self.alloc(batch, x, y, True)
+            return b
+        staged = x if isinstance(x, StagedBatch) else None
+        if staged is not None:
+            b.x, b.x_tp, b.x_tp_strides = staged.x, staged.tp, (_lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
+        else:
+            b.x = x
+            if (self.conv_mode & 1) and self.obs_size == 4 and batch:
+                # a plain batch in bf16 mode: converted per call into a persistent plane buffer (stable pointer for graphs)
+                sliding = x.stride(0) == H * W and x.stride(1) == H * W
+                n_planes = batch + self.obs_size - 1 if sliding else batch * self.obs_size
+                own = getattr(b, "_tp_own", None)
+                if own is None or own.shape[0] != n_planes:
+                    own = b._tp_own = torch.empty((n_planes, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=self.device)
+                b.x_tp, b.x_tp_strides = self.to_tp(x, out=own)
+        b.y = y
+        return b
+
+    def grad_view(self) -> torch.Tensor:
+        """The arena-shaped buffer the backward of the current step writes (peer exchange: the half the epoch selects)."""
+        return self.peer.current() if self.peer is not None else self.grads
+
+    def next_grad_slot(self, params) -> torch.Tensor:
+        """Gradient arena for the next fused step. Two arenas alternate, so the .grad views autograd adopted from the
+        previous step stay intact until zero_grad() drops them (Lightning runs training_step BEFORE zero_grad); should a
+        live .grad still alias the arena about to be rewritten (gradient accumulation over >2 micro-steps), it is copied
+        out first."""
+        if self.peer is not None:
+            flat = self.peer.current()
+        else:
+            if self._slots is None:
+                self._slots = [self.grads, torch.zeros_like(self.grads)]
+            self._slot_i ^= 1
+            flat = self.grads = self._slots[self._slot_i]
+        lo = flat.data_ptr()
+        hi = lo + flat.numel() * 4
+        for p in params:
+            g = p.grad
+            if g is not None and lo <= g.data_ptr() < hi:
+                p.grad = g.clone()
+        return flat
+
+    def side_handles(self):
+        """(side stream, events, ctypes void*[4]) of the overlapped backward; created outside any graph capture."""
+        if self._side is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("create the engine's side stream before capturing (run one eager step first)")
+            with torch.cuda.device(self.device):
+                side = torch.cuda.Stream(self.device)
+                evs = [torch.cuda.Event() for _ in range(4)]
+                for e in evs:
+                    e.record()                      # torch creates the cudaEvent lazily: force it now
+                arr = (C.c_void_p * 4)(*[e.cuda_event for e in evs])
+            self._side = (side, evs, arr)
+        return self._side
 
     def set_mode(self, mode: str) -> None:
         """'fp32' = exact FFMA kernels (rel 1e-5); 'bf16' = tcgen05 kernels on bf16-staged frames (rel 2e-2)."""
         self.conv_mode = {"fp32": 0, "bf16": 15}[mode]
 
     def pack_weights(self) -> None:
-        """Refresh the bf16 operand images from the f32 master weights (after every optimiser step in bf16 mode)."""
+        """Derive the bf16 operand images from the f32 master weights (one launch). The fused Adam kernels keep the images
+        current afterwards (bc_adam_tick_step / bc_adam_step_exchange with w_packed), so a training loop calls this once."""
         c = _lib.BcCtx()
         c.obs_size, c.n_actions = self.obs_size, self.n_actions
         c.params, c.w_packed = self.arena.data_ptr(), self.w_packed.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bc_pack_weights(C.byref(c), _stream_ptr()), "bc_pack_weights")
+        self._packed_version = self.arena._version
+
+    def ensure_packed(self) -> None:
+        """Re-pack only when the master weights changed behind the kernels' back (torch in-place ops bump arena._version:
+        load_state_dict, p.data.copy_, a foreign optimiser). FusedAdam refreshes the images itself."""
+        if self.conv_mode and self._packed_version != self.arena._version:
+            self.pack_weights()
+
+    def packed_ptr(self) -> Optional[int]:
+        """w_packed for the optimiser kernels: the images follow the weights only in bf16 mode (obs_size 4)."""
+        return self.w_packed.data_ptr() if (self.conv_mode and self.obs_size == 4) else None
+
+    _ERRORS = {1: "a tcgen05 pipeline wait timed out inside a kernel (mbarrier protocol error)",
+               3: "a label outside [0, n_actions) reached the CrossEntropy kernel (nn.CrossEntropyLoss raises on it too)"}
 
     def check_device_errors(self) -> None:
-        """Host-side check of the bounded-wait flag (synchronises; call outside the hot loop)."""
-        if int(self.err_flag.item()) != 0:
-            raise RuntimeError("a tcgen05 pipeline wait timed out inside a kernel (mbarrier protocol error)")
+        """Host-side check of the device error flag (synchronises; call outside the hot loop, e.g. at epoch end)."""
+        code = int(self.err_flag.item())
+        if code != 0:
+            self.err_flag.zero_()
+            raise RuntimeError(self._ERRORS.get(code, f"device error flag {code}"))
 
     # ------------------------------------------------------------------ kernels
     def forward(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, backward: bool = False,
                 loss_scale: Optional[float] = None) -> StepBuffers:
         """conv1..4 (+ReLU+pool) and the head; with `y` also CE loss and dlogits, in the same head launch."""
         x = self.check_input(x)
+        self.ensure_packed()
         if y is not None:
             _require_cuda(y, "y")
             if y.dtype != torch.int64 or y.shape != (x.shape[0],):
@@ -293,17 +382,31 @@ class BCEngine:
     def train_forward_backward(self, x: torch.Tensor, y: torch.Tensor, loss_scale: Optional[float] = None) -> StepBuffers:
         """Forward, CE loss and full backward in one enqueue (no autograd). grads land in self.grads."""
         x = self.check_input(x)
+        self.ensure_packed()
         b = self.alloc(x.shape[0], x, y.contiguous(), True)
         self.enqueue_train(b, loss_scale)
         return b
 
-    def enqueue_train(self, b: StepBuffers, loss_scale: Optional[float] = None) -> None:
+    def _check_labels(self, b: StepBuffers) -> None:
+        y = b.y
+        if y is None or not y.is_cuda or y.dtype != torch.int64 or tuple(y.shape) != (b.batch,) or not y.is_contiguous():
+            raise ValueError("y must be a contiguous (B,) int64 CUDA tensor of class ids (imitation_dataset.py:131)")
+
+    def enqueue_train(self, b: StepBuffers, loss_scale: Optional[float] = None, reduce_mode: int = 0) -> None:
+        """Forward, CE loss and the whole backward on the current stream (gradients -> self.grads). With self.overlap the
+        weight-gradient kernels of conv4..conv2 run on the engine's side stream under the dgrad chain; reduce_mode 1 is
+        the data-parallel variant (parallel.PeerExchangeStep) that leaves the join to the caller."""
+        self._check_labels(b)
         c = self.ctx(b, loss_scale)
         s = _stream_ptr()
         with torch.cuda.device(self.device):
             for layer in range(4):   # the head's forward is fused into bc_backward's first launch
                 _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
-            _lib.check(self.lib.bc_backward(C.byref(c), 1, s), "bc_backward")
+            if self.overlap or reduce_mode:
+                side, _evs, arr = self.side_handles()
+                _lib.check(self.lib.bc_backward_overlap(C.byref(c), 1, s, side.cuda_stream, arr, reduce_mode), "bc_backward_overlap")
+            else:
+                _lib.check(self.lib.bc_backward(C.byref(c), 1, s), "bc_backward")
 
     def argmax(self, logits: torch.Tensor) -> torch.Tensor:
         out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)

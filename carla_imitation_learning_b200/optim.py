@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._bound = None
         self._dev_lr: Optional[float] = None
         self.grad_scale = 1.0
+        self.exchange = None          # parallel.ModuleExchange when the module path trains data-parallel
 
     # ------------------------------------------------------------------ state
     def _bind(self):
@@ -45,6 +46,10 @@ class FusedAdam(torch.optim.Optimizer):
             return self._bound
         if not arena.is_cuda:
             raise RuntimeError("FusedAdam.step needs the parameters on a CUDA (sm_100) device; there is no CPU fallback")
+        if torch.cuda.is_current_stream_capturing():
+            # the zero-fills below would be baked into the graph and reset the moments, the step count and the LR at
+            # every replay
+            raise RuntimeError("FusedAdam state must exist before CUDA-graph capture: call optimizer.prepare() (or run one eager step) first")
         old = self._bound
         m = torch.zeros_like(arena)
         v = torch.zeros_like(arena)
@@ -67,6 +72,19 @@ class FusedAdam(torch.optim.Optimizer):
         if self._dev_lr != g["lr"]:
             st[_LR:_LR + 1].fill_(float(g["lr"]))   # async fill, no host sync; graph-safe (value lives on device)
             self._dev_lr = g["lr"]
+
+    def prepare(self) -> None:
+        """Allocate the state (first call) and push a changed learning rate to its device scalar. Call before capturing a
+        CUDA graph that contains the step and before every replay: MultiStepLR milestones (imitation.py:84-86) change
+        param_groups[0]['lr'] on the host, the captured kernels read the device scalar."""
+        _arena, _m, _v, st, _ = self._bind()
+        self._sync_scalars(st)
+
+    def _packed(self):
+        """(w_packed pointer or None, obs_size, n_actions): bf16 mode lets the Adam kernel refresh the MMA operand images."""
+        net = self._arena_of
+        eng = getattr(net, "_engine", None)
+        return (eng.packed_ptr() if eng is not None else None), int(net.obs_size), int(net.n_actions)
 
     def set_grad_scale(self, scale: float) -> None:
         """Fold the data-parallel 1/world_size mean into the update's gradient read."""
@@ -102,28 +120,37 @@ class FusedAdam(torch.optim.Optimizer):
         arena, m, v, st, flat_g = self._bind()
         self._sync_scalars(st)
         g = self._flat_grads(arena, flat_g)
-        self.step_flat(g)
+        if self.exchange is not None:          # data parallel through the module path: this rank's gradients -> the peer-visible arena
+            self.exchange.step_from(g)
+        else:
+            self.step_flat(g)
         return loss
 
     def step_flat(self, flat_grads: torch.Tensor) -> None:
         """Tick and fused update in one launch, gradients given as an arena-shaped tensor (the engine's grads)."""
         arena, m, v, st, _ = self._bind()
-        self._sync_scalars(st)
+        if not torch.cuda.is_current_stream_capturing():
+            self._sync_scalars(st)
+        wp, obs, na = self._packed()
         lib, s = _lib.lib(), _stream_ptr()
         with torch.cuda.device(arena.device):
             _lib.check(lib.bc_adam_tick_step(arena.data_ptr(), flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                             st.data_ptr(), arena.numel(), s), "bc_adam_tick_step")
+                                             st.data_ptr(), arena.numel(), wp, obs, na, s), "bc_adam_tick_step")
 
-    def step_exchange(self, peer) -> None:
-        """Data-parallel step: tick + ONE kernel that sums every rank's gradient arena straight from NVLink peer memory
-        (rank order), folds the 1/world mean and applies Adam (bc_adam_step_exchange; `peer` = parallel.PeerGrads)."""
+    def step_exchange(self, peer, lo: int = 0, hi: Optional[int] = None, bucket: int = 1, publish: bool = True, stream=None) -> None:
+        """Data-parallel step of the arena floats [lo, hi): ONE kernel that sums every rank's gradients straight from NVLink
+        peer memory (rank order), folds the 1/world mean and applies Adam (bc_adam_step_exchange; `peer` = parallel.PeerGrads).
+        The launch with publish=True also ticks the step counter and completes the exchange epoch."""
         arena, m, v, st, _ = self._bind()
-        self._sync_scalars(st)
-        lib, s = _lib.lib(), _stream_ptr()
+        if not torch.cuda.is_current_stream_capturing():
+            self._sync_scalars(st)
+        wp, obs, na = self._packed()
+        lib = _lib.lib()
+        s = _stream_ptr() if stream is None else stream
         with torch.cuda.device(arena.device):
-            _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), peer.grads_dev, peer.signals_dev, m.data_ptr(), v.data_ptr(),
-                                                 st.data_ptr(), peer.sync.data_ptr(), arena.numel(), peer.rank, peer.world,
-                                                 peer.err.data_ptr(), s), "bc_adam_step_exchange")
+            _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), m.data_ptr(), v.data_ptr(), st.data_ptr(), arena.numel(),
+                                                 peer.c_struct, lo, arena.numel() if hi is None else hi, bucket, int(publish),
+                                                 wp, obs, na, s), "bc_adam_step_exchange")
 
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict):

@@ -74,45 +74,81 @@ class GradExchange:
 
 
 class PeerGrads:
-    """The gradient arena of this rank in a symmetric allocation every rank maps (torch symmetric memory = cudaIpc /
-    fabric handles; plumbing), plus the per-rank signal pad and the private sync words of bc_adam_step_exchange."""
+    """This rank's gradients in a symmetric allocation every rank maps (torch symmetric memory = cudaIpc / fabric handles;
+    plumbing): TWO arenas back to back -- step e writes and exchanges arena e & 1, so no "done reading" handshake is needed
+    (csrc/abi.cu) -- plus the per-rank signal pad and the private sync words of bc_adam_step_exchange."""
 
     def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        n = engine.arena.numel()
-        self.buf = symm.empty(n, dtype=torch.float32, device=engine.device)
+        self.n = n = engine.arena.numel()
+        self.buf = symm.empty(2 * n, dtype=torch.float32, device=engine.device)
         self.hdl = symm.rendezvous(self.buf, group.group_name)
         self.buf.zero_()
         self.hdl.get_signal_pad(self.rank).zero_()
-        self.grads_dev, self.signals_dev = int(self.hdl.buffer_ptrs_dev), int(self.hdl.signal_pad_ptrs_dev)
-        self.sync = torch.zeros(2, dtype=torch.int32, device=engine.device)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=engine.device)     # [0] completed epochs, [1] CTA counter
         self.err = torch.zeros(1, dtype=torch.int32, device=engine.device)
-        engine.grads = self.buf                       # backward now reduces its partial sums straight into peer-visible memory
+        self.c_struct = _lib.BcPeer(int(self.hdl.buffer_ptrs_dev), int(self.hdl.signal_pad_ptrs_dev), self.sync.data_ptr(),
+                                    self.err.data_ptr(), self.rank, self.world)
+        self.host_epoch = 0                           # mirrors sync[0]: one per completed (publishing) exchange launch
+        # backward now reduces its partial sums straight into peer-visible memory, into the half the device epoch selects
+        engine.grads, engine.grads_epoch, engine.grads_stride, engine.peer = self.buf, self.sync, n, self
+        self.buckets = grad_buckets(engine.obs_size, engine.n_actions)
         torch.cuda.synchronize(engine.device)
         dist.barrier(group)                           # every pad is zero before anybody signals
 
+    def current(self) -> torch.Tensor:
+        """The arena the NEXT exchange reads (= the one the backward of the current step writes)."""
+        half = (self.host_epoch + 1) & 1
+        return self.buf[half * self.n:(half + 1) * self.n]
+
     def check(self) -> None:
         if int(self.err.item()) != 0:
-            raise RuntimeError("bc_adam_step_exchange: a peer rank never signalled (rank died, or the ranks ran different step counts)")
+            raise RuntimeError("bc_adam_step_exchange: a peer rank never signalled (rank died, or the ranks ran different step "
+                               "counts); the parameters were left untouched from that step on")
 
 
 class PeerExchangeStep:
     """One optimisation step on this rank's shard with the gradient exchange FUSED into the Adam kernel over NVLink
-    peer memory: forward, backward, then one kernel that reads all ranks' arenas, sums in rank order, updates.
-    No NCCL call and no host round trip inside the step, so the whole step is one CUDA graph."""
+    peer memory. overlap=True (default): the [fc..conv2] bucket is reduced, exchanged and applied on the engine's side
+    stream UNDER conv1's wgrad; only the 12.6 KB conv1 bucket is exchanged after the backward. No NCCL call and no host
+    round trip inside the step, so the whole step is one CUDA graph."""
 
-    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None):
-        self.eng, self.opt = engine, optimizer
+    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None, overlap: bool = True):
+        self.eng, self.opt, self.overlap = engine, optimizer, overlap
         self.peer = PeerGrads(engine, group)
         optimizer.set_grad_scale(1.0 / self.peer.world)
+        optimizer.prepare()
+        if overlap:
+            engine.side_handles()
+
+    def exchange(self) -> None:
+        """The exchange + Adam launches that follow a backward enqueued with reduce_mode = 1 (overlap) or 0."""
+        eng, opt, peer = self.eng, self.opt, self.peer
+        if self.overlap:
+            (lo0, hi0), (lo1, hi1) = peer.buckets
+            side, evs, _arr = eng.side_handles()
+            main = torch.cuda.current_stream(eng.device)
+            opt.step_exchange(peer, lo0, hi0, bucket=0, publish=False, stream=side.cuda_stream)   # under conv1's wgrad
+            c = eng.ctx(self._bufs)
+            with torch.cuda.device(eng.device):
+                _lib.check(eng.lib.bc_reduce_partials_range(C.byref(c), 4, 5, 0, main.cuda_stream), "reduce [conv1]")
+            evs[3].record(side)
+            main.wait_event(evs[3])
+            opt.step_exchange(peer, lo1, hi1, bucket=1, publish=True)
+        else:
+            opt.step_exchange(peer)
+        if not torch.cuda.is_current_stream_capturing():
+            peer.host_epoch += 1
 
     def __call__(self, bufs, loss_scale: Optional[float] = None) -> None:
-        self.eng.enqueue_train(bufs, loss_scale)
-        self.opt.step_exchange(self.peer)
+        self._bufs = bufs
+        self.eng.enqueue_train(bufs, loss_scale, reduce_mode=1 if self.overlap else 0)
+        self.exchange()
 
     def capture(self, bufs, pre=None):
+        self.opt.prepare()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             if pre is not None:
@@ -121,7 +157,29 @@ class PeerExchangeStep:
         return g
 
     def replay(self, graph) -> None:
+        self.opt.prepare()                   # a MultiStepLR milestone reaches the device scalar the captured kernels read
         graph.replay()
+        self.peer.host_epoch += 1
+
+
+class ModuleExchange:
+    """Data parallelism THROUGH the module contract (Imitation.training_step -> loss.backward() -> FusedAdam.step, the loop
+    train.py:125-129 hands to pl.Trainer(gpus=[...])): FusedAdam.step calls step_from() with this rank's arena-shaped
+    gradients; they already sit in the peer-visible arena when the fused step produced them (zero-copy), else they are
+    copied there; then one bc_adam_step_exchange launch sums all ranks' arenas and applies Adam."""
+
+    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None):
+        self.eng, self.opt = engine, optimizer
+        self.peer = PeerGrads(engine, group)
+        optimizer.set_grad_scale(1.0 / self.peer.world)
+        optimizer.exchange = self
+
+    def step_from(self, flat_grads: torch.Tensor) -> None:
+        cur = self.peer.current()
+        if flat_grads.data_ptr() != cur.data_ptr():
+            cur.copy_(flat_grads)
+        self.opt.step_exchange(self.peer)
+        self.peer.host_epoch += 1
 
 
 class DataParallelStep:
@@ -168,6 +226,7 @@ class DataParallelStep:
     def capture(self, bufs, pre=None):
         """Capture the three kernel segments as CUDA graphs (NCCL stays outside). `pre` = optional callable
         enqueuing work that precedes the step (staging, weight packing) into the first segment."""
+        self.opt.prepare()
         ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga):
             if pre is not None:
@@ -181,6 +240,7 @@ class DataParallelStep:
 
     def replay(self, graphs) -> None:
         ga, gb, gc = graphs
+        self.opt.prepare()
         ga.replay()
         self.xchg.start(self.eng.grads, 0)
         gb.replay()

@@ -73,7 +73,7 @@ typedef struct {
     float loss_scale;        /* dlogits = (softmax-onehot)*loss_scale; 1/batch for the mean */
     int32_t conv_mode;       /* bit mask of tcgen05 (bf16) kernels: 1 forward, 2 dgrad, 4 wgrad conv2-4, 8 wgrad conv1; 0 = exact f32 */
     void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
-    int32_t* err_flag;       /* device int, set to 1 if a bounded mbarrier wait expired              */
+    int32_t* err_flag;       /* device int: 1 = a bounded mbarrier wait expired, 3 = a label outside [0, n_actions) */
     void* act_bf16[3];       /* bf16 mode: bf16 copies of act[0..2] in the layouts the shifted-window kernels read
                                 (csrc/conv_sw.cu, conv4_sw.cu): act1 P8 (B,2,784,8), act2 P8 (B,4,144,8),
                                 act3 P8B (8,B,16,8) = [c/8][b][pixel][8]; written by the conv epilogues     */
@@ -83,6 +83,10 @@ typedef struct {
                                 stride_n == stride_c is the sliding window: consecutive samples share 3 of 4 planes
                                 and conv1 then loads every plane once for 4 samples                              */
     int64_t x_tp_stride_n, x_tp_stride_c;
+    const uint32_t* grads_epoch; /* data-parallel peer exchange only (else NULL): device word counting COMPLETED exchanges. The gradient
+                                arena is then double-buffered, bc_reduce_partials writes arena ((*grads_epoch + 1) & 1) at
+                                grads + that * grads_stride -- the one bc_adam_step_exchange reads next (see bc_peer)           */
+    int64_t grads_stride;    /* floats between the two arenas                                                                 */
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);
@@ -118,6 +122,12 @@ int bc_head(const bc_ctx* c, int head_mode, void* stream);
 /* ---- a9-a10: training_step loss + autograd backward (src/models/imitation.py:38-45).
  * bc_backward assumes bc_forward ran on the same ctx; fills grads (and loss when with_loss). */
 int bc_backward(const bc_ctx* c, int with_loss, void* stream);
+/* bc_backward with the weight-gradient kernels of conv4..conv2 on `side_stream`, overlapping the dgrad chain (wgrad(l) and
+ * dgrad(l) are independent). ev = 4 caller-owned cudaEvent_t (timing disabled) for the fork/join; capturable.
+ * reduce_mode 0: everything is joined and reduced on `stream` (like bc_backward). reduce_mode 1 (data-parallel overlap):
+ * segments [fc..conv2] are reduced on the SIDE stream, conv1's wgrad is left running on `stream`, nothing is joined -- the
+ * caller launches the bucket-0 exchange on the side stream, then bc_reduce_partials_range(c, 4, 5, ..) + the join itself. */
+int bc_backward_overlap(const bc_ctx* c, int with_loss, void* stream, void* side_stream, void* const* ev, int reduce_mode);
 int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream);   /* layer 1..3 -> gact[layer-1] */
 int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream);   /* layer 0..3 -> partials      */
 int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream); /* partials -> grads (, loss) */
@@ -133,21 +143,38 @@ int bc_loss_reduce(const bc_ctx* c, void* stream);                 /* head CTAs'
 int bc_adam_tick(double* state, void* stream);
 int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                  const double* state, int64_t n, void* stream);
-/* tick + step in ONE launch (what the training step uses): state9 = the 8 doubles above + one more word used as a CTA counter */
-int bc_adam_tick_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double* state9, int64_t n, void* stream);
+/* tick + step in ONE launch (what the training step uses): state9 = the 8 doubles above + one more word used as a CTA counter.
+ * w_packed != NULL (bf16 mode, obs_size 4; n must be the arena of (obs_size, n_actions)): the kernel also rewrites the bf16
+ * MMA operand images of the conv weights it has just updated, so the step needs no bc_pack_weights launch. */
+int bc_adam_tick_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, double* state9, int64_t n,
+                      void* w_packed, int obs_size, int n_actions, void* stream);
 
 /* ---- a12 folded into a11: the DDP gradient mean (train.py:125 `pl.Trainer(gpus=[...])`, utils.py:60-64) inside the Adam step.
- * peer_grads_dev / peer_signals_dev: DEVICE arrays of `world` pointers -- rank r's gradient arena and signal pad mapped into
- * this process (peer memory over NVLink; torch symmetric memory provides both). Each rank launches this once per step after its
- * own gradients are complete: flag exchange, sum of the `world` arenas in rank order read straight from peer memory, Adam update
- * with state[5] = grad_scale = 1/world (the tick is folded in: do NOT call bc_adam_tick before it), second flag exchange (nobody
- * still reads this rank's gradients when the kernel ends).
- * sync_state: 2 device u32 {epoch, CTA counter}, zero-initialised, private to the rank. *err_flag = 2 if a peer never arrived. */
-int bc_adam_step_exchange(float* params, const void* peer_grads_dev, const void* peer_signals_dev, float* exp_avg, float* exp_avg_sq,
-                          double* state, uint32_t* sync_state, int64_t n, int rank, int world, int32_t* err_flag, void* stream);
+ * bc_peer: peer_grads_dev / peer_signals_dev are DEVICE arrays of `world` pointers -- rank r's gradient arenas (TWO arenas of n
+ * floats back to back: step e uses arena e & 1) and signal pad mapped into this process (peer memory over NVLink; torch
+ * symmetric memory provides both). sync_state: 4 device u32 {completed epochs, CTA counter, -, -}, zero-initialised, private to
+ * the rank; bc_ctx.grads_epoch points at its first word. *err_flag = 2 if a peer never arrived (parameters are then left alone).
+ * Each rank launches the exchange once per bucket and step after that bucket's gradients are complete: flag exchange, sum of the
+ * `world` arenas in rank order read straight from peer memory, Adam update of floats [lo, hi) with state[5] = grad_scale =
+ * 1/world. bucket 0 = [fc..conv2] (launched on a side stream under conv1's wgrad, publish = 0), bucket 1 = conv1 or the whole
+ * arena (publish = 1: the tick -- do NOT call bc_adam_tick -- and the epoch are published by its last CTA; launch it after
+ * bucket 0 has completed). */
+typedef struct {
+    const void* peer_grads_dev;
+    const void* peer_signals_dev;
+    uint32_t* sync_state;
+    int32_t* err_flag;
+    int32_t rank, world;
+} bc_peer;
+int bc_adam_step_exchange(float* params, float* exp_avg, float* exp_avg_sq, double* state9, int64_t n, const bc_peer* peer,
+                          int64_t lo, int64_t hi, int bucket, int publish, void* w_packed, int obs_size, int n_actions, void* stream);
 
 /* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
 int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);
+
+/* v[0..n) *= *scale_dev (a device scalar), nothing is touched when it is exactly 1: how `loss.backward(gradient=g)` reaches
+ * gradients that the fused step has already computed for d loss (imitation.py:38-45 returns the loss, Lightning calls backward) */
+int bc_scale_inplace(float* v, int64_t n, const float* scale_dev, void* stream);
 
 /* ---- self-test of the tcgen05/TMEM primitives the bf16 conv kernels are built from:
  * D[M,N] f32 = A[M,K] bf16 * B[N,K]^T bf16 (K contiguous). *err_flag is set to 1 if an mbarrier

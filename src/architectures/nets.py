@@ -21,7 +21,7 @@ except Exception:  # pragma: no cover - Lightning is not installed in the build 
     _Base = nn.Module
 
 from carla_imitation_learning_b200 import _lib
-from carla_imitation_learning_b200.autograd import LossFunction, NetFunction
+from carla_imitation_learning_b200.autograd import FusedStepFunction, LossFunction, NetFunction
 from carla_imitation_learning_b200.engine import BCEngine
 
 # layer table in constructor order: (container, slot, weight shape builder)
@@ -67,6 +67,17 @@ class ConvNet1(_Base):
             self.precision = 'fp32'
         if self.precision not in ('fp32', 'bf16'):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
+        # B200 additions (configs/model/imitation.yaml), all absent from the reference and all optional:
+        #   cuda_graph: true  -> training_step runs the fused forward+backward as ONE CUDA graph per loader slot
+        #   fused_step: true  -> the same fused enqueue without graph capture
+        #   overlap_backward  -> weight-gradient kernels of conv4..conv2 on a side stream (bc_backward_overlap)
+        def _opt(key, default=False):
+            try:
+                return hparams[key] if key in hparams else default
+            except TypeError:
+                return default
+        self.fast_step = "graph" if _opt('cuda_graph') else ("eager" if _opt('fused_step') else None)
+        self.overlap_backward = bool(_opt('overlap_backward', True))
 
         # same RNG consumption order as the reference: example input first (nets.py:14) ...
         self.example_input_array = torch.randn((1, obs_size, 256, 256))
@@ -157,8 +168,8 @@ class ConvNet1(_Base):
             self._engine = BCEngine(self._arena, self.obs_size, self.n_actions)
             if self.precision == 'bf16' and self.obs_size == 4:
                 self._engine.set_mode('bf16')
-        if self._engine.conv_mode:
-            self._engine.pack_weights()     # bf16 operand images follow the f32 master weights (cheap: 2 launches)
+            self._engine.overlap = self.overlap_backward
+        self._engine.ensure_packed()        # bf16 operand images: re-derived only when the master weights changed outside FusedAdam
         return self._engine
 
     def _to_device(self, t: torch.Tensor) -> torch.Tensor:
@@ -170,7 +181,10 @@ class ConvNet1(_Base):
 
     def loss(self, x, y):
         """Fused forward + CrossEntropyLoss() (mean) -- what Imitation.training_step needs."""
-        return LossFunction.apply(self._to_device(x), self._to_device(y), self, *self._ordered_params)
+        x, y = self._to_device(x), self._to_device(y)
+        if self.fast_step and torch.is_grad_enabled():
+            return FusedStepFunction.apply(x, y, self, *self._ordered_params)
+        return LossFunction.apply(x, y, self, *self._ordered_params)
 
     @torch.no_grad()
     def act(self, x):

@@ -52,9 +52,10 @@ class Imitation(_Base):
 
     def _loss(self, x, y):
         fused = getattr(self.net, "loss", None)
-        if fused is not None:
-            return fused(x, y)
-        return nn.functional.cross_entropy(self.forward(x), y)   # a foreign net: plain contract
+        if fused is None:
+            raise TypeError("Imitation drives the B200 kernels through net.loss(x, y): pass a src.architectures.nets.ConvNet1 "
+                            "(there is no eager-PyTorch path in this module)")
+        return fused(x, y)
 
     def training_step(self, batch, batch_idx):
         x, y = batch
@@ -72,6 +73,13 @@ class Imitation(_Base):
         sch = self.lr_schedulers()
         if sch is not None:
             sch.step()
+        # the one host synchronisation per epoch: a bounded device wait that expired, an out-of-range label or a peer that
+        # never signalled would have left wrong numbers behind -- raise instead of training on
+        eng = getattr(self.net, "_engine", None)
+        if eng is not None:
+            eng.check_device_errors()
+            if getattr(eng, "peer", None) is not None:
+                eng.peer.check()
         loss = torch.stack([o['loss'].detach() for o in outputs]).mean()   # stays on device until logged
         self._add_scalars({"train_loss": loss})
 
@@ -96,10 +104,10 @@ class Imitation(_Base):
     # -- optimiser (imitation.py:82-87) ----------------------------------------------------------
     def configure_optimizers(self):
         params = list(self.parameters())
-        if all(hasattr(p, "_bc_arena") for p in params):
-            optimizer = FusedAdam(params, lr=1e-3)     # LR is hard-coded in the reference (LEARNING_RATE is unused)
-        else:
-            optimizer = torch.optim.Adam(params, lr=1e-3)
+        if not all(hasattr(p, "_bc_arena") for p in params):
+            raise TypeError("Imitation.configure_optimizers builds the fused arena Adam: every parameter must belong to a "
+                            "src.architectures.nets.ConvNet1")
+        optimizer = FusedAdam(params, lr=1e-3)         # LR is hard-coded in the reference (LEARNING_RATE is unused)
         scheduler = lr_scheduler.MultiStepLR(optimizer, milestones=[20, 30], gamma=0.1)
         if not _HAVE_PL:
             self._schedulers = scheduler
@@ -107,3 +115,12 @@ class Imitation(_Base):
 
     def scale_image(self, img):
         return (img + 1) / 2
+
+    if not _HAVE_PL:
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, hparams=None, net=None, data_loader=None, strict=True, **_kw):
+            """pl.LightningModule.load_from_checkpoint as train.py:198-201 calls it (constructor kwargs passed in)."""
+            from carla_imitation_learning_b200.trainer import load_checkpoint_into
+            model = cls(hparams, net, data_loader)
+            load_checkpoint_into(model, checkpoint_path, strict=strict)
+            return model

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert _lib.lib().bc_abi_version() == 1
+    assert _lib.lib().bc_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback():
