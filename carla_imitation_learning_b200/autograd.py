@@ -46,7 +46,7 @@ class NetFunction(torch.autograd.Function):
         eng = net.engine()
         bufs.dlogits.copy_(dlogits)
         eng.backward(bufs)
-        flat = eng.grad_view().clone()
+        flat = eng._last_flat = eng.grad_view().clone()
         return (None, None, *_param_grads(net, flat))
 
 
@@ -68,7 +68,7 @@ class LossFunction(torch.autograd.Function):
         saved = bufs.dlogits
         bufs.dlogits = saved * gloss      # device-side scale: no host sync; keeps `saved` for a second backward
         eng.backward(bufs)
-        flat = eng.grad_view().clone()
+        flat = eng._last_flat = eng.grad_view().clone()
         bufs.dlogits = saved
         return (None, None, None, *_param_grads(net, flat))
 

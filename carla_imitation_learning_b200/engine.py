@@ -281,6 +281,18 @@ class BCEngine:
         """The arena-shaped buffer the backward of the current step writes (peer exchange: the half the epoch selects)."""
         return self.peer.current() if self.peer is not None else self.grads
 
+    def grad_arena_at(self, ptr: int) -> Optional[torch.Tensor]:
+        """The engine-owned arena-shaped gradient buffer starting at device address `ptr` (None if there is none): lets the
+        optimiser recognise .grad tensors that are views of one arena and consume it without a copy."""
+        cands = [self.grads] + (self._slots or []) + ([self._last_flat] if getattr(self, "_last_flat", None) is not None else [])
+        if self.peer is not None:
+            n = self.peer.n
+            cands = [self.peer.buf[:n], self.peer.buf[n:]] + cands[1:]
+        for t in cands:
+            if t.data_ptr() == ptr and t.numel() >= self.arena.numel():
+                return t[:self.arena.numel()]
+        return None
+
     def next_grad_slot(self, params) -> torch.Tensor:
         """Gradient arena for the next fused step. Two arenas alternate, so the .grad views autograd adopted from the
         previous step stay intact until zero_grad() drops them (Lightning runs training_step BEFORE zero_grad); should a

@@ -37,6 +37,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._dev_lr: Optional[float] = None
         self.grad_scale = 1.0
         self.exchange = None          # parallel.ModuleExchange when the module path trains data-parallel
+        self.stats = {"zero_copy": 0, "gathered": 0}   # how step() found the gradients: as one arena (no copy) / gathered per tensor
 
     # ------------------------------------------------------------------ state
     def _bind(self):
@@ -94,15 +95,19 @@ class FusedAdam(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ step
     def _flat_grads(self, arena, flat_g) -> torch.Tensor:
-        """The gradients as one arena-shaped buffer; zero-copy when autograd left arena views in .grad."""
+        """The gradients as one arena-shaped buffer; zero-copy when the .grad tensors are (still) the views the CUDA
+        backward handed to autograd, i.e. they sit at their arena offsets inside one gradient arena of the engine."""
         first = self._params[0].grad
         if first is not None:
             base = first.data_ptr() - self._params[0]._bc_offset * 4
             if all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
                    and p.grad.data_ptr() == base + p._bc_offset * 4 for p in self._params):
-                owner = getattr(first, "_bc_flat", None)
-                if owner is not None and owner.data_ptr() == base:
+                eng = getattr(self._arena_of, "_engine", None)
+                owner = eng.grad_arena_at(base) if eng is not None else None
+                if owner is not None:
+                    self.stats["zero_copy"] += 1
                     return owner
+        self.stats["gathered"] += 1
         for p in self._params:
             off, n = p._bc_offset, p.numel()
             if p.grad is None:
