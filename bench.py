@@ -317,11 +317,7 @@ def run_b200(args):
         lab = np.concatenate([np.zeros(4, np.int64)] + [host_labels[i].numpy() for i in range(NBUF)])
         loader = SequentialFrames(seq, lab, batch_size=B, device=dev, dtype=torch.float32, layout=("tp" if args.mode == "bf16" else "plain"))
 
-        def batches():
-            while True:
-                for xy in loader:
-                    yield xy
-        it = batches()
+        it = loader.cycle()       # endless: the next pass's first batch is uploaded under the current pass's last one
 
         def e2e_step(i):
             x, y = next(it)
@@ -607,7 +603,7 @@ def main():
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="N>1 gradient exchange: fused peer-memory Adam, or NCCL buckets")
     ap.add_argument("--dp-overlap", type=int, default=1, help="peer exchange: [fc..conv2] bucket on a side stream under conv1's wgrad")
-    ap.add_argument("--overlap", type=int, default=1, help="weight-gradient kernels of conv4..conv2 on a side stream (bc_backward_overlap)")
+    ap.add_argument("--overlap", type=int, default=0, help="weight-gradient kernels of conv4..conv2 on a side stream (bc_backward_overlap)")
     ap.add_argument("--e2e-api", default="module", choices=["module", "engine"])
     ap.add_argument("--no-module", action="store_true", help="skip the device-resident module-path measurement")
     ap.add_argument("--no-graph", action="store_true")

@@ -98,29 +98,42 @@ class _StepGraphs:
 
 
 class FusedStepFunction(torch.autograd.Function):
-    """loss = CE(ConvNet1(x), y) with the gradients of all 14 parameters computed in the same enqueue."""
+    """loss = CE(ConvNet1(x), y) with the gradients of all 14 parameters computed in the same enqueue.
+
+    backward() does what autograd's AccumulateGrad would do with the 14 gradients -- adopt them as .grad when there is none,
+    add them otherwise -- but with per-slot CACHED arena views, so a step costs 14 attribute stores instead of 14 tensor
+    constructions, and FusedAdam recognises the arena by identity (no gather, no copy)."""
 
     @staticmethod
     def forward(ctx, x, y, net, *params):
         eng = net.engine()
         x = eng.check_input(x)
         B = x.shape[0]
-        flat = eng.next_grad_slot(net._ordered_params)          # a gradient arena no live .grad aliases
+        flat, views = eng.next_grad_slot(net._ordered_params)   # a gradient arena no live .grad aliases
         bufs = eng.static_buffers(B, x, y)
         if net.fast_step == "graph":
             xp = x.tp.data_ptr() if isinstance(x, StagedBatch) else x.data_ptr()
-            graphs = net.__dict__.setdefault("_step_graphs", _StepGraphs())
+            graphs = net.__dict__.get("_step_graphs")
+            if graphs is None:
+                graphs = net.__dict__["_step_graphs"] = _StepGraphs()
             graphs.run((xp, y.data_ptr(), B, flat.data_ptr()), lambda: eng.enqueue_train(bufs))
         else:
             eng.enqueue_train(bufs)
-        ctx.net, ctx.flat = net, flat
+        ctx.net, ctx.flat, ctx.views = net, flat, views
         return bufs.loss.clone()         # the static loss cell is rewritten by the next step; epoch-end hooks keep these
 
     @staticmethod
     def backward(ctx, gloss):
-        net, flat = ctx.net, ctx.flat
+        net, flat, views = ctx.net, ctx.flat, ctx.views
         eng = net.engine()
-        g = gloss.reshape(1).to(torch.float32)
+        g = gloss.reshape(1)
+        if g.dtype != torch.float32:
+            g = g.float()
         with torch.cuda.device(eng.device):
             _lib.check(eng.lib.bc_scale_inplace(flat.data_ptr(), flat.numel(), g.data_ptr(), _stream_ptr()), "bc_scale_inplace")
-        return (None, None, None, *_param_grads(net, flat))
+        for p, v in zip(net._ordered_params, views):
+            if p.grad is None:
+                p.grad = v
+            else:
+                p.grad.add_(v)
+        return (None,) * (3 + len(views))

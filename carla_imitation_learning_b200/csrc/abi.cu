@@ -357,24 +357,30 @@ static int record_wait(void* ev, void* on, void* waiter) {
     return BC_OK;
 }
 
-int bc_backward_overlap(const bc_ctx* c, int with_loss, void* stream, void* side_stream, void* const* ev, int reduce_mode) {
+int bc_backward_overlap(const bc_ctx* c, int with_loss, void* stream, void* side_stream, void* const* ev, int flags) {
     BC_CHECK_ARG(c && side_stream && ev && ev[0] && ev[1] && ev[2] && ev[3], "bc_backward_overlap: null ctx / side stream / events");
     BC_CHECK_ARG(side_stream != stream, "bc_backward_overlap: the side stream must differ from the main stream");
+    const bool dp_split = flags & 1, wgrad_main = flags & 2;
     int rc = bc_head(c, with_loss ? 3 : 2, stream);
     if (rc) return rc;
     for (int l = 3; l >= 1; --l) {
-        if ((rc = record_wait(ev[3 - l], stream, side_stream))) return rc;     // the gradient of layer l's output is complete
-        if ((rc = bc_conv_bwd_wgrad(c, l, side_stream))) return rc;
+        if (wgrad_main) {
+            if ((rc = bc_conv_bwd_wgrad(c, l, stream))) return rc;
+        } else {
+            if ((rc = record_wait(ev[3 - l], stream, side_stream))) return rc;     // the gradient of layer l's output is complete
+            if ((rc = bc_conv_bwd_wgrad(c, l, side_stream))) return rc;
+        }
         if ((rc = bc_conv_bwd_dgrad(c, l, stream))) return rc;
     }
-    if (reduce_mode == 1) {
+    if (dp_split) {
         // data-parallel overlap: [fc..conv2] are reduced on the side stream as soon as conv2's wgrad is done; the caller
         // launches the bucket-0 exchange there, then joins (ev[3]) and reduces conv1 on the main stream
+        if (wgrad_main && (rc = record_wait(ev[0], stream, side_stream))) return rc;   // everything up to conv2's dgrad (and wgrad) is enqueued
         if ((rc = bc_reduce_partials_range(c, 0, 4, with_loss, side_stream))) return rc;
         return bc_conv_bwd_wgrad(c, 0, stream);
     }
     if ((rc = bc_conv_bwd_wgrad(c, 0, stream))) return rc;
-    if ((rc = record_wait(ev[3], side_stream, stream))) return rc;
+    if (!wgrad_main && (rc = record_wait(ev[3], side_stream, stream))) return rc;
     return bc_reduce_partials(c, with_loss, stream);
 }
 

@@ -116,16 +116,27 @@ class SequentialFrames:
         return ev
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        return self._batches(loop=False)
+
+    def cycle(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        """Endless iteration over the sequence; the first batch of the next pass is uploaded under the last batch of the
+        current one (a fresh __iter__ per epoch would start every pass with an exposed H2D copy)."""
+        return self._batches(loop=True)
+
+    def _batches(self, loop: bool) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         nb = len(self)
-        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(cur)
         ev = self._produce(0, 0)
-        for k in range(nb):
-            slot = k & 1
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            if k + 1 < nb:
+        n = 0                                   # batches produced so far: slot = n & 1
+        while True:
+            k, slot = n % nb, n & 1
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            if loop or k + 1 < nb:
                 # the other slot was consumed one iteration ago on the compute stream
-                self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
-                ev = self._produce(k + 1, slot ^ 1)
+                self._copy_stream.wait_stream(cur)
+                ev = self._produce((k + 1) % nb, slot ^ 1)
             lo = k * self.batch_size
             b = min(self.batch_size, self.n_samples - lo)
             if self.layout == "tp":
@@ -133,6 +144,9 @@ class SequentialFrames:
             else:
                 x = sliding_window(self._gray[slot][:b + self.frame_skip], self.frame_skip)
             yield x, self._lab[slot][:b]
+            n += 1
+            if not loop and n == nb:
+                return
 
 
 def sequential_train_val_test_iterator(hparams, frames_by_split=None):

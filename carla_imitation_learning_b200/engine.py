@@ -150,7 +150,8 @@ class BCEngine:
         self.w_packed = torch.zeros(int(self.lib.bc_packed_weight_bytes()), dtype=torch.uint8, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.conv_mode = 0            # bit mask, see bc_ctx.conv_mode: 0 = exact f32 FFMA kernels, 15 = all tcgen05 kernels
-        self._packed_version = None   # arena._version the bf16 operand images were last derived from (None = never)
+        self._packed_version = None   # weights_version() the bf16 operand images were last derived from (None = never)
+        self.weights_version = lambda: self.arena._version     # ConvNet1 widens it to every Parameter view (p.copy_ bumps p's own counter)
         self.overlap = False          # backward with the conv4..conv2 weight-gradient kernels on a side stream (bc_backward_overlap)
         self._side = None             # (side stream, 4 events, ctypes array of their handles)
         self._static = {}             # batch -> StepBuffers reused by the static-shape paths (no per-step allocation)
@@ -293,10 +294,19 @@ class BCEngine:
                 return t[:self.arena.numel()]
         return None
 
-    def next_grad_slot(self, params) -> torch.Tensor:
-        """Gradient arena for the next fused step. Two arenas alternate, so the .grad views autograd adopted from the
-        previous step stay intact until zero_grad() drops them (Lightning runs training_step BEFORE zero_grad); should a
-        live .grad still alias the arena about to be rewritten (gradient accumulation over >2 micro-steps), it is copied
+    def _views_of(self, flat: torch.Tensor, params):
+        """Per-parameter views of an arena-shaped gradient buffer, cached per buffer address."""
+        cache = self.__dict__.setdefault("_grad_views", {})
+        key = flat.data_ptr()
+        v = cache.get(key)
+        if v is None:
+            v = cache[key] = (flat, [flat[p._bc_offset:p._bc_offset + p.numel()].view(p.shape) for p in params])
+        return v
+
+    def next_grad_slot(self, params):
+        """(arena, per-parameter views) for the next fused step. Two arenas alternate, so the .grad tensors of the previous
+        step stay intact until zero_grad() drops them (Lightning runs training_step BEFORE zero_grad); should a live .grad
+        still alias the arena about to be rewritten (gradient accumulation over more than two micro-steps), it is copied
         out first."""
         if self.peer is not None:
             flat = self.peer.current()
@@ -305,13 +315,21 @@ class BCEngine:
                 self._slots = [self.grads, torch.zeros_like(self.grads)]
             self._slot_i ^= 1
             flat = self.grads = self._slots[self._slot_i]
-        lo = flat.data_ptr()
-        hi = lo + flat.numel() * 4
-        for p in params:
-            g = p.grad
-            if g is not None and lo <= g.data_ptr() < hi:
-                p.grad = g.clone()
-        return flat
+        flat, views = self._views_of(flat, params)
+        for p, v in zip(params, views):
+            if p.grad is v:
+                p.grad = v.clone()
+        return flat, views
+
+    def grads_as_arena(self, params) -> Optional[torch.Tensor]:
+        """The gradient arena whose cached views ARE the .grad tensors of `params` (identity), else None."""
+        first = params[0].grad
+        if first is None:
+            return None
+        for flat, views in self.__dict__.get("_grad_views", {}).values():
+            if views[0] is first:
+                return flat if all(p.grad is v for p, v in zip(params, views)) else None
+        return None
 
     def side_handles(self):
         """(side stream, events, ctypes void*[4]) of the overlapped backward; created outside any graph capture."""
@@ -339,12 +357,12 @@ class BCEngine:
         c.params, c.w_packed = self.arena.data_ptr(), self.w_packed.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.bc_pack_weights(C.byref(c), _stream_ptr()), "bc_pack_weights")
-        self._packed_version = self.arena._version
+        self._packed_version = self.weights_version()
 
     def ensure_packed(self) -> None:
-        """Re-pack only when the master weights changed behind the kernels' back (torch in-place ops bump arena._version:
-        load_state_dict, p.data.copy_, a foreign optimiser). FusedAdam refreshes the images itself."""
-        if self.conv_mode and self._packed_version != self.arena._version:
+        """Re-pack only when the master weights changed behind the kernels' back (torch in-place ops bump the version
+        counters: load_state_dict, p.copy_, p.data.add_, a foreign optimiser). FusedAdam refreshes the images itself."""
+        if self.conv_mode and self._packed_version != self.weights_version():
             self.pack_weights()
 
     def packed_ptr(self) -> Optional[int]:
@@ -404,19 +422,20 @@ class BCEngine:
         if y is None or not y.is_cuda or y.dtype != torch.int64 or tuple(y.shape) != (b.batch,) or not y.is_contiguous():
             raise ValueError("y must be a contiguous (B,) int64 CUDA tensor of class ids (imitation_dataset.py:131)")
 
-    def enqueue_train(self, b: StepBuffers, loss_scale: Optional[float] = None, reduce_mode: int = 0) -> None:
+    def enqueue_train(self, b: StepBuffers, loss_scale: Optional[float] = None, dp_split: bool = False) -> None:
         """Forward, CE loss and the whole backward on the current stream (gradients -> self.grads). With self.overlap the
-        weight-gradient kernels of conv4..conv2 run on the engine's side stream under the dgrad chain; reduce_mode 1 is
-        the data-parallel variant (parallel.PeerExchangeStep) that leaves the join to the caller."""
+        weight-gradient kernels of conv4..conv2 run on the engine's side stream under the dgrad chain; dp_split is the
+        data-parallel variant (parallel.PeerExchangeStep): [fc..conv2] reduced on the side stream, join left to the caller."""
         self._check_labels(b)
         c = self.ctx(b, loss_scale)
         s = _stream_ptr()
         with torch.cuda.device(self.device):
             for layer in range(4):   # the head's forward is fused into bc_backward's first launch
                 _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
-            if self.overlap or reduce_mode:
+            if self.overlap or dp_split:
                 side, _evs, arr = self.side_handles()
-                _lib.check(self.lib.bc_backward_overlap(C.byref(c), 1, s, side.cuda_stream, arr, reduce_mode), "bc_backward_overlap")
+                flags = (1 if dp_split else 0) | (0 if self.overlap else 2)
+                _lib.check(self.lib.bc_backward_overlap(C.byref(c), 1, s, side.cuda_stream, arr, flags), "bc_backward_overlap")
             else:
                 _lib.check(self.lib.bc_backward(C.byref(c), 1, s), "bc_backward")
 

@@ -97,6 +97,12 @@ class FusedAdam(torch.optim.Optimizer):
     def _flat_grads(self, arena, flat_g) -> torch.Tensor:
         """The gradients as one arena-shaped buffer; zero-copy when the .grad tensors are (still) the views the CUDA
         backward handed to autograd, i.e. they sit at their arena offsets inside one gradient arena of the engine."""
+        eng = getattr(self._arena_of, "_engine", None)
+        if eng is not None:
+            owner = eng.grads_as_arena(self._params)           # the fused step's cached views, recognised by identity
+            if owner is not None:
+                self.stats["zero_copy"] += 1
+                return owner
         first = self._params[0].grad
         if first is not None:
             base = first.data_ptr() - self._params[0]._bc_offset * 4
@@ -156,6 +162,12 @@ class FusedAdam(torch.optim.Optimizer):
             _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), m.data_ptr(), v.data_ptr(), st.data_ptr(), arena.numel(),
                                                  peer.c_struct, lo, arena.numel() if hi is None else hi, bucket, int(publish),
                                                  wp, obs, na, s), "bc_adam_step_exchange")
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        for p in self._params:
+            p.grad = None
 
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict):

