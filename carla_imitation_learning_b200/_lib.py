@@ -36,6 +36,7 @@ class BcCtx(C.Structure):
         ("reserved0", C.c_void_p),
         ("x_tp", C.c_void_p), ("x_tp_stride_n", C.c_int64), ("x_tp_stride_c", C.c_int64),
         ("grads_epoch", C.c_void_p), ("grads_stride", C.c_int64),
+        ("gact0_p8", C.c_void_p), ("amax0_p8", C.c_void_p),
     ]
 
 

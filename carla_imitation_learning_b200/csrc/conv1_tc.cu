@@ -92,7 +92,7 @@ struct TileIter {
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
                 const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
-                __nv_bfloat16* __restrict__ ybf, int B, int* err, int ablate) {
+                __nv_bfloat16* __restrict__ ybf, uint8_t* __restrict__ amax_p8, int B, int* err, int ablate) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* b_full = bars;
@@ -299,6 +299,9 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                         uint2 pk;
                         pk.x = *reinterpret_cast<uint32_t*>(&p01); pk.y = *reinterpret_cast<uint32_t*>(&p23);
                         *reinterpret_cast<uint2*>(P_ + ((cq >> 1) * 56 + pyl * 28 + px) * 8 + (cq & 1) * 4) = pk;   // P8 bf16 tile [c/8][pixel][8], stored in pass B
+                        if (amax_p8)   // the routing again in P8 order [b][c/8][pixel][8] (one 4 B store): what conv1's wgrad builders read
+                            *reinterpret_cast<uint32_t*>(amax_p8 + (((size_t)b * 2 + (cq >> 1)) * 784 + (2 * ty + pyl) * 28 + px) * 8 + (cq & 1) * 4) =
+                                (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
                     }
                 }
                 if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -338,17 +341,20 @@ constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, 1-3 
 constexpr int ROWB = 336;
 constexpr int VIEW = 6 * ROWB;               // 2016: one (ky,h) slice = 126 rows x 16 B
 constexpr int A_SLOT = 16 * VIEW;            // 14 slices + 2 all-ones blocks
-constexpr int NA = 4;
 constexpr int DY_BYTES = 64 * 256;           // [8 n-blocks][128 rows][16 B]
-constexpr int NDY = 5;
 constexpr int TP_PIECE_BYTES = 86 * ROWB;
-constexpr int OFF_A = 0;
-constexpr int OFF_DY = (OFF_A + NA * A_SLOT + 64 + 1023) / 1024 * 1024;
-constexpr int OFF_BAR = OFF_DY + NDY * DY_BYTES;
-constexpr int NBAR = 2 * NA + 2 * NDY + 1;
-constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 32;   // + TMEM address and the 4 'accumulator written' flags
+// ring depths: NA plane slots, NDY gradient slots (4 live -- plane P meets dY(P..P-3) -- plus the ones being built ahead)
+template <int NA_, int NDY_>
+struct Ring {
+    static constexpr int NA = NA_, NDY = NDY_;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_DY = (OFF_A + NA * A_SLOT + 64 + 1023) / 1024 * 1024;
+    static constexpr int OFF_BAR = OFF_DY + NDY * DY_BYTES;
+    static constexpr int NBAR = 2 * NA + 2 * NDY + 1;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 32;   // + TMEM address and the 4 'accumulator written' flags
+    static_assert(SMEM_BYTES <= 227 * 1024, "conv1 wgrad (TP) shared memory");
+};
 constexpr int TMEM_COLS = 256;
-static_assert(SMEM_BYTES <= 227 * 1024, "conv1 wgrad (TP) shared memory");
 
 // One CTA owns a contiguous range of the job list i = ty * NJ + P; a "segment" is the part of it inside one tile row.
 struct Seg { int ty, Pa, Pb, sa, sb; };
@@ -377,10 +383,16 @@ struct SegIter {
     }
 };
 
+// COMPACT: the builders read the ReLU-masked bf16 gradient and the routing in the P8 layout ([b][c/8][pixel][8]: one 16 B + one
+// 8 B load per (pooled pixel, 8 channels) unit, written by conv2's dgrad and conv1's forward) instead of 24 scalar loads from the
+// f32 NCHW gradient / activation / u8 routing tensors; gP then points at the bf16 gradient and amax at the P8 routing.
+template <bool COMPACT, typename R>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
-                      const float* __restrict__ gP, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
+                      const void* __restrict__ gP_, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
                       float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate) {
+    constexpr int NA = R::NA, NDY = R::NDY, OFF_A = R::OFF_A, OFF_DY = R::OFF_DY, OFF_BAR = R::OFF_BAR, NBAR = R::NBAR;
+    const float* __restrict__ gP = reinterpret_cast<const float*>(gP_);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;                  // [NA]
@@ -520,30 +532,45 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
             }
             __device__ void step_group() { step(); if (valid) step(); }
         };
-        float ug0[8], ug1[8]; uint32_t up0 = 0u, up1 = 0u;                 // two register sets (named: no dynamic indexing)
-        auto fetch = [&](float (&ug)[8], uint32_t& up, const Build& bd) {
+        struct Regs { float g[8]; uint32_t pos; uint4 g8; uint2 a8; };     // one register set: f32 path uses g/pos, compact path g8/a8
+        Regs r0, r1;                                                       // two register sets (named: no dynamic indexing)
+        r0.pos = r1.pos = 0u; r0.g8 = r1.g8 = make_uint4(0, 0, 0, 0); r0.a8 = r1.a8 = make_uint2(0xffffffffu, 0xffffffffu);
+        auto fetch = [&](Regs& r, const Build& bd) {
             if (!unit || !bd.valid) return;
-            const size_t g0 = (((size_t)bd.smp * 16 + ucg * 8) * 28 + 2 * bd.sg.ty + upyl) * 28 + upx;
-            uint32_t pk = 0;
+            if constexpr (COMPACT) {
+                const size_t idx = ((size_t)bd.smp * 2 + ucg) * 784 + (2 * bd.sg.ty + upyl) * 28 + upx;
+                r.g8 = __ldg(reinterpret_cast<const uint4*>(gP_) + idx);
+                r.a8 = __ldg(reinterpret_cast<const uint2*>(amax) + idx);
+            } else {
+                const size_t g0 = (((size_t)bd.smp * 16 + ucg * 8) * 28 + 2 * bd.sg.ty + upyl) * 28 + upx;
+                uint32_t pk = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const size_t g = g0 + (size_t)k * 784;
-                ug[k] = aP[g] > 0.f ? gP[g] : 0.f;
-                pk |= (uint32_t)amax[g] << (4 * k);
+                for (int k = 0; k < 8; ++k) {
+                    const size_t g = g0 + (size_t)k * 784;
+                    r.g[k] = aP[g] > 0.f ? gP[g] : 0.f;
+                    pk |= (uint32_t)amax[g] << (4 * k);
+                }
+                r.pos = pk;
             }
-            up = pk;
         };
-        auto store = [&](const float (&ug)[8], uint32_t up, uint8_t* dy) {
+        auto store = [&](const Regs& r, uint8_t* dy) {
             if (!unit) return;
 #pragma unroll
             for (int p = 0; p < 9; ++p) {
                 uint32_t w[4];
+                if constexpr (COMPACT) {
+                    // per-byte equality masks of the 8 routing codes against p, widened to the bf16 halves they select
+                    const uint32_t m_lo = __vcmpeq4(r.a8.x, 0x01010101u * (uint32_t)p), m_hi = __vcmpeq4(r.a8.y, 0x01010101u * (uint32_t)p);
+                    w[0] = r.g8.x & __byte_perm(m_lo, 0, 0x1100); w[1] = r.g8.y & __byte_perm(m_lo, 0, 0x3322);
+                    w[2] = r.g8.z & __byte_perm(m_hi, 0, 0x1100); w[3] = r.g8.w & __byte_perm(m_hi, 0, 0x3322);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float lo = ((up >> (8 * k)) & 15u) == (uint32_t)p ? ug[2 * k] : 0.f;
-                    const float hi = ((up >> (8 * k + 4)) & 15u) == (uint32_t)p ? ug[2 * k + 1] : 0.f;
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                    w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                    for (int k = 0; k < 4; ++k) {
+                        const float lo = ((r.pos >> (8 * k)) & 15u) == (uint32_t)p ? r.g[2 * k] : 0.f;
+                        const float hi = ((r.pos >> (8 * k + 4)) & 15u) == (uint32_t)p ? r.g[2 * k + 1] : 0.f;
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                        w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
                 }
                 const int oyl = 3 * upyl + p / 3, ox = 3 * upx + p % 3;
                 // row r = (oyl, ox / 4), column block = (ox % 4) * 2 + channel half: [n/8][128 rows][16 B]
@@ -553,9 +580,9 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         Build cur(B, sliding);
         if (grp && cur.valid) cur.step();                  // group 1 starts at the CTA's second build
         Build ahead = cur;
-        fetch(ug0, up0, ahead);
+        fetch(r0, ahead);
         if (ahead.valid) ahead.step_group();
-        fetch(ug1, up1, ahead);
+        fetch(r1, ahead);
         if (ahead.valid) ahead.step_group();               // `ahead` = two group-builds past `cur`
         bool ok = true;
 #pragma unroll 1
@@ -564,11 +591,11 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
             ok = tc05::mbar_wait(dy_empty + slot, ((cur.kb / NDY) & 1) ^ 1, err);
             if (!ok) break;
             uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
-            if (n & 1) store(ug1, up1, dy); else store(ug0, up0, dy);
+            if (n & 1) store(r1, dy); else store(r0, dy);
             tc05::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc05::mbar_arrive(dy_full + slot);
-            if (n & 1) fetch(ug1, up1, ahead); else fetch(ug0, up0, ahead);   // the set just stored is free: load two group-builds ahead
+            if (n & 1) fetch(r1, ahead); else fetch(r0, ahead);   // the set just stored is free: load two group-builds ahead
             cur.step_group();
             if (ahead.valid) ahead.step_group();
         }
@@ -650,7 +677,7 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
 #endif
     bc::launch_pdl(c1tp::conv1_tp_kernel, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
         (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
-        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], c->batch, c->err_flag, ablate);
+        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], (c->conv_mode & 16) ? c->amax0_p8 : nullptr, c->batch, c->err_flag, ablate);
     BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
     return BC_OK;
 }
@@ -670,14 +697,27 @@ int bc_conv1_wgrad_tp_grid(const bc_ctx* c) {
 }
 
 static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
-    BC_CHECK_ARG(c->err_flag && c->partials && c->gact[0] && c->act[0] && c->amax[0], "conv1 wgrad (tcgen05, TP): null buffer");
+    const bool compact = (c->conv_mode & 16) != 0;
+    BC_CHECK_ARG(c->err_flag && c->partials && (compact ? (c->gact0_p8 && c->amax0_p8) : (c->gact[0] && c->act[0] && c->amax[0])),
+                 "conv1 wgrad (tcgen05, TP): null buffer (%s gradient path)", compact ? "compact P8" : "f32 NCHW");
+    BC_CHECK_ARG(!compact || ((uintptr_t)c->gact0_p8 % 16 == 0 && (uintptr_t)c->amax0_p8 % 8 == 0), "conv1 wgrad (tcgen05, TP): gact0_p8 / amax0_p8 alignment");
     BC_CHECK_ARG(c->obs_size == 4, "conv1 wgrad (tcgen05, TP): obs_size 4 only");
     BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0,
                  "conv1 wgrad (tcgen05, TP): x_tp and its strides must be 16 B aligned");
+    // ring depths: the compact builders are fast enough that a deeper gradient ring pays (3 plane + 7 gradient slots); the f32
+    // NCHW builders are throughput-bound either way and keep the 4 + 5 split they were tuned with
+    using RC = c1wg2::Ring<3, 7>;
+    using RF = c1wg2::Ring<4, 5>;
+    auto kc = c1wg2::conv1_wgrad_tp_kernel<true, RC>;
+    auto kf = c1wg2::conv1_wgrad_tp_kernel<false, RF>;
+    auto kc45 = c1wg2::conv1_wgrad_tp_kernel<true, RF>;       // measurement switch BC_C1WG_RING=45 (same results, shallower ring)
+    static const bool ring45 = getenv("BC_C1WG_RING") && atoi(getenv("BC_C1WG_RING")) == 45;
     static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(c1wg2::conv1_wgrad_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1wg2::SMEM_BYTES);
-        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05, TP): smem opt-in %d B failed: %s", c1wg2::SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, RC::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, RF::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kc45, cudaFuncAttributeMaxDynamicSharedMemorySize, RF::SMEM_BYTES);
+        if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad (tcgen05, TP): smem opt-in failed: %s", cudaGetErrorString(e));
         configured = true;
     }
     const bc::Arena ar = bc::arena_layout(c->obs_size, c->n_actions);
@@ -688,9 +728,14 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
 #else
     constexpr int ablate = 0;
 #endif
-    bc::launch_pdl(c1wg2::conv1_wgrad_tp_kernel, dim3(grid), dim3(c1wg2::NTHREADS), c1wg2::SMEM_BYTES, (cudaStream_t)stream,
-        (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, c->gact[0], c->act[0], c->amax[0],
-        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
+    if (compact)
+        bc::launch_pdl(ring45 ? kc45 : kc, dim3(grid), dim3(c1wg2::NTHREADS), ring45 ? RF::SMEM_BYTES : RC::SMEM_BYTES, (cudaStream_t)stream,
+            (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const void*)c->gact0_p8, (const float*)nullptr, (const uint8_t*)c->amax0_p8,
+            c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
+    else
+        bc::launch_pdl(kf, dim3(grid), dim3(c1wg2::NTHREADS), RF::SMEM_BYTES, (cudaStream_t)stream,
+            (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const void*)c->gact[0], (const float*)c->act[0], (const uint8_t*)c->amax[0],
+            c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
     BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
     return BC_OK;
 }

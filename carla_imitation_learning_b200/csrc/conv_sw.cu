@@ -347,6 +347,9 @@ struct DgradArgs {
     const __nv_bfloat16* wpk;                                // dgrad operand image: step (tap, co/16): CIN rows x 16 k
     float* gin;                                              // (B, CIN, HIN, HIN) f32
     int B; int* err;
+    // conv2 only, compact conv1 gradient path (bc_ctx.conv_mode bit 16): instead of `gin`, the gradient leaves ReLU-masked
+    // (input activation > 0) as bf16 in the P8 layout of that activation, which is what conv1's wgrad builders consume
+    const __nv_bfloat16* act_in_p8; __nv_bfloat16* gin_p8;
 };
 
 template <typename C>
@@ -475,6 +478,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
             const int m = t * 128 + ew * 32 + lane;           // GEMM row inside the image
             const int iy = m / WP, ix = m % WP;
             const bool valid = m < C::MROWS && ix < HIN;
+            if constexpr (N == 16) {
+                if (a.gin_p8) {
+                    // compact path: one pixel x 16 channels per thread = two 16 B stores, masked by the bf16 activation
+                    float v[16];
+                    tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW, v);
+                    tc05::tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int cg = 0; cg < 2; ++cg) {
+                            const size_t idx = ((size_t)b * 2 + cg) * (HIN * HIN) + iy * HIN + ix;
+                            const uint4 av = __ldg(reinterpret_cast<const uint4*>(a.act_in_p8) + idx);
+                            const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+                            uint32_t o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float lo = (aw[k] & 0xffffu) ? v[cg * 8 + 2 * k] : 0.f;       // act is post-ReLU: non-zero bits <=> > 0
+                                const float hi = (aw[k] >> 16) ? v[cg * 8 + 2 * k + 1] : 0.f;
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                                o[k] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            reinterpret_cast<uint4*>(a.gin_p8)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                    tc05::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc05::mbar_arrive(t_empty + acc);
+                    continue;
+                }
+            }
 #pragma unroll
             for (int c0 = 0; c0 < N; c0 += 16) {
                 float v[16];
@@ -743,7 +775,9 @@ int launch_dgrad(const bc_ctx* c, int layer, const uint8_t* wpk, cudaStream_t s,
     const int ntiles = c->batch * C::TPI;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
-    DgradArgs args{c->gact[layer], c->act[layer], c->amax[layer], (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag};
+    const bool compact = layer == 1 && (c->conv_mode & 16) && c->gact0_p8 && c->act_bf16[0];
+    DgradArgs args{c->gact[layer], c->act[layer], c->amax[layer], (const __nv_bfloat16*)wpk, c->gact[layer - 1], c->batch, c->err_flag,
+                   compact ? (const __nv_bfloat16*)c->act_bf16[0] : nullptr, compact ? (__nv_bfloat16*)c->gact0_p8 : nullptr};
     bc::launch_pdl(kern, dim3(grid), dim3(NTHREADS), C::SMEM_BYTES, s, args);
     BC_CUDA_LAUNCH_CHECK(name);
     return BC_OK;

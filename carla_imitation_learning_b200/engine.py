@@ -120,6 +120,8 @@ class StepBuffers:
     ghead: Optional[torch.Tensor] = None
     gact: List[torch.Tensor] = field(default_factory=list)
     act_bf16: List[torch.Tensor] = field(default_factory=list)   # bf16 mode: bf16 copies feeding the next layer's MMA
+    gact0_p8: Optional[torch.Tensor] = None                      # bf16 mode: masked gradient w.r.t. act1, P8 bf16 (conv2 dgrad -> conv1 wgrad)
+    amax0_p8: Optional[torch.Tensor] = None                      # bf16 mode: conv1's pool routing again in P8 order
     x_tp: Optional[torch.Tensor] = None                          # bf16 mode: the input as Toeplitz-ready planes
     x_tp_strides: tuple = (0, 0)                                 # (sample, channel) element strides into x_tp
 
@@ -181,6 +183,9 @@ class BCEngine:
             bufs.act_bf16 = [torch.empty((batch, 2, 784, 8), dtype=torch.bfloat16, device=dev),
                              torch.empty((batch, 4, 144, 8), dtype=torch.bfloat16, device=dev),
                              torch.empty((8, batch, 16, 8), dtype=torch.bfloat16, device=dev)]
+        if self.conv_mode & 16:
+            bufs.gact0_p8 = torch.zeros((batch, 2, 784, 8), dtype=torch.bfloat16, device=dev)
+            bufs.amax0_p8 = torch.zeros((batch, 2, 784, 8), dtype=torch.uint8, device=dev)
         if backward:
             self._alloc_bwd(bufs)
         return bufs
@@ -253,6 +258,8 @@ class BCEngine:
             c.x_tp, (c.x_tp_stride_n, c.x_tp_stride_c) = b.x_tp.data_ptr(), b.x_tp_strides
         if self.grads_epoch is not None:
             c.grads_epoch, c.grads_stride = self.grads_epoch.data_ptr(), self.grads_stride
+        if b.gact0_p8 is not None:
+            c.gact0_p8, c.amax0_p8 = b.gact0_p8.data_ptr(), b.amax0_p8.data_ptr()
         return c
 
     def static_buffers(self, batch: int, x, y: Optional[torch.Tensor]) -> StepBuffers:
@@ -347,7 +354,7 @@ class BCEngine:
 
     def set_mode(self, mode: str) -> None:
         """'fp32' = exact FFMA kernels (rel 1e-5); 'bf16' = tcgen05 kernels on bf16-staged frames (rel 2e-2)."""
-        self.conv_mode = {"fp32": 0, "bf16": 15}[mode]
+        self.conv_mode = {"fp32": 0, "bf16": 31}[mode]     # 31 = every tcgen05 kernel + the compact conv1 gradient path
 
     def pack_weights(self) -> None:
         """Derive the bf16 operand images from the f32 master weights (one launch). The fused Adam kernels keep the images

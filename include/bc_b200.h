@@ -71,7 +71,7 @@ typedef struct {
     float* loss;             /* [1] mean CE                             */
     float* partials;         /* workspace, bc_partials_floats() floats  */
     float loss_scale;        /* dlogits = (softmax-onehot)*loss_scale; 1/batch for the mean */
-    int32_t conv_mode;       /* bit mask of tcgen05 (bf16) kernels: 1 forward, 2 dgrad, 4 wgrad conv2-4, 8 wgrad conv1; 0 = exact f32 */
+    int32_t conv_mode;       /* bit mask of tcgen05 (bf16) kernels: 1 forward, 2 dgrad, 4 wgrad conv2-4, 8 wgrad conv1, 16 compact conv1 gradient path (gact0_p8 / amax0_p8, needs 1|2|8); 0 = exact f32 */
     void* w_packed;          /* bc_packed_weight_bytes() bytes: bf16 MMA operand images (bc_pack_weights) */
     int32_t* err_flag;       /* device int: 1 = a bounded mbarrier wait expired, 3 = a label outside [0, n_actions) */
     void* act_bf16[3];       /* bf16 mode: bf16 copies of act[0..2] in the layouts the shifted-window kernels read
@@ -87,6 +87,9 @@ typedef struct {
                                 arena is then double-buffered, bc_reduce_partials writes arena ((*grads_epoch + 1) & 1) at
                                 grads + that * grads_stride -- the one bc_adam_step_exchange reads next (see bc_peer)           */
     int64_t grads_stride;    /* floats between the two arenas                                                                 */
+    void* gact0_p8;          /* conv_mode bit 16: the ReLU-masked gradient w.r.t. act[0] as bf16 in the P8 layout (B,2,784,8), written by
+                                conv2's tcgen05 dgrad INSTEAD of gact[0]; conv1's tcgen05 wgrad builds its dY operand from it       */
+    uint8_t* amax0_p8;       /* conv_mode bit 16: amax[0] again in the P8 layout (B,2,784,8) u8, written by conv1's tcgen05 forward */
 } bc_ctx;
 
 size_t bc_partials_floats(int obs_size, int n_actions);

@@ -311,6 +311,7 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
     x = sliding_window(stage_gray(torch.from_numpy(frames).to(dev), dtype=torch.bfloat16))
     y = torch.from_numpy(labels[4:4 + B]).to(dev)
     bufs = eng.train_forward_backward(x, y)
+    eng.conv_mode = 15        # kernel by kernel on the f32 NCHW gradient buffers this test fills (the compact conv1 path: next test)
     s = torch.cuda.current_stream().cuda_stream
     gen = torch.Generator(device="cpu").manual_seed(6)
     params = dict(net.named_parameters())
@@ -352,6 +353,39 @@ def test_tc_backward_is_exact_on_its_bf16_operands(B):
             ed = float((got_d - ref_d).abs().max() / ref_d.abs().max())
             assert ed <= 2e-5, (layer, "dgrad", ed)
     eng.check_device_errors()
+
+
+@pytest.mark.parametrize("B", [3, 37])
+def test_compact_conv1_gradient_path_is_bitwise_the_nchw_path(B):
+    """conv_mode bit 16 (what set_mode('bf16') enables): conv1's forward also writes its routing in P8 order, conv2's dgrad
+    writes the ReLU-masked bf16 gradient in P8 order instead of f32 NCHW, conv1's wgrad builds dY from those -- a pure
+    re-layout: every product is bit-identical to the f32 NCHW path (conv_mode 15)."""
+    import ctypes as C
+    from carla_imitation_learning_b200 import _lib, stage_frames
+    from oracle import bc_oracle as O
+    from src.architectures.nets import ConvNet1
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": "bf16"}).to(dev)
+    eng = net.engine()
+    assert eng.conv_mode == 31
+    frames, labels = O.synth_frames(23 + B, B + 4)
+    y = torch.from_numpy(labels[4:4 + B].copy()).to(dev)
+    bufs = eng.train_forward_backward(stage_frames(torch.from_numpy(frames).to(dev)), y)
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    g_compact = eng.grads.clone()
+    p8 = lambda t: t.reshape(B, 2, 8, 784).permute(0, 1, 3, 2).contiguous()
+    assert torch.equal(bufs.amax0_p8, p8(bufs.amax[0]))
+    # the same backward through the f32 NCHW buffers
+    eng.conv_mode = 15
+    c = eng.ctx(bufs)
+    _lib.check(eng.lib.bc_backward(C.byref(c), 1, torch.cuda.current_stream().cuda_stream), "bc_backward")
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    assert torch.equal(eng.grads, g_compact)
+    masked = torch.where(bufs.act[0] > 0, bufs.gact[0], torch.zeros_like(bufs.gact[0])).to(torch.bfloat16)
+    assert torch.equal(bufs.gact0_p8.view(torch.int16), p8(masked).view(torch.int16))
 
 
 def _tp_reference(planes):
