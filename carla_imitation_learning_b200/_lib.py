@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 # -cudart shared: the library reuses the libcudart.so.12 torch has already loaded (one CUDA runtime per process)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", os.environ.get("BC_CUDART", "shared"))
@@ -90,7 +90,7 @@ def build(verbose: bool = False) -> str:
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *srcs]
+    cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BC_NVCC_EXTRA", "").split(), "-o", LIB_PATH, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

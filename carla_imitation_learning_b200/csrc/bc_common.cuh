@@ -135,3 +135,5 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 }  // namespace bc
+
+int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Partials& pl, int grid, void* stream);   // conv1_wgrad3.cu

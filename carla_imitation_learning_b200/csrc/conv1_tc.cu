@@ -339,8 +339,11 @@ namespace c1wg2 {
 using c1tc::MROWS; using c1tc::NG; using c1tc::TILES_PER_FRAME;
 constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, 1-3 and 8 issuers, 4-7 / 9-12 dY builder groups (4-7 also epilogue)
 constexpr int ROWB = 336;
-constexpr int VIEW = 6 * ROWB;               // 2016: one (ky,h) slice = 126 rows x 16 B
-constexpr int A_SLOT = 16 * VIEW;            // 14 slices + 2 all-ones blocks
+constexpr int VIEW = 6 * ROWB;               // 2016: one (ky,h) slice = 126 rows x 16 B (what a bulk copy brings)
+constexpr int VPAD = 2048;                   // slice pitch in shared memory: every 128 B core matrix of the A operand stays inside one
+                                             // 128 B line (at the natural 2016 B pitch each core straddles two lines and the operand
+                                             // fetch of an MMA costs twice the wavefronts: tools/mma_bench.py)
+constexpr int A_SLOT = 16 * VPAD;            // 14 slices + 2 all-ones blocks
 constexpr int DY_BYTES = 64 * 256;           // [8 n-blocks][128 rows][16 B]
 constexpr int TP_PIECE_BYTES = 86 * ROWB;
 // ring depths: NA plane slots, NDY gradient slots (4 live -- plane P meets dY(P..P-3) -- plus the ones being built ahead)
@@ -411,11 +414,11 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         tc05::mbar_fence_init();
     }
     if (warp == 0) tc05::tmem_alloc(tmem_slot, TMEM_COLS);
-    // A slots start as zeros (the K rows 126,127 of a slice read 32 B of its neighbour: never a NaN pattern) with
+    // A slots start as zeros (the K rows 126,127 of a slice are its 32 B of padding: zeros, never a NaN pattern) with
     // the two trailing blocks of every slot set to bf16 ones (accumulator rows 112.. = sum_r dY = the bias gradient)
     for (int i = threadIdx.x; i < (NA * A_SLOT + 64) / 16; i += NTHREADS) {
         const int within = (i * 16) % A_SLOT;
-        const uint32_t v = (i * 16 < NA * A_SLOT && within >= 14 * VIEW) ? 0x3f803f80u : 0u;
+        const uint32_t v = (i * 16 < NA * A_SLOT && within >= 14 * VPAD) ? 0x3f803f80u : 0u;
         reinterpret_cast<uint4*>(smem + OFF_A)[i] = make_uint4(v, v, v, v);
     }
     // the dY ring: rows 0..125 of a slot are rewritten for every sample tile, rows 126,127 stay zero
@@ -436,7 +439,7 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
             uint32_t k = 0;
             bool ok = true;
             const int ky = lane >> 1, h = lane & 1;
-            const int src_off = ((ky % 3) * 2 + h) * TP_PIECE_BYTES + (ky / 3) * ROWB, dst_off = (ky * 2 + h) * VIEW;
+            const int src_off = ((ky % 3) * 2 + h) * TP_PIECE_BYTES + (ky / 3) * ROWB, dst_off = (ky * 2 + h) * VPAD;
             while (ok && it.next(sg)) {
                 for (int P = sg.Pa; P <= sg.Pb; ++P, ++k) {
                     const uint32_t slot = k % NA, ph = (k / NA) & 1;
@@ -459,7 +462,7 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         // ------------------------------------------------------------------ issuer ci: D[ci] += A(job)^T dY(sample)
         const int ci = warp == 8 ? 0 : warp;
         constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, 64, 1, 1);      // MN-major A and B
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_A), 128, VIEW, tc05::SW_NONE);
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_A), 128, VPAD, tc05::SW_NONE);
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_DY), 128, 2048, tc05::SW_NONE);
         const uint32_t d_tmem = tmem_base + ci * 64;
         SegIter it(B, sliding);
@@ -728,6 +731,9 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
 #else
     constexpr int ablate = 0;
 #endif
+    static const bool gen2 = getenv("BC_C1WG_GEN") && atoi(getenv("BC_C1WG_GEN")) == 2;     // measurement switch: second-generation kernel
+    if (compact && c->x_tp_stride_n == c->x_tp_stride_c && !gen2)
+        return bc_conv1_wgrad3_launch(c, ar, pl, grid, stream);                                 // third generation (conv1_wgrad3.cu)
     if (compact)
         bc::launch_pdl(ring45 ? kc45 : kc, dim3(grid), dim3(c1wg2::NTHREADS), ring45 ? RF::SMEM_BYTES : RC::SMEM_BYTES, (cudaStream_t)stream,
             (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const void*)c->gact0_p8, (const float*)nullptr, (const uint8_t*)c->amax0_p8,

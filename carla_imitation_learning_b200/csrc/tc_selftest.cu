@@ -73,13 +73,13 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const __nv_bfloat
 // mode 3+: full producer/consumer ring with NS = mode-2 stages: warp 1+st "refills" stage st (waits the
 //          stage's empty barrier, fence.proxy.async, arrives on its full barrier), the MMA thread waits full,
 //          issues, commits to empty -- the synchronisation skeleton of the conv kernels without any data movement.
-__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, int M, int mn_major, long long* cycles, int* err) {
+__global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int mode, int M, int mn_major, int a_off16, int a_sbo, long long* cycles, int* err) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar, full[14], empty[14];
     __shared__ uint32_t tmem_base_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NS = mode >= 3 ? mode - 2 : 0;
-    for (int i = threadIdx.x; i < (8 * 4096 + 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    for (int i = threadIdx.x; i < (8 * 4096 + 16384 + 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         tc05::mbar_init(&bar, 1);
         for (int i = 0; i < 14; ++i) { tc05::mbar_init(full + i, 1); tc05::mbar_init(empty + i, 1); }
@@ -95,7 +95,9 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
         // whole warp runs the loop, one elected lane issues (the pattern of the conv kernels)
         // mn_major: both operands MN-major, [core along M/N at 2048 B][16 K rows x 16 B] (the wgrad kernels' layout)
         const uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, (uint32_t)M, (uint32_t)N, mn_major, mn_major);
-        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem), 128, mn_major ? 2048 : 256, tc05::SW_NONE);
+        // a_off16 / a_sbo: A operand start shifted by a_off16 x 16 B and an explicit stride between its 8-row core groups -- does a core
+        // matrix (128 B) that is not 128 B aligned cost a second shared-memory wavefront?
+        const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem) + 16u * (uint32_t)a_off16, 128, a_sbo ? (uint32_t)a_sbo : (mn_major ? 2048u : 256u), tc05::SW_NONE);
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + 8 * 4096), 128, mn_major ? 2048 : 256, tc05::SW_NONE);
         const long long t0 = clock64();
         bool ok = true;
@@ -152,14 +154,16 @@ __global__ void __launch_bounds__(512) tc_mma_bench_kernel(int N, int reps, int 
 extern "C" int bc_tc_mma_bench(int N, int reps, int mode, int grid, long long* cycles2, int* err_flag, void* stream) {
     const int M = (mode & (1 << 20)) ? 64 : 128;          // bit 20: M=64 instructions
     const int mn_major = (mode >> 21) & 1;                // bit 21: MN-major operands
-    mode &= ~(3 << 20);
+    const int a_off16 = (mode >> 22) & 7;                 // bits 22-24: A start offset in 16 B units
+    const int a_sbo = ((mode >> 25) & 1) ? 2016 : 0;      // bit 25: A core-group stride 2016 B (the un-padded conv1 wgrad slices)
+    mode &= ~(0x3f << 20);
     BC_CHECK_ARG(!mn_major || N <= 64, "bc_tc_mma_bench: the MN-major variant has room for N <= 64");
     const int threads = (mode >> 8) ? (mode >> 8) : 512;   // bits 8.. of mode: CTA size override
     mode &= 0xff;
     BC_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && cycles2 && err_flag, "bc_tc_mma_bench: bad arguments");
-    const int smem = 8 * 4096 + 16384;
+    const int smem = 8 * 4096 + 16384 + 1024;
     cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, M, mn_major, cycles2, err_flag);
+    tc_mma_bench_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(N, reps, mode, M, mn_major, a_off16, a_sbo, cycles2, err_flag);
     BC_CUDA_LAUNCH_CHECK("tc_mma_bench_kernel");
     return BC_OK;
 }

@@ -25,3 +25,10 @@ for N in (32, 64):
     print(f"M=64 N {N:3d} unrolled x8 groups, one commit: issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1 | (1 << 20)))
 for N in (16, 32, 64):
     print(f"MN-major M=128 N {N:3d} unrolled x8 groups: issue %.1f complete %.1f cyc/mma err %d" % run(N, 512, 1 | (1 << 21)))
+for off in (0, 1, 2, 5, 7):
+    print(f"K-major  N  64 unrolled x8, A start +{16 * off:3d} B : issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, 1 | (off << 22)))
+for off in (0, 2, 5):
+    print(f"K-major  N 256 unrolled x8, A start +{16 * off:3d} B : issue %.1f complete %.1f cyc/mma err %d" % run(256, 512, 1 | (off << 22)))
+for sbo in (0, 1):
+    for off in (0, 2):
+        print(f"MN-major N  64 unrolled x8, A core-group stride {2016 if sbo else 2048}, start +{16 * off} B: issue %.1f complete %.1f cyc/mma err %d" % run(64, 512, 1 | (1 << 21) | (sbo << 25) | (off << 22)))
