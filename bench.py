@@ -602,7 +602,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="N>1 gradient exchange: fused peer-memory Adam, or NCCL buckets")
-    ap.add_argument("--dp-overlap", type=int, default=1, help="peer exchange: [fc..conv2] bucket on a side stream under conv1's wgrad")
+    ap.add_argument("--dp-overlap", type=int, default=0, help="peer exchange: [fc..conv2] bucket on a side stream under conv1's wgrad")
     ap.add_argument("--overlap", type=int, default=0, help="weight-gradient kernels of conv4..conv2 on a side stream (bc_backward_overlap)")
     ap.add_argument("--e2e-api", default="module", choices=["module", "engine"])
     ap.add_argument("--no-module", action="store_true", help="skip the device-resident module-path measurement")

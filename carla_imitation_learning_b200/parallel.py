@@ -111,11 +111,13 @@ class PeerGrads:
 
 class PeerExchangeStep:
     """One optimisation step on this rank's shard with the gradient exchange FUSED into the Adam kernel over NVLink
-    peer memory. overlap=True (default): the [fc..conv2] bucket is reduced, exchanged and applied on the engine's side
-    stream UNDER conv1's wgrad; only the 12.6 KB conv1 bucket is exchanged after the backward. No NCCL call and no host
-    round trip inside the step, so the whole step is one CUDA graph."""
+    peer memory: after the backward ONE kernel sums all ranks' arenas and applies Adam (default). overlap=True: the
+    [fc..conv2] bucket is reduced, exchanged and applied on the engine's side stream UNDER conv1's wgrad and only the
+    12.6 KB conv1 bucket is exchanged after the backward -- measured on 2 x B200 the fork/join costs more than the overlap
+    hides (0.2599 vs 0.2455 ms/step, profiles/README.md), so it is off by default. No NCCL call and no host round trip
+    inside the step either way: the whole step is one CUDA graph."""
 
-    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None, overlap: bool = True):
+    def __init__(self, engine, optimizer, group: Optional[dist.ProcessGroup] = None, overlap: bool = False):
         self.eng, self.opt, self.overlap = engine, optimizer, overlap
         self.peer = PeerGrads(engine, group)
         optimizer.set_grad_scale(1.0 / self.peer.world)

@@ -33,7 +33,7 @@ class TrainStep:
     replay it -- so a caller that rotates over a few device slots pays one graph launch per step."""
 
     def __init__(self, net, optimizer: FusedAdam, batch: int, *, group=None, exchange: Optional[str] = None,
-                 overlap: Optional[bool] = None, graph: bool = True, dp_overlap: bool = True):
+                 overlap: Optional[bool] = None, graph: bool = True, dp_overlap: bool = False):
         self.net, self.opt, self.batch, self.graph = net, optimizer, int(batch), graph
         self.eng: BCEngine = net.engine()
         if overlap is not None:
