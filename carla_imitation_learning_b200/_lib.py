@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "head_branched.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 # -cudart shared: the library reuses the libcudart.so.12 torch has already loaded (one CUDA runtime per process)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", os.environ.get("BC_CUDART", "shared"))
@@ -46,6 +46,15 @@ class BcPeer(C.Structure):
                 ("err_flag", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class BcBranched(C.Structure):
+    """Mirror of `bc_branched` (include/bc_b200.h): the branched-head extension."""
+    _fields_ = [("n_branches", C.c_int32), ("n_out", C.c_int32), ("batch", C.c_int32), ("loss_kind", C.c_int32),
+                ("feat", C.c_void_p), ("command", C.c_void_p), ("labels", C.c_void_p), ("targets", C.c_void_p),
+                ("params", C.c_void_p), ("grads", C.c_void_p), ("out", C.c_void_p), ("dout", C.c_void_p),
+                ("gfeat", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p), ("err_flag", C.c_void_p),
+                ("loss_scale", C.c_float)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "bc_arena_layout": (C.c_int64, [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -54,6 +63,7 @@ EXPORTS = {
     "bc_pack_weights": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_packed_weight_bytes": (C.c_size_t, []),
     "bc_stage_gray_tp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "bc_stage_augment": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bc_planes_to_tp": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "bc_forward": (C.c_int, [C.POINTER(BcCtx), C.c_void_p]),
     "bc_conv_relu_pool_fwd": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p]),
@@ -72,6 +82,9 @@ EXPORTS = {
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bc_backward_overlap": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "bc_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_head_branched": (C.c_int, [C.POINTER(BcBranched), C.c_int, C.c_void_p]),
+    "bc_head_branched_partials_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "bc_head_branched_layout": (C.c_int64, [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bc_scale_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "bc_tc_gemm_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bc_tc_mma_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -164,7 +164,94 @@ __global__ void __launch_bounds__(256) planes_to_tp_kernel(const TIN* __restrict
         }, out, u);
 }
 
+// ---- EXTENSION (no counterpart in the reference; oracle/ext_oracle.py::stage_augmented): crop + colour jitter + normalise fused
+// into the staging pass. Per frame one row of `table` = {crop_y, crop_x, brightness, contrast, saturation, mean, 1/std, -}
+// (generated on the host from a seed: data.augment_table). Every step is a single-rounded f32 operation in the oracle's order
+// (no FMA contraction), so the f32 output is bit-identical to the numpy specification and the bf16 output is its rounding.
+struct AugRow { float cy, cx, br, ct, sa, mean, istd, pad; };
+__device__ __forceinline__ float clamp255(float v) { return fminf(fmaxf(v, 0.f), 255.f); }
+__device__ __forceinline__ float luma(float r, float g, float b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+}
+__device__ __forceinline__ float aug_px(const uint8_t* __restrict__ px, const AugRow& t) {
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = clamp255(__fmul_rn((float)__ldg(px + k), t.br));
+        c[k] = clamp255(__fadd_rn(__fmul_rn(__fadd_rn(v, -127.5f), t.ct), 127.5f));
+    }
+    const float y = luma(c[0], c[1], c[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = clamp255(__fadd_rn(y, __fmul_rn(__fadd_rn(c[k], -y), t.sa)));
+    const float g = __fmul_rn(luma(c[0], c[1], c[2]), 1.0f / 255.0f);
+    return __fmul_rn(__fadd_rn(g, -t.mean), t.istd);
+}
+
+// plain f32 planes (n,256,256): one thread = 4 pixels
+__global__ void __launch_bounds__(256) stage_aug_f32_kernel(const uint8_t* __restrict__ rgb, int src_h, int src_w, const AugRow* __restrict__ table,
+                                                            float* __restrict__ out, int64_t n_groups) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_groups; u += stride) {
+        const int x4 = (int)(u % (BC_W / 4)), R = (int)((u / (BC_W / 4)) % BC_H);
+        const int64_t plane = u / ((BC_W / 4) * BC_H);
+        const AugRow t = table[plane];
+        const uint8_t* src = rgb + ((plane * src_h + (int)t.cy + R) * (int64_t)src_w + (int)t.cx + 4 * x4) * 3;
+        float4 v;
+        v.x = aug_px(src, t); v.y = aug_px(src + 3, t); v.z = aug_px(src + 6, t); v.w = aug_px(src + 9, t);
+        reinterpret_cast<float4*>(out)[u] = v;
+    }
+}
+
+// Toeplitz-ready bf16 planes: the unit decomposition of stage_gray_tp_kernel (12 pixels per thread)
+__global__ void __launch_bounds__(256) stage_aug_tp_kernel(const uint8_t* __restrict__ rgb, int src_h, int src_w, const AugRow* __restrict__ table,
+                                                           __nv_bfloat16* __restrict__ out, int64_t n_units) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {
+        const int g = (int)(u % TP_NU), q = (int)((u / TP_NU) % TP_NQ), c = (int)((u / (TP_NU * TP_NQ)) % 3);
+        const int64_t plane = u / (TP_NU * TP_NQ * 3);
+        const int R = 3 * q + c;
+        uint32_t pk[6] = {0, 0, 0, 0, 0, 0};
+        if (R < BC_H) {
+            const AugRow t = table[plane];
+            const uint8_t* src = rgb + ((plane * src_h + (int)t.cy + R) * (int64_t)src_w + (int)t.cx + 12 * g) * 3;
+            const int npx = g < TP_NG ? 12 : 4;
+            float v[12];
+#pragma unroll
+            for (int p = 0; p < 12; ++p) v[p] = p < npx ? aug_px(src + 3 * p, t) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        }
+        __nv_bfloat16* row0 = out + plane * BC_TP_PLANE_ELEMS + ((int64_t)(c * 2) * TP_NQ + q) * (TP_NG * 8);
+        __nv_bfloat16* row1 = row0 + TP_NQ * TP_NG * 8;
+        if (g < TP_NG) {
+            *reinterpret_cast<uint4*>(row0 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint2*>(row1 + g * 8) = make_uint2(pk[4], pk[5]);
+        }
+        if (g > 0) *reinterpret_cast<uint2*>(row1 + (g - 1) * 8 + 4) = make_uint2(pk[0], pk[1]);
+    }
+}
+
 }  // namespace
+
+extern "C" int bc_stage_augment(const uint8_t* rgb, int64_t n_frames, int src_h, int src_w, const float* table, void* out, int out_dtype, void* stream) {
+    BC_CHECK_ARG(rgb && table && out && n_frames >= 0, "bc_stage_augment: null pointer");
+    BC_CHECK_ARG(src_h >= BC_H && src_w >= BC_W, "bc_stage_augment: source frames %dx%d are smaller than the %dx%d crop", src_h, src_w, BC_H, BC_W);
+    BC_CHECK_ARG(out_dtype == BC_F32 || out_dtype == BC_BF16_TP, "bc_stage_augment: output is BC_F32 planes or BC_BF16_TP planes, got %d", out_dtype);
+    BC_CHECK_ARG((uintptr_t)out % 16 == 0 && (uintptr_t)table % 16 == 0, "bc_stage_augment: out and table must be 16 B aligned");
+    if (n_frames == 0) return BC_OK;
+    const int64_t cap = (int64_t)bc::num_sms() * 16;
+    if (out_dtype == BC_F32) {
+        const int64_t groups = n_frames * BC_H * (BC_W / 4);
+        const int blocks = (int)((groups + 255) / 256 < cap ? (groups + 255) / 256 : cap);
+        stage_aug_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, src_h, src_w, (const AugRow*)table, (float*)out, groups);
+    } else {
+        const int64_t units = n_frames * 3 * TP_NQ * TP_NU;
+        const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
+        stage_aug_tp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, src_h, src_w, (const AugRow*)table, (__nv_bfloat16*)out, units);
+    }
+    BC_CUDA_LAUNCH_CHECK("stage_aug_kernel");
+    return BC_OK;
+}
 
 extern "C" int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream) {
     BC_CHECK_ARG(planes && out_tp && n_planes >= 0, "bc_planes_to_tp: null pointer");

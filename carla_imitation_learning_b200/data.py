@@ -55,6 +55,23 @@ def continous_to_discreet(steer, throttle, brake, steer_threshold: float = 0.05)
     return acc * 3 + s
 
 
+def augment_table(seed: int, n_frames: int, src_hw, out_hw=(256, 256), brightness: float = 0.2, contrast: float = 0.2,
+                  saturation: float = 0.2, mean: float = 0.0, std: float = 1.0) -> np.ndarray:
+    """EXTENSION (no counterpart in the reference): the per-frame table of engine.stage_augmented, reproducible from `seed`
+    on the host (numpy PCG64): (n_frames, 8) f32 rows [crop_y, crop_x, brightness, contrast, saturation, mean, 1/std, 0] --
+    crop offsets uniform over the valid range, jitter factors uniform in [1 - a, 1 + a]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    t = np.zeros((n_frames, 8), np.float32)
+    t[:, 0] = rng.integers(0, src_hw[0] - out_hw[0] + 1, size=n_frames)
+    t[:, 1] = rng.integers(0, src_hw[1] - out_hw[1] + 1, size=n_frames)
+    t[:, 2] = rng.uniform(1 - brightness, 1 + brightness, size=n_frames)
+    t[:, 3] = rng.uniform(1 - contrast, 1 + contrast, size=n_frames)
+    t[:, 4] = rng.uniform(1 - saturation, 1 + saturation, size=n_frames)
+    t[:, 5] = mean
+    t[:, 6] = 1.0 / std
+    return t
+
+
 class SequentialFrames:
     """Iterable of (x, y) batches over one frame sequence, staged on the device.
 

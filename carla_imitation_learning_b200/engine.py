@@ -104,6 +104,33 @@ def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, fra
     return out
 
 
+def stage_augmented(frames_u8: torch.Tensor, table: torch.Tensor, layout: str = "plain", frame_skip: int = 4):
+    """EXTENSION (no counterpart in the reference): crop + colour jitter + normalise fused into the staging pass.
+    frames (n, Hs, Ws, 3) u8 on the device with Hs, Ws >= 256; table (n, 8) f32 = data.augment_table(seed, ...) rows
+    {crop_y, crop_x, brightness, contrast, saturation, mean, 1/std, -}. layout 'plain' -> (n,256,256) f32 gray planes
+    (use sliding_window() on them), 'tp' -> StagedBatch of Toeplitz-ready bf16 planes for precision='bf16'."""
+    _require_cuda(frames_u8, "frames")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3 or not frames_u8.is_contiguous():
+        raise ValueError("frames must be a contiguous (n,Hs,Ws,3) uint8 tensor")
+    n, hs, ws, _ = frames_u8.shape
+    if hs < H or ws < W:
+        raise ValueError(f"source frames {hs}x{ws} are smaller than the {H}x{W} crop")
+    table = table.to(device=frames_u8.device, dtype=torch.float32).contiguous()
+    if tuple(table.shape) != (n, 8):
+        raise ValueError("the augmentation table is (n_frames, 8) float32")
+    if layout == "plain":
+        out = torch.empty((n, H, W), dtype=torch.float32, device=frames_u8.device)
+        code, res = _lib.BC_F32, out
+    elif layout == "tp":
+        out = torch.empty((n, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=frames_u8.device)
+        code, res = _lib.BC_BF16_TP, StagedBatch(out, None, frame_skip)
+    else:
+        raise ValueError("layout is 'plain' or 'tp'")
+    if n:
+        _lib.check(_lib.lib().bc_stage_augment(frames_u8.data_ptr(), n, hs, ws, table.data_ptr(), out.data_ptr(), code, _stream_ptr()), "bc_stage_augment")
+    return res
+
+
 @dataclass
 class StepBuffers:
     """Everything one forward produces and one backward consumes."""

@@ -104,6 +104,13 @@ int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, int out_dtyp
  * plain_bf16 is not NULL, the same gray values also as plain (n,256,256) bf16 planes, in one pass over the frames. */
 int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, int64_t n_frames, void* stream);
 
+/* EXTENSION (no counterpart in the reference; oracle/ext_oracle.py::stage_augmented): crop + colour jitter + normalise inside the
+ * staging pass. rgb (n, src_h, src_w, 3) u8 with src >= 256; table (n, 8) f32 on the device, one row per frame:
+ * {crop_y, crop_x, brightness, contrast, saturation, mean, 1/std, -} (host side: data.augment_table(seed, ...)). Output
+ * BC_F32 = plain (n,256,256) planes, BC_BF16_TP = Toeplitz-ready bf16 planes. Identity parameters reproduce bc_stage_gray to
+ * f32 rounding; the un-augmented kernels stay the bit-exact ones. */
+int bc_stage_augment(const uint8_t* rgb, int64_t n_frames, int src_h, int src_w, const float* table, void* out, int out_dtype, void* stream);
+
 /* plain planes (f32 or bf16; 256x256, rows contiguous, `plane_stride` elements apart) -> BC_BF16_TP planes:
  * how a reference-style (B,4,256,256) batch enters the tcgen05 conv1 (bf16 mode) */
 int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream);
@@ -180,6 +187,34 @@ int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, v
 /* v[0..n) *= *scale_dev (a device scalar), nothing is touched when it is exactly 1: how `loss.backward(gradient=g)` reaches
  * gradients that the fused step has already computed for d loss (imitation.py:38-45 returns the loss, Lightning calls backward) */
 int bc_scale_inplace(float* v, int64_t n, const float* scale_dev, void* stream);
+
+/* ---- EXTENSION (no counterpart in the reference; oracle/ext_oracle.py): command-conditioned branched heads.
+ * G branches of the reference's MLP shape 128 -> 64 -> 32 -> n_out (nets.py:31-33 has ONE such head); sample b is evaluated by
+ * branch command[b] only (branch-select mask). loss_kind 0 = CrossEntropy on labels (imitation.py:43-44), 1 = L1, 2 = MSE on
+ * (B, n_out) regression targets (steer, throttle, brake), mean reduction: pass loss_scale = 1/B (CE) or 1/(B*n_out).
+ * params / grads: G x head_len floats, per branch in the order of the arena's head segment [fc.4 w,b | fc.2 w,b | fc.0 w,b]
+ * (bc_head_branched_layout gives the per-branch offsets in state_dict order 0.weight 0.bias 2.weight 2.bias 4.weight 4.bias).
+ * feat = bc_ctx.act[3] of the conv trunk, gfeat = bc_ctx.ghead for the trunk's backward. mode bit0: loss + dout from
+ * labels/targets; bit1: backward from dout (grads, gfeat); 0 = outputs only. */
+typedef struct {
+    int32_t n_branches, n_out, batch, loss_kind;
+    const float* feat;        /* (B,128)                               */
+    const int64_t* command;   /* (B,) in [0, n_branches)               */
+    const int64_t* labels;    /* (B,) class ids (CE) or NULL           */
+    const float* targets;     /* (B,n_out) (L1/MSE) or NULL            */
+    const float* params;
+    float* grads;
+    float* out;               /* (B,n_out) outputs of the commanded branch */
+    float* dout;              /* (B,n_out) d loss / d out, in/out      */
+    float* gfeat;             /* (B,128)                               */
+    float* loss;              /* [1]                                   */
+    float* partials;          /* bc_head_branched_partials_floats() floats */
+    int32_t* err_flag;        /* 3 = label out of range, 4 = command out of range */
+    float loss_scale;
+} bc_branched;
+int bc_head_branched(const bc_branched* h, int mode, void* stream);
+size_t bc_head_branched_partials_floats(int n_branches, int n_out);
+int64_t bc_head_branched_layout(int n_out, int64_t offsets[6], int64_t sizes[6]);
 
 /* ---- self-test of the tcgen05/TMEM primitives the bf16 conv kernels are built from:
  * D[M,N] f32 = A[M,K] bf16 * B[N,K]^T bf16 (K contiguous). *err_flag is set to 1 if an mbarrier

@@ -31,16 +31,11 @@ def branch_param_names(n_branches: int):
 
 
 def init_branched_params(seed: int, obs_size: int, n_out: int, n_branches: int) -> "OrderedDict[str, torch.Tensor]":
-    """Conv trunk as ConvNet1 (same RNG consumption: example input, conv stack), then G heads 128->64->32->n_out with
-    torch's default Linear init, branch after branch."""
-    torch.manual_seed(seed)
-    torch.randn((1, obs_size, 256, 256))
-    out = OrderedDict()
-    cin = obs_size
-    for (name, k, _s, _p), cout in zip(O.CONV_SPECS, O.CONV_CHANNELS):
-        m = torch.nn.Conv2d(cin, cout, k)
-        out[f"{name}.weight"], out[f"{name}.bias"] = m.weight.detach().clone(), m.bias.detach().clone()
-        cin = cout
+    """ConvNet1's own initialisation first (bc_oracle.init_params: example input, conv stack, the reference's single head --
+    which the branched net keeps in its arena but never uses), then G heads 128->64->32->n_out with torch's default Linear
+    init, branch after branch, from the same RNG stream."""
+    base = O.init_params(seed, obs_size, n_out)
+    out = OrderedDict((k, v) for k, v in base.items() if k.startswith("cnn_base."))
     for g in range(n_branches):
         for i, (fi, fo) in zip((0, 2, 4), ((128, 64), (64, 32), (32, n_out))):
             m = torch.nn.Linear(fi, fo)

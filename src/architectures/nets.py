@@ -158,6 +158,18 @@ class ConvNet1(_Base):
                     p.copy_(state_dict[k])
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
+    @torch.no_grad()
+    def fold_batchnorm(self, layer: int, gamma, beta, running_mean, running_var, eps: float = 1e-5) -> None:
+        """EXTENSION (the reference has no BatchNorm layer): fold an inference-time BatchNorm2d that follows conv `layer`
+        (0..3) into that conv -- W' = W * s, b' = (b - mean) * s + beta, s = gamma / sqrt(var + eps) -- so that the
+        conv+BN+ReLU block the north star names runs as the same fused conv+bias+ReLU+pool kernel (the BN scale/shift IS the
+        kernel's weight/bias epilogue). Specification: oracle/ext_oracle.py::fold_batchnorm."""
+        slot = self.cnn_base[_CONV[layer][0]]
+        dev = slot.weight.device
+        s = gamma.to(dev, torch.float32) / torch.sqrt(running_var.to(dev, torch.float32) + eps)
+        slot.bias.copy_((slot.bias - running_mean.to(dev, torch.float32)) * s + beta.to(dev, torch.float32))
+        slot.weight.mul_(s.view(-1, 1, 1, 1))
+
     # ------------------------------------------------------------------ compute
     def engine(self) -> BCEngine:
         if self._engine is None:
