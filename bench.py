@@ -422,6 +422,17 @@ def run_b200(args):
         breakdown["adam_tick_step" + ("_pack" if wp else "")] = round(_event_ms(lambda: _lib.check(L.bc_adam_tick_step(
             sp.data_ptr(), eng.grads.data_ptr(), sm.data_ptr(), sv.data_ptr(), sst.data_ptr(), sp.numel(),
             scratch_pack.data_ptr() if wp else None, 4, 9, s))) * 1e3, 1)
+    if world > 1 and args.dp == "peer":
+        # the fused exchange + Adam launch, timed live on every rank at once (it really exchanges: all ranks run the same 13 launches,
+        # on the gradients of the last step -- the replicas stay identical, which the check below verifies after it)
+        def xchg():
+            c2 = eng.ctx(bufs)
+            _lib.check(L.bc_reduce_partials(C.byref(c2), 1, s))
+            ts.dp.exchange()
+        ts.dp._bufs = bufs
+        dist.barrier()
+        breakdown["reduce_then_adam_exchange"] = round(_event_ms(xchg) * 1e3, 1)
+        ts.check()
     eng.check_device_errors()
     stage_ms = breakdown["stage_gray"] * 1e-3
     # algorithmic bytes of the staging kernel: u8 RGB in; gray planes out (bf16 mode: Toeplitz-ready bf16 planes)

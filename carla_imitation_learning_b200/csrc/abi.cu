@@ -198,12 +198,12 @@ __global__ void __launch_bounds__(128) adam_exchange_kernel(const ExchangeArgs a
     const AdamK k = adam_consts(a.st, s_sc[1], s_sc[2]);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = a.lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.hi4; i += stride) {
+        float4 pp = a.p[i], mm = a.m[i], vv = a.v[i];               // local state first: in flight under the NVLink round trips
         float4 gg = ld_relaxed_sys_f4(a.peer_grads[0] + par + i);
         for (int r = 1; r < a.world; ++r) {
             const float4 o = ld_relaxed_sys_f4(a.peer_grads[r] + par + i);
             gg.x = __fadd_rn(gg.x, o.x); gg.y = __fadd_rn(gg.y, o.y); gg.z = __fadd_rn(gg.z, o.z); gg.w = __fadd_rn(gg.w, o.w);
         }
-        float4 pp = a.p[i], mm = a.m[i], vv = a.v[i];
         adam4(pp, gg, mm, vv, k);
         a.p[i] = pp; a.m[i] = mm; a.v[i] = vv;
         ctc::pack_updated4(a.pm, 4 * i, &pp.x);
@@ -338,8 +338,9 @@ int bc_adam_step_exchange(float* params, float* exp_avg, float* exp_avg_sq, doub
     a.m = (float4*)exp_avg; a.v = (float4*)exp_avg_sq; a.st = state9; a.sync = peer->sync_state;
     a.lo4 = lo / 4; a.hi4 = hi / 4; a.arena4 = n / 4;
     a.rank = peer->rank; a.world = peer->world; a.bucket = bucket; a.publish = publish; a.err = peer->err_flag;
-    int blocks = (int)((a.hi4 - a.lo4 + 127) / 128);
-    if (blocks > 128) blocks = 128;                            // every CTA spins on the flags: all of them must be resident, next to conv1's wgrad
+    int blocks = (int)((a.hi4 - a.lo4 + 127) / 128);           // one float4 per thread: a single NVLink round trip per thread
+    const int cap = 2 * bc::num_sms();                         // every CTA spins on the flags: all of them must be resident
+    if (blocks > cap) blocks = cap;
     bc::launch_pdl(adam_exchange_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("adam_exchange_kernel");
     return BC_OK;
