@@ -602,6 +602,115 @@ def run_infer(args):
         "gpu_launches": 7 * reps * 13, "clocks": clocks}), flush=True)
 
 
+def run_stacked12(args):
+    """BASELINE configs[3]: the channel-stacked multi-camera variant -- obs_size 12 = 3 cameras x 4 frames, 256x256 (what
+    nets.py:14 hard-codes), exact-f32 kernels (the tcgen05 conv1 exists for obs_size 4), one B200 per rank, weak scaling.
+    The three cameras' frames are interleaved frame by frame in the u8 input, so a sample is a zero-copy window of 12
+    consecutive gray planes advancing by 3 (engine.sliding_window(step=3)); stage -> forward -> backward -> Adam as one CUDA graph."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from carla_imitation_learning_b200 import FusedAdam, _lib, sliding_window, stage_gray
+    from src.architectures.nets import ConvNet1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.build()
+    B = args.batch if args.batch != 256 else 64
+    torch.manual_seed(12345)
+    net = ConvNet1({"obs_size": 12, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    opt = FusedAdam(list(net.parameters()), lr=1e-3)
+    nfr = 3 * (B + 3)                                     # 3 cameras x (B + 3) frames: sample b = frames b..b+3 of every camera
+    rng = np.random.Generator(np.random.PCG64(7 + rank))
+    frames = [torch.from_numpy(rng.integers(0, 256, size=(nfr, 256, 256, 3), dtype=np.uint8)).to(dev) for _ in range(2)]
+    labels = torch.from_numpy(rng.integers(0, 9, size=B)).to(dev)
+    gray = torch.empty((nfr, 256, 256), dtype=torch.float32, device=dev)
+    x = sliding_window(gray, frame_skip=12, step=3)
+    assert x.shape[0] == B
+    bufs = eng.alloc(B, x, labels, True)
+    opt.prepare()
+    xchg = None
+    if world > 1:
+        from carla_imitation_learning_b200.parallel import PeerExchangeStep
+        xchg = PeerExchangeStep(eng, opt)
+
+    def enqueue(fr):
+        stage_gray(fr, out=gray)
+        if xchg is not None:
+            xchg(bufs)
+        else:
+            eng.enqueue_train(bufs)
+            opt.step_flat(eng.grads)
+    for i in range(3):
+        enqueue(frames[i & 1])
+    torch.cuda.synchronize()
+    graphs = []
+    for fr in frames:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            enqueue(fr)
+        graphs.append(g)
+
+    def step(i):
+        opt.prepare()
+        graphs[i & 1].replay()
+        if xchg is not None:
+            xchg.peer.host_epoch += 1
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    loss = float(bufs.loss)
+    eng.check_device_errors()
+    if xchg is not None:
+        xchg.peer.check()
+    if not (loss == loss and 0.0 < loss < 20.0):
+        raise RuntimeError(f"non-finite loss {loss}")
+    if rank == 0:
+        time.sleep(0.25)
+        sampler.window(t0, t1)
+        clocks = sampler.stop()
+        peaks = load_peaks()
+        flops = 327.5e6                                   # SURVEY 8(d): train FLOPs per frame at 12 channels, 256x256
+        value = B * world * args.steps / (ms * 1e-3)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ConvNet1 BC train step, channel-stacked variant (BASELINE configs[3]): obs 12 = 3 cameras x 4 frames at 256x256, "
+                                   f"batch {B}/GPU, exact-f32 FFMA kernels, u8 RGB frames staged on the device", "global_batch": B * world,
+                       "parallelism": f"dp{world}", "cuda_graph": True, "final_loss": loss,
+                       "l2": "inputs alternate over 2 device buffers of %d MB" % (nfr * FRAME_BYTES // 1000000)},
+            "roofline": {"kernel": "whole step (f32 FFMA kernels)", "bound": "tensor", "achieved": flops * value / 1e12, "peak": peaks["tf_sust"],
+                         "unit": "TFLOP/s", "frac": flops * value / 1e12 / peaks["tf_sust"], "traffic": None,
+                         "note": "the exact-f32 path runs on CUDA cores; the fraction is against the bf16 tensor peak for comparability"},
+            "gpu_launches": 15 * args.steps, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -609,7 +718,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"], help="train = BASELINE configs[1]/[2]; infer = configs[4] batch sweep")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "stacked12"],
+                    help="train = BASELINE configs[1]/[2]; infer = configs[4] batch sweep; stacked12 = configs[3] (12 channels, exact-f32 kernels)")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="N>1 gradient exchange: fused peer-memory Adam, or NCCL buckets")
@@ -624,6 +734,8 @@ def main():
         run_reference(args)
     elif args.workload == "infer":
         run_infer(args)
+    elif args.workload == "stacked12":
+        run_stacked12(args)
     else:
         run_b200(args)
 

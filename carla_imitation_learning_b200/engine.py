@@ -46,16 +46,19 @@ def stage_gray(frames_u8: torch.Tensor, dtype: torch.dtype = torch.float32, out:
     return out
 
 
-def sliding_window(gray: torch.Tensor, frame_skip: int = 4) -> torch.Tensor:
-    """Zero-copy (n-frame_skip, frame_skip, H, W) view: sample i = planes [i, i+frame_skip).
+def sliding_window(gray: torch.Tensor, frame_skip: int = 4, step: int = 1) -> torch.Tensor:
+    """Zero-copy ((n-frame_skip)/step, frame_skip, H, W) view: sample i = planes [i*step, i*step+frame_skip).
 
     The reference's loader is shuffle=False (imitation_dataset.py:270-274) with
     files[index-frame_skip:index], index=i+4 (:117,:125), so consecutive samples share 3 of 4
-    planes; the view hands that overlap to the conv1 kernels without materialising it."""
+    planes; the view hands that overlap to the conv1 kernels without materialising it.
+    step > 1 is the multi-camera stacking of BASELINE configs[3]: with the planes of `step` cameras interleaved frame by
+    frame (plane = t*step + cam), sample i = window of frame_skip = step*frames planes starting at plane i*step, i.e.
+    channels ordered (frame, camera)."""
     n, h, w = gray.shape
     if n <= frame_skip:
         raise ValueError(f"need more than {frame_skip} frames, got {n}")
-    return gray.as_strided((n - frame_skip, frame_skip, h, w), (h * w, h * w, w, 1))
+    return gray.as_strided(((n - frame_skip) // step, frame_skip, h, w), (step * h * w, h * w, w, 1))
 
 
 class StagedBatch:

@@ -475,6 +475,31 @@ def test_stacked_12_channel_variant_matches_oracle():
         assert _relerr(g, ref[k]) <= REL_F32, k
 
 
+def test_stacked_camera_window_view_equals_materialised_batch():
+    """configs[3] input pipeline: 3 cameras interleaved frame by frame -> sliding_window(frame_skip=12, step=3) is a zero-copy
+    (B,12,256,256) batch; the step on the view == the step on the materialised copy, bit for bit."""
+    from carla_imitation_learning_b200 import sliding_window, stage_gray
+    from src.architectures.nets import ConvNet1
+    dev = _dev()
+    torch.manual_seed(7)
+    net = ConvNet1({"obs_size": 12, "n_actions": 9}).to(dev)
+    eng = net.engine()
+    B = 5
+    rng = np.random.Generator(np.random.PCG64(2))
+    frames = torch.from_numpy(rng.integers(0, 256, size=(3 * (B + 3), 256, 256, 3), dtype=np.uint8)).to(dev)
+    y = torch.from_numpy(rng.integers(0, 9, size=B)).to(dev)
+    x = sliding_window(stage_gray(frames), frame_skip=12, step=3)
+    assert tuple(x.shape) == (B, 12, 256, 256) and x.stride(0) == 3 * 65536 and x.stride(1) == 65536
+    b1 = eng.train_forward_backward(x, y)
+    g1 = eng.grads.clone()
+    b2 = eng.train_forward_backward(x.contiguous(), y)
+    torch.cuda.synchronize()
+    assert torch.equal(b1.logits, b2.logits) and torch.equal(g1, eng.grads)
+    # sample 1, channel (frame 2, camera 1) is plane 3*1 + 3*2 + 1
+    gray = stage_gray(frames)
+    assert torch.equal(x[1, 7], gray[3 + 7])
+
+
 def _peer_exchange_world1(_proc, out_path, port):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
