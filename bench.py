@@ -625,7 +625,7 @@ def run_stacked12(args):
     net = ConvNet1({"obs_size": 12, "n_actions": 9}).to(dev)
     eng = net.engine()
     opt = FusedAdam(list(net.parameters()), lr=1e-3)
-    nfr = 3 * (B + 3)                                     # 3 cameras x (B + 3) frames: sample b = frames b..b+3 of every camera
+    nfr = 3 * (B + 4)                                     # 3 cameras x (B + 4) frames: sample b = frames b..b+3 of every camera (+ the frame that carries its label)
     rng = np.random.Generator(np.random.PCG64(7 + rank))
     frames = [torch.from_numpy(rng.integers(0, 256, size=(nfr, 256, 256, 3), dtype=np.uint8)).to(dev) for _ in range(2)]
     labels = torch.from_numpy(rng.integers(0, 9, size=B)).to(dev)

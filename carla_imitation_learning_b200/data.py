@@ -98,6 +98,7 @@ class SequentialFrames:
         self.batch_size, self.frame_skip, self.dtype = int(batch_size), int(frame_skip), dtype
         self.n_samples = len(frames_u8) - frame_skip
         self._copy_stream = torch.cuda.Stream(self.device)
+        self._staged = [None, None]
         n, h, w, _ = frames_u8.shape
         rows = self.batch_size + frame_skip
         self._raw = [torch.empty((rows, h, w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
@@ -118,19 +119,30 @@ class SequentialFrames:
         return (self.n_samples + self.batch_size - 1) // self.batch_size
 
     def _produce(self, k: int, slot: int) -> torch.cuda.Event:
+        """H2D of chunk k's frames and labels into raw slot `slot` on the copy stream (nothing else runs there: uploads go
+        back to back; the staging kernel runs on the consumer's stream right before the batch is handed out)."""
         lo = k * self.batch_size
         hi = min(lo + self.batch_size, self.n_samples) + self.frame_skip
         with torch.cuda.stream(self._copy_stream):
+            if self._staged[slot] is not None:
+                self._copy_stream.wait_event(self._staged[slot])       # the staging pass that last read this raw slot
             self._raw[slot][:hi - lo].copy_(self.frames[lo:hi], non_blocking=True)
             nb = hi - lo - self.frame_skip
             self._lab[slot][:nb].copy_(self.labels[lo + self.frame_skip: lo + self.frame_skip + nb], non_blocking=True)
-            if self.layout == "tp":
-                stage_frames(self._raw[slot][:hi - lo], out=StagedBatch(self._gray[slot][:hi - lo], None, self.frame_skip))
-            else:
-                stage_gray(self._raw[slot][:hi - lo], out=self._gray[slot][:hi - lo])
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return ev
+
+    def _stage(self, k: int, slot: int, cur) -> None:
+        lo = k * self.batch_size
+        hi = min(lo + self.batch_size, self.n_samples) + self.frame_skip
+        if self.layout == "tp":
+            stage_frames(self._raw[slot][:hi - lo], out=StagedBatch(self._gray[slot][:hi - lo], None, self.frame_skip))
+        else:
+            stage_gray(self._raw[slot][:hi - lo], out=self._gray[slot][:hi - lo])
+        if self._staged[slot] is None:
+            self._staged[slot] = torch.cuda.Event()
+        self._staged[slot].record(cur)
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         return self._batches(loop=False)
@@ -142,17 +154,17 @@ class SequentialFrames:
 
     def _batches(self, loop: bool) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         nb = len(self)
+        self._staged = [None, None]
         cur = torch.cuda.current_stream(self.device)
-        self._copy_stream.wait_stream(cur)
+        self._copy_stream.wait_stream(cur)      # whatever still reads the slots from a previous pass
         ev = self._produce(0, 0)
         n = 0                                   # batches produced so far: slot = n & 1
         while True:
             k, slot = n % nb, n & 1
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
+            self._stage(k, slot, cur)           # on the consumer's stream: ordered before the step that reads the planes
             if loop or k + 1 < nb:
-                # the other slot was consumed one iteration ago on the compute stream
-                self._copy_stream.wait_stream(cur)
                 ev = self._produce((k + 1) % nb, slot ^ 1)
             lo = k * self.batch_size
             b = min(self.batch_size, self.n_samples - lo)

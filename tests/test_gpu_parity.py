@@ -486,7 +486,7 @@ def test_stacked_camera_window_view_equals_materialised_batch():
     eng = net.engine()
     B = 5
     rng = np.random.Generator(np.random.PCG64(2))
-    frames = torch.from_numpy(rng.integers(0, 256, size=(3 * (B + 3), 256, 256, 3), dtype=np.uint8)).to(dev)
+    frames = torch.from_numpy(rng.integers(0, 256, size=(3 * (B + 4), 256, 256, 3), dtype=np.uint8)).to(dev)
     y = torch.from_numpy(rng.integers(0, 9, size=B)).to(dev)
     x = sliding_window(stage_gray(frames), frame_skip=12, step=3)
     assert tuple(x.shape) == (B, 12, 256, 256) and x.stride(0) == 3 * 65536 and x.stride(1) == 65536

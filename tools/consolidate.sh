@@ -1,11 +1,18 @@
 #!/bin/bash
-# one GPU call: tests, bench (both arms), launch list and the full capture of the roofline kernel
+# one GPU call: pytest -m gpu, bench.py (both arms + the other workloads), the ncu launch list and --set full captures that profiles/ holds
+# usage: bash tools/consolidate.sh r2x
 set -x
-BC_TEST_OUT=gpurun_out python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-python bench.py > gpurun_out/bench_r1g.json 2> gpurun_out/bench_r1g.err; tail -c 600 gpurun_out/bench_r1e.json
-python bench.py --impl reference --steps 30 --warmup 3 > gpurun_out/bench_r1g_ref.json 2>/dev/null; tail -c 300 gpurun_out/bench_r1e_ref.json
-python bench.py --no-cpu --no-graph --steps 2 --warmup 3 > gpurun_out/plain_ll.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 40 --csv --log-file gpurun_out/r1g_launches_bf16path.csv python bench.py --no-cpu --no-graph --steps 2 --warmup 3 > gpurun_out/ncu_ll.log 2>&1
-python bench.py --no-cpu --no-graph --steps 3 --warmup 3 > gpurun_out/plain_full.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'conv1_tp_kernel|conv1_wgrad_tp_kernel|stage_gray_tp_kernel|sw_wgrad_kernel|sw_dgrad_kernel' -s 21 -c 7 -o gpurun_out/prof_r1g python bench.py --no-cpu --no-graph --steps 3 --warmup 3 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log | cut -c1-200
+T=${1:-r2x}
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+BC_TEST_OUT=gpurun_out timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -rf > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${T}_pytest_gpu.log | cut -c1-300
+timeout 900 python bench.py > gpurun_out/${T}_bench_bf16path.json 2> gpurun_out/${T}_bench.err; tail -c 600 gpurun_out/${T}_bench_bf16path.json; tail -3 gpurun_out/${T}_bench.err
+timeout 600 python bench.py --impl reference --steps 30 --warmup 3 > gpurun_out/${T}_bench_reference_cpu.json 2>/dev/null; tail -c 400 gpurun_out/${T}_bench_reference_cpu.json
+timeout 600 python bench.py --workload infer --steps 200 > gpurun_out/${T}_bench_infer_sweep.json 2>/dev/null; tail -c 300 gpurun_out/${T}_bench_infer_sweep.json
+timeout 600 python bench.py --workload stacked12 --steps 50 --warmup 5 > gpurun_out/${T}_bench_stacked12.json 2> gpurun_out/${T}_stacked12.err; tail -c 600 gpurun_out/${T}_bench_stacked12.json; tail -3 gpurun_out/${T}_stacked12.err
+timeout 600 python bench.py --mode fp32 --steps 50 --no-cpu --no-module --e2e-api engine > gpurun_out/${T}_bench_fp32path.json 2>/dev/null; tail -c 300 gpurun_out/${T}_bench_fp32path.json
+python bench.py --no-cpu --no-graph --no-module --e2e-api engine --steps 2 --warmup 3 > gpurun_out/${T}_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 75 -c 30 --csv --log-file gpurun_out/${T}_launches_bf16path.csv python bench.py --no-cpu --no-graph --no-module --e2e-api engine --steps 2 --warmup 3 > gpurun_out/${T}_ncu_ll.log 2>&1
+python bench.py --no-cpu --no-graph --no-module --e2e-api engine --steps 3 --warmup 3 > gpurun_out/${T}_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'conv1_tp_kernel|conv1_wgrad3_kernel|stage_gray_tp_kernel|adam_tick_step_kernel|head_kernel|reduce_partials_kernel' -s 14 -c 6 -o gpurun_out/${T}_full python bench.py --no-cpu --no-graph --no-module --e2e-api engine --steps 3 --warmup 3 > gpurun_out/${T}_ncu_full.log 2>&1
+tail -2 gpurun_out/${T}_ncu_full.log | cut -c1-200
