@@ -9,6 +9,7 @@
 
 int bc_conv1_tc_launch(const bc_ctx* c, void* stream);            // conv1_tc.cu
 int bc_conv1_wgrad_tc_launch(const bc_ctx* c, void* stream);
+int bc_conv1_fwd4_launch(const bc_ctx* c, void* stream);           // conv1_fwd4.cu (swapped-role forward; args checked by bc_conv1_tc_launch)
 int bc_conv1_wgrad_tp_grid(const bc_ctx* c);   // CTAs = partial-sum slots the tcgen05 conv1 wgrad writes
 int bc_conv_tc_launch(const bc_ctx* c, int layer, void* stream);  // conv_tc.cu (layers 1..3)
 int bc_conv_tc_pack(const bc_ctx* c, void* stream);

@@ -669,6 +669,10 @@ static int conv1_tp_launch(const bc_ctx* c, void* stream) {
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05, TP): smem opt-in %d B failed: %s", c1tp::SMEM_BYTES, cudaGetErrorString(e));
         configured = true;
     }
+    // BC_C1FW_GEN=4 selects the swapped-role kernel (conv1_fwd4.cu: same results, register-local pooling; measured 31 us against
+    // 28 us here because its M=128 x N=128 MMAs fetch 8 KB of operands per 64 cycles = the whole shared-memory bandwidth)
+    static const bool gen4 = getenv("BC_C1FW_GEN") && atoi(getenv("BC_C1FW_GEN")) == 4;
+    if (gen4) return bc_conv1_fwd4_launch(c, stream);
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
     const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();

@@ -14,7 +14,8 @@ struct PackArgs { const float* w1; const float* w2; const float* w3; const float
 
 constexpr int kNW2 = L2::COUT * L2::CIN * L2::KS * L2::KS, kNW3 = L3::COUT * L3::CIN * L3::KS * L3::KS, kNW4 = L4::COUT * L4::CIN * L4::KS * L4::KS;
 constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz image, element-ordered (it has structural zeros)
-constexpr int kPackElems = kNC1 + kNW2 + kNW3 + kNW4;
+constexpr int kNC1V4 = kC1V4Blocks * 1024;                 // the swapped-role image of conv1 (conv1_fwd4.cu), element-ordered as well
+constexpr int kPackElems = kNC1 + kNC1V4 + kNW2 + kNW3 + kNW4;
 // all seven operand images (conv1 Toeplitz, conv2-4 forward + dgrad) in one launch
 __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
     bc::pdl_wait();
@@ -30,6 +31,18 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
         return;
     }
     i -= kNC1;
+    if (i < kNC1V4) {
+        // block (ky, ci) = 1 + 5 ky + (3 - ci), zero blocks at 5 ky; row = co*4 + j; Wt[(co,j)][p] = W[co][ci][ky][p - 3j] or 0
+        const int k = i & 15, r = (i >> 4) & 63, blk = i >> 10;
+        float v = 0.f;
+        if (blk % 5 != 0) {
+            const int ky = (blk - 1) / 5, ci = 3 - (blk - 1) % 5, co = r >> 2, j = r & 3, kx = k - 3 * j;
+            if (kx >= 0 && kx < 7) v = a.w1[((co * 4 + ci) * 7 + ky) * 7 + kx];
+        }
+        reinterpret_cast<__nv_bfloat16*>(a.base + kPackC1V4)[(size_t)blk * 1024 + op_off(r, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
+        return;
+    }
+    i -= kNC1V4;
     if (i < kNW2) { pack_src_elem<L2>(a.w2[i], (__nv_bfloat16*)(a.base + o2), (__nv_bfloat16*)(a.base + d2), i); return; } i -= kNW2;
     if (i < kNW3) { pack_src_elem<L3>(a.w3[i], (__nv_bfloat16*)(a.base + o3), (__nv_bfloat16*)(a.base + d3), i); return; } i -= kNW3;
     if (i < kNW4) pack_src_elem<L4>(a.w4[i], (__nv_bfloat16*)(a.base + o4), (__nv_bfloat16*)(a.base + d4), i);

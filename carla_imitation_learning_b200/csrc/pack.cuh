@@ -32,7 +32,13 @@ constexpr size_t kPackOff1 = 0, kPackOff2 = 57344;
 constexpr size_t kPackOff3 = kPackOff2 + L2::B_BYTES, kPackOff4 = kPackOff3 + L3::B_BYTES;
 constexpr size_t kPackD2 = kPackOff4 + L4::B_BYTES;
 constexpr size_t kPackD3 = kPackD2 + DCfg<L2>::B_BYTES, kPackD4 = kPackD3 + DCfg<L3>::B_BYTES;
-constexpr size_t kPackTotal = kPackD4 + DCfg<L4>::B_BYTES;
+// conv1's Toeplitz image for the swapped-role forward (conv1_fwd4.cu): 36 blocks of 64 rows (co*4 + j) x 16 k, ordered
+// [Z][ky=0: ci 3,2,1,0][Z][ky=1: ...]...[Z] -- descending channel with zero blocks between the kernel rows, so that the 128 rows
+// [W(ci) ; W(ci-1)] of two consecutive window samples are one contiguous slice for every ci = 0..4
+constexpr int kC1V4Blocks = 36, kC1V4Bytes = kC1V4Blocks * 2048;
+constexpr size_t kPackC1V4 = kPackD4 + DCfg<L4>::B_BYTES;
+constexpr size_t kPackTotal = kPackC1V4 + kC1V4Bytes;
+__host__ __device__ constexpr int c1v4_block(int ky, int ci) { return 1 + 5 * ky + (3 - ci); }
 constexpr int kNC1W = 16 * 4 * 7 * 7;                      // conv1 weights (obs_size 4)
 
 // One source weight W[co][ci][tap] of conv2-4 -> its position in the forward image and in the dgrad image.
@@ -55,14 +61,17 @@ __device__ __forceinline__ void pack_src_elem(float w, __nv_bfloat16* __restrict
 // One conv1 weight W[co][ci][ky][kx] (obs_size 4) -> its up to four copies in the Toeplitz image (conv1_tc.cu):
 // step (ky,ci): 64 rows n = j*16+co x 16 k, Wt[(j,co)][p] = W[..][p - 3j]; the other entries are structural zeros
 // written once by pack_all_kernel.
-__device__ __forceinline__ void pack_conv1_elem(float w, __nv_bfloat16* __restrict__ img, int i) {
+__device__ __forceinline__ void pack_conv1_elem(float w, __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ img4, int i) {
     const int kx = i % 7, ky = (i / 7) % 7, ci = (i / 49) & 3, co = i / 196;
     const __nv_bfloat16 v = __float2bfloat16_rn(w);
-    const int st = ky * 4 + ci;
+    const int st = ky * 4 + ci, blk = c1v4_block(ky, ci);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int k = kx + 3 * j, n = j * 16 + co;
-        if (k < 16) img[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = v;
+        if (k < 16) {
+            img[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = v;
+            img4[(size_t)blk * 1024 + op_off(co * 4 + j, k >> 3) / 2 + (k & 7)] = v;      // swapped-role image: row = co*4 + j
+        }
     }
 }
 
@@ -81,7 +90,7 @@ __device__ __forceinline__ void pack_updated4(const PackMap& pm, int64_t idx, co
     if (idx >= pm.w1) {
         const int i = (int)(idx - pm.w1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (i + k < kNC1W) pack_conv1_elem(v[k], (__nv_bfloat16*)pm.base, i + k);
+        for (int k = 0; k < 4; ++k) if (i + k < kNC1W) pack_conv1_elem(v[k], (__nv_bfloat16*)pm.base, (__nv_bfloat16*)(pm.base + kPackC1V4), i + k);
     } else if (idx >= pm.w2) {
         const int i = (int)(idx - pm.w2);
 #pragma unroll
