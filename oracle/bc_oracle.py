@@ -164,6 +164,12 @@ def cross_entropy(logits: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return (lse - logits.gather(1, y[:, None]).squeeze(1)).mean()
 
 
+def aux_criterion(params, x, y2, dtype=torch.float32):
+    """ImitationAux's lossCriterion (/root/reference/src/models/imitation.py:11-24 with 109-117): of the three terms only
+    l3 = cross_entropy(output[2], y[:, 1]) is live -- the action logits against column 1 of the (B, 2) labels."""
+    return loss_and_grads(params, x, y2[:, 1], dtype=dtype)
+
+
 def loss_and_grads(params, x, y, dtype=torch.float32):
     """Loss and d loss / d param for every tensor, by autograd on the restated forward."""
     leaf = OrderedDict((k, v.detach().to(dtype).clone().requires_grad_(True)) for k, v in params.items())

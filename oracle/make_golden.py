@@ -182,11 +182,51 @@ def oracle_curve_f64(B, steps, data_seed, path):
     np.save(path, np.asarray(out, np.float64))
 
 
+def golden_aux(B, data_seed, path):
+    """ImitationAux + lossCriterion of the UNMODIFIED reference (imitation.py:11-24, 94-159) on a net whose third output is the
+    reference ConvNet1's logits (CNNAuxNet is not shipped): two-column labels [traffic light, action], loss = CE(out[2], y[:, 1]).
+    Also records that the reference's ConvNetRawSegment cannot be constructed (nets.py:44)."""
+    from src.models.imitation import ImitationAux as RefAux  # noqa: E402 (reference)
+    from src.architectures.nets import ConvNetRawSegment as RefRaw  # noqa: E402 (reference)
+
+    class AuxNet(torch.nn.Module):
+        def __init__(self, base):
+            super().__init__()
+            self.base = base
+
+        def forward(self, x):
+            return None, None, self.base(x)
+
+    frames, labels = O.synth_frames(data_seed, B + 4)
+    x_np, y_np = O.sequential_samples(frames, labels)
+    rng = np.random.Generator(np.random.PCG64(data_seed + 99))
+    y2 = np.stack([rng.integers(0, 3, size=B), y_np], axis=1).astype(np.int64)       # column 0: traffic-light status (unused by the loss)
+    x, y = torch.from_numpy(x_np), torch.from_numpy(y2)
+    net, _ = build_ref()
+    model = RefAux(HP, AuxNet(net), {})
+    loss = model.training_step((x, y), 0)
+    loss.backward()
+    grads = flat({k: p.grad for k, p in net.named_parameters()})
+    val = model.validation_step((x, y), 0)
+    try:
+        RefRaw(HP)
+        raw_error = ""
+    except Exception as e:  # noqa: BLE001
+        raw_error = type(e).__name__
+    np.savez_compressed(path, B=B, data_seed=data_seed, y2=y2, loss=float(loss.detach()), val_loss=float(val), grads=grads,
+                        logged_val_loss=("val_loss" in model.logged), raw_segment_error=raw_error)
+    print(path, "aux loss", float(loss), "ConvNetRawSegment(hp) raises", raw_error)
+
+
 if __name__ == "__main__":
     g = os.path.join(ROOT, "tests", "golden")
     os.makedirs(g, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if "--aux-only" in sys.argv:
+        golden_aux(4, 0, os.path.join(g, "ref_aux_step_b4.npz"))
+        sys.exit(0)
     golden_step(4, 0, os.path.join(g, "ref_step_b4.npz"))
+    golden_aux(4, 0, os.path.join(g, "ref_aux_step_b4.npz"))
     golden_step(1, 1, os.path.join(g, "ref_step_b1.npz"))
     golden_labels(os.path.join(g, "ref_labels.npz"))
     golden_gray(os.path.join(g, "ref_gray.npz"))

@@ -207,3 +207,16 @@ class ConvNet1(_Base):
         """Greedy action ids = argmax over logits (src/data/stat.py:41, imitation.py:177)."""
         eng = self.engine()
         return eng.argmax(eng.forward(self._to_device(x)).logits)
+
+
+class ConvNetRawSegment(_Base):
+    """The two-stream variant of /root/reference/src/architectures/nets.py:42-78. In the reference its constructor starts with
+    `super(ConvNet1, self).__init__()` (nets.py:44) -- `self` is not a ConvNet1, so EVERY construction raises TypeError before
+    a single layer exists; no caller, config or checkpoint in the reference uses the class. The drop-in keeps that behaviour
+    (same exception type at the same point) instead of inventing semantics the reference never had; the kernels of the hot
+    path are built for ConvNet1's geometry (out of scope)."""
+
+    def __init__(self, hparams):
+        raise TypeError("super(type, obj): obj must be an instance or subtype of type "
+                        "[/root/reference/src/architectures/nets.py:44 calls super(ConvNet1, self).__init__() inside ConvNetRawSegment: "
+                        "the class cannot be constructed in the reference either]")

@@ -26,6 +26,21 @@ except Exception:  # pragma: no cover - Lightning is not installed in the build 
 from carla_imitation_learning_b200.optim import FusedAdam
 
 
+def lossCriterion(obj, inp, out):
+    """The criterion of ImitationAux (/root/reference/src/models/imitation.py:11-24; name kept). In the reference every term but the
+    last is commented out: loss = l3 = cross_entropy(inp[2], out[1][:, 1]) -- the autopilot-action logits (third output of the
+    auxiliary net) against column 1 of the two-column label tensor. `out` is the module's `target = [x, y]`, so the fused kernels
+    can compute exactly that from `out` alone: one launch chain for forward, CrossEntropy and (on backward) the gradients;
+    `inp` (the separate forward the reference runs first) is not needed and may be None."""
+    x, y = out
+    if y.dim() != 2 or y.shape[1] < 2:
+        raise IndexError("ImitationAux labels are (B, 2): [traffic-light status, autopilot action] (imitation.py:13-14)")
+    fused = getattr(obj.net, "loss", None)
+    if fused is None:
+        raise TypeError("ImitationAux drives the B200 kernels through net.loss(x, y): pass a src.architectures.nets.ConvNet1")
+    return fused(x, y[:, 1].contiguous())
+
+
 class Imitation(_Base):
     def __init__(self, hparams, net, data_loader):
         super().__init__()
@@ -124,3 +139,26 @@ class Imitation(_Base):
             model = cls(hparams, net, data_loader)
             load_checkpoint_into(model, checkpoint_path, strict=strict)
             return model
+
+
+class ImitationAux(Imitation):
+    """The auxiliary-task module of /root/reference/src/models/imitation.py:94-159, hook for hook: `criterion = lossCriterion`,
+    training_step / validation_step build `target = [x, y]` and return `criterion(self, output, target)`, validation does NOT
+    log 'val_loss' (the reference's ImitationAux does not), epoch hooks / dataloaders / optimiser / scale_image as Imitation.
+    The reference's lossCriterion keeps only the action term, so any ConvNet1 serves as `net` here: its logits ARE the third
+    output the reference indexes (the image-reconstruction and traffic-light heads belong to CNNAuxNet, which the reference
+    does not ship -- SURVEY 0.2). The separate `self.forward(x)` the reference runs before the criterion is skipped: the fused
+    loss recomputes the forward inside the same launch chain."""
+
+    def __init__(self, hparams, net, data_loader):
+        super().__init__(hparams, net, data_loader)
+        self.criterion = lossCriterion
+
+    def training_step(self, batch, batch_idx):
+        x, y = batch
+        return self.criterion(self, None, [x, y])
+
+    def validation_step(self, batch, batch_idx):
+        x, y = batch
+        with torch.no_grad():
+            return self.criterion(self, None, [x, y])

@@ -130,3 +130,22 @@ def test_product_code_never_imports_the_oracle():
                 if f.endswith(".py") and re.search(r"^\s*(from|import)\s+oracle\b", open(os.path.join(dp, f)).read(), re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_imitation_aux_and_raw_segment_mirror_the_reference_contract():
+    """ImitationAux (imitation.py:94-159): criterion attribute = lossCriterion, Imitation's hooks; ConvNetRawSegment (nets.py:42-78)
+    raises TypeError on construction exactly like the reference's class does (recorded in ref_aux_step_b4.npz)."""
+    from src.architectures.nets import ConvNet1, ConvNetRawSegment
+    from src.models import imitation as M
+    hp = {"obs_size": 4, "n_actions": 9}
+    model = M.ImitationAux(hp, ConvNet1(hp), {"train_dataloader": 1, "val_dataloader": 2, "test_dataloader": 3})
+    assert model.criterion is M.lossCriterion
+    assert (model.train_dataloader(), model.val_dataloader(), model.test_dataloader()) == (1, 2, 3)
+    for hook in ("forward", "training_step", "validation_step", "training_epoch_end", "validation_epoch_end", "configure_optimizers", "scale_image"):
+        assert callable(getattr(model, hook))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_aux_step_b4.npz"))
+    with pytest.raises(TypeError):
+        ConvNetRawSegment(hp)
+    assert str(g["raw_segment_error"]) == "TypeError"
+    with pytest.raises(IndexError):       # one-column labels: the reference indexes y[:, 1]
+        M.lossCriterion(model, None, [torch.zeros(2, 4, 256, 256), torch.zeros(2, dtype=torch.int64)])

@@ -150,3 +150,17 @@ def test_oracle_f64_curve_sits_inside_the_reference_reproducibility_envelope(gol
         check_curve(c, golden_dir, tol=1e-2)
     with pytest.raises(AssertionError):
         check_curve(np.full(1000, 2.1972), golden_dir, tol=2e-2)
+
+
+def test_oracle_aux_criterion_matches_the_reference_imitation_aux(golden_dir):
+    """ImitationAux + lossCriterion of the unmodified reference (golden ref_aux_step_b4.npz, oracle/make_golden.py::golden_aux)."""
+    g = np.load(os.path.join(golden_dir, "ref_aux_step_b4.npz"))
+    frames, labels = O.synth_frames(int(g["data_seed"]), int(g["B"]) + 4)
+    x, _y = O.sequential_samples(frames, labels)
+    P = O.init_params(12345)
+    loss, _logits, grads = O.aux_criterion(P, torch.from_numpy(x), torch.from_numpy(g["y2"]))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    got = np.concatenate([grads[k].detach().reshape(-1).numpy() for k in O.PARAM_ORDER])
+    assert np.abs(got - g["grads"]).max() <= 1e-6 * np.abs(g["grads"]).max()
+    assert not bool(g["logged_val_loss"])                   # the reference's ImitationAux.validation_step does not log
+    assert str(g["raw_segment_error"]) == "TypeError"       # ConvNetRawSegment(hparams) cannot be constructed (nets.py:44)
