@@ -604,14 +604,17 @@ def run_infer(args):
 
 def run_stacked12(args):
     """BASELINE configs[3]: the channel-stacked multi-camera variant -- obs_size 12 = 3 cameras x 4 frames, 256x256 (what
-    nets.py:14 hard-codes), exact-f32 kernels (the tcgen05 conv1 exists for obs_size 4), one B200 per rank, weak scaling.
+    nets.py:14 hard-codes), one B200 per rank, weak scaling. `--mode bf16` (default): every convolution on tcgen05, conv1 as three
+    4-frame camera streams accumulated into one result (csrc/conv1_tc.cu); `--mode fp32`: the exact FFMA kernels.
     The three cameras' frames are interleaved frame by frame in the u8 input, so a sample is a zero-copy window of 12
-    consecutive gray planes advancing by 3 (engine.sliding_window(step=3)); stage -> forward -> backward -> Adam as one CUDA graph."""
+    consecutive gray planes advancing by 3 (stage_frames(frame_skip=12, step=3) / sliding_window(step=3)); stage -> forward ->
+    backward -> Adam as one CUDA graph."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from carla_imitation_learning_b200 import FusedAdam, _lib, sliding_window, stage_gray
+    from carla_imitation_learning_b200 import FusedAdam, StagedBatch, _lib, sliding_window, stage_frames, stage_gray
     from src.architectures.nets import ConvNet1
+    bf16 = args.mode == "bf16"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -622,15 +625,18 @@ def run_stacked12(args):
     _lib.build()
     B = args.batch if args.batch != 256 else 64
     torch.manual_seed(12345)
-    net = ConvNet1({"obs_size": 12, "n_actions": 9}).to(dev)
+    net = ConvNet1({"obs_size": 12, "n_actions": 9, "precision": args.mode}).to(dev)
     eng = net.engine()
     opt = FusedAdam(list(net.parameters()), lr=1e-3)
     nfr = 3 * (B + 4)                                     # 3 cameras x (B + 4) frames: sample b = frames b..b+3 of every camera (+ the frame that carries its label)
     rng = np.random.Generator(np.random.PCG64(7 + rank))
     frames = [torch.from_numpy(rng.integers(0, 256, size=(nfr, 256, 256, 3), dtype=np.uint8)).to(dev) for _ in range(2)]
     labels = torch.from_numpy(rng.integers(0, 9, size=B)).to(dev)
-    gray = torch.empty((nfr, 256, 256), dtype=torch.float32, device=dev)
-    x = sliding_window(gray, frame_skip=12, step=3)
+    if bf16:
+        x = StagedBatch(torch.empty((nfr, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=dev), None, 12, 3)
+    else:
+        gray = torch.empty((nfr, 256, 256), dtype=torch.float32, device=dev)
+        x = sliding_window(gray, frame_skip=12, step=3)
     assert x.shape[0] == B
     bufs = eng.alloc(B, x, labels, True)
     opt.prepare()
@@ -640,7 +646,10 @@ def run_stacked12(args):
         xchg = PeerExchangeStep(eng, opt)
 
     def enqueue(fr):
-        stage_gray(fr, out=gray)
+        if bf16:
+            stage_frames(fr, out=x, frame_skip=12, step=3)
+        else:
+            stage_gray(fr, out=gray)
         if xchg is not None:
             xchg(bufs)
         else:
@@ -698,15 +707,16 @@ def run_stacked12(args):
         value = B * world * args.steps / (ms * 1e-3)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
             "config": {"workload": f"ConvNet1 BC train step, channel-stacked variant (BASELINE configs[3]): obs 12 = 3 cameras x 4 frames at 256x256, "
-                                   f"batch {B}/GPU, exact-f32 FFMA kernels, u8 RGB frames staged on the device", "global_batch": B * world,
+                                   f"batch {B}/GPU, " + ("tcgen05 kernels (conv1 = three camera streams)" if bf16 else "exact-f32 FFMA kernels")
+                                   + ", u8 RGB frames staged on the device", "global_batch": B * world,
                        "parallelism": f"dp{world}", "cuda_graph": True, "final_loss": loss,
                        "l2": "inputs alternate over 2 device buffers of %d MB" % (nfr * FRAME_BYTES // 1000000)},
-            "roofline": {"kernel": "whole step (f32 FFMA kernels)", "bound": "tensor", "achieved": flops * value / 1e12, "peak": peaks["tf_sust"],
+            "roofline": {"kernel": "whole step (" + ("tcgen05 kernels" if bf16 else "f32 FFMA kernels") + ")", "bound": "tensor", "achieved": flops * value / 1e12, "peak": peaks["tf_sust"],
                          "unit": "TFLOP/s", "frac": flops * value / 1e12 / peaks["tf_sust"], "traffic": None,
-                         "note": "the exact-f32 path runs on CUDA cores; the fraction is against the bf16 tensor peak for comparability"},
-            "gpu_launches": 15 * args.steps, "clocks": clocks}), flush=True)
+                         "note": "algorithmic FLOPs of the 12-channel step (327.5 MFLOP/frame) against the sustained bf16 tensor peak" + ("" if bf16 else "; the exact-f32 path runs on CUDA cores")},
+            "gpu_launches": (19 if bf16 else 15) * args.steps, "clocks": clocks}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -719,7 +729,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "infer", "stacked12"],
-                    help="train = BASELINE configs[1]/[2]; infer = configs[4] batch sweep; stacked12 = configs[3] (12 channels, exact-f32 kernels)")
+                    help="train = BASELINE configs[1]/[2]; infer = configs[4] batch sweep; stacked12 = configs[3] (12 channels = 3 cameras x 4 frames)")
     ap.add_argument("--mode", default="bf16", choices=["fp32", "bf16"], help="fp32 = exact FFMA kernels; bf16 = tcgen05 kernels")
     ap.add_argument("--nbuf", type=int, default=4)
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="N>1 gradient exchange: fused peer-memory Adam, or NCCL buckets")

@@ -33,7 +33,7 @@ class BcCtx(C.Structure):
         ("logits", C.c_void_p), ("dlogits", C.c_void_p), ("loss", C.c_void_p), ("partials", C.c_void_p),
         ("loss_scale", C.c_float), ("conv_mode", C.c_int32),
         ("w_packed", C.c_void_p), ("err_flag", C.c_void_p), ("act_bf16", C.c_void_p * 3),
-        ("reserved0", C.c_void_p),
+        ("c1_acc", C.c_void_p),
         ("x_tp", C.c_void_p), ("x_tp_stride_n", C.c_int64), ("x_tp_stride_c", C.c_int64),
         ("grads_epoch", C.c_void_p), ("grads_stride", C.c_int64),
         ("gact0_p8", C.c_void_p), ("amax0_p8", C.c_void_p),

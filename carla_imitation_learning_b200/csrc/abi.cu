@@ -296,13 +296,13 @@ int bc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 }
 
 static int pack_map_for(ctc::PackMap* pm, void* w_packed, int obs_size, int n_actions, int64_t n, const char* who) {
-    *pm = ctc::PackMap{nullptr, 0, 0, 0, 0};
+    *pm = ctc::PackMap{nullptr, 0, 0, 0, 0, 0};
     if (!w_packed) return BC_OK;
-    if (obs_size != 4) return bc::fail(BC_ERR_ARG, "%s: the bf16 operand images exist for obs_size 4 only (got %d)", who, obs_size);
+    if (obs_size != 4 && obs_size != 12) return bc::fail(BC_ERR_ARG, "%s: the bf16 operand images exist for obs_size 4 and 12 (got %d)", who, obs_size);
     const bc::Arena a = bc::arena_layout(obs_size, n_actions);
     if (a.total != n) return bc::fail(BC_ERR_ARG, "%s: n=%lld is not the arena of (obs %d, actions %d) = %lld floats", who, (long long)n, obs_size, n_actions, (long long)a.total);
     if ((uintptr_t)w_packed % 16 != 0) return bc::fail(BC_ERR_ARG, "%s: w_packed must be 16 B aligned", who);
-    *pm = ctc::pack_map(a, w_packed);
+    *pm = ctc::pack_map(a, w_packed, obs_size);
     return BC_OK;
 }
 

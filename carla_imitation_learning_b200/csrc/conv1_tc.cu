@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "bc_common.cuh"
 #include "tc05.cuh"
+#include "pack.cuh"
 
 namespace c1tc {
 
@@ -89,10 +90,15 @@ struct TileIter {
     }
 };
 
+// ADD_IN / RAW_OUT: the 12-channel conv1 of BASELINE configs[3] (3 cameras x 4 frames, channel = 3*frame + camera) runs as three
+// launches over the cameras' own 4-frame sliding windows (x + cam planes, strides 3 planes, the camera's weight image): the first
+// two leave the raw f32 accumulators in `acc` ([sample*14 + tile row][126 rows][64]), the later ones add what is there; the
+// last launch pools as usual. The 4-channel network is <false, false> and never touches `acc`.
+template <bool ADD_IN, bool RAW_OUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, const __nv_bfloat16* __restrict__ wpk,
                 const float* __restrict__ bias, float* __restrict__ y, uint8_t* __restrict__ amax,
-                __nv_bfloat16* __restrict__ ybf, uint8_t* __restrict__ amax_p8, int B, int* err, int ablate) {
+                __nv_bfloat16* __restrict__ ybf, uint8_t* __restrict__ amax_p8, float* __restrict__ acc, int B, int* err, int ablate) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* b_full = bars;
@@ -255,6 +261,23 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 tc05::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(t_empty + idx);   // accumulator drained
+                if constexpr (ADD_IN || RAW_OUT) {
+                    if (r < MROWS) {
+                        float4* a4 = reinterpret_cast<float4*>(acc + (((size_t)(b0 + s) * TILES_PER_FRAME + ty) * MROWS + r) * 64);
+                        if constexpr (ADD_IN) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const float4 t = a4[q];
+                                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                            }
+                        }
+                        if constexpr (RAW_OUT) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) a4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
+                    if constexpr (RAW_OUT) continue;               // not the last camera: no pooling, nothing else to write
+                }
                 if (r < MROWS) {
                     float4* dst = reinterpret_cast<float4*>(S_ + r * S_PITCH);
 #pragma unroll
@@ -651,42 +674,60 @@ fin:
 
 extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c && c->params && c->w_packed, "bc_pack_weights: null buffer");
-    BC_CHECK_ARG(c->obs_size == 4, "bc_pack_weights: the tcgen05 conv1 operand exists for obs_size 4 only");
+    BC_CHECK_ARG(c->obs_size == 4 || c->obs_size == 12, "bc_pack_weights: the tcgen05 conv1 operand exists for obs_size 4 and 12");
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
     return bc_conv_tc_pack(c, stream);     // one launch: conv1's Toeplitz image, then conv2-4's forward and dgrad images
 }
 
 extern "C" size_t bc_packed_weight_bytes(void) { return bc_conv_tc_pack_total(); }
 
-static int conv1_tp_launch(const bc_ctx* c, void* stream) {
-    BC_CHECK_ARG(c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05, TP): null buffer (w_packed, err_flag, act, amax)");
-    BC_CHECK_ARG(c->obs_size == 4, "conv1 (tcgen05, TP): obs_size 4 only");
-    BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
-                 "conv1 (tcgen05, TP): x_tp, its strides and w_packed must be 16 B aligned");
+template <bool ADD_IN, bool RAW_OUT>
+static int conv1_tp_launch_one(const bc_ctx* c, int cam, int64_t sn, int64_t sc, int ablate, void* stream) {
+    auto kern = c1tp::conv1_tp_kernel<ADD_IN, RAW_OUT>;
     static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(c1tp::conv1_tp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tp::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c1tp::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 (tcgen05, TP): smem opt-in %d B failed: %s", c1tp::SMEM_BYTES, cudaGetErrorString(e));
         configured = true;
     }
-    // BC_C1FW_GEN=4 selects the swapped-role kernel (conv1_fwd4.cu: same results, register-local pooling; measured 31 us against
-    // 28 us here because its M=128 x N=128 MMAs fetch 8 KB of operands per 64 cycles = the whole shared-memory bandwidth)
-    static const bool gen4 = getenv("BC_C1FW_GEN") && atoi(getenv("BC_C1FW_GEN")) == 4;
-    if (gen4) return bc_conv1_fwd4_launch(c, stream);
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
     const int ntiles = c->batch * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();
     if (grid > ntiles) grid = ntiles;
+    bc::launch_pdl(kern, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
+        (const __nv_bfloat16*)c->x_tp + (int64_t)cam * c->x_tp_stride_c, sn, sc,
+        (const __nv_bfloat16*)((const uint8_t*)c->w_packed + ctc::c1_cam_off(cam)), c->params + a.b[0],
+        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], (c->conv_mode & 16) ? c->amax0_p8 : nullptr, (float*)c->c1_acc, c->batch, c->err_flag, ablate);
+    BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
+    return BC_OK;
+}
+
+static int conv1_tp_launch(const bc_ctx* c, void* stream) {
+    BC_CHECK_ARG(c->w_packed && c->err_flag && c->act[0] && c->amax[0], "conv1 (tcgen05, TP): null buffer (w_packed, err_flag, act, amax)");
+    BC_CHECK_ARG(c->obs_size == 4 || c->obs_size == 12, "conv1 (tcgen05, TP): obs_size 4 or 12");
+    BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0 && ((uintptr_t)c->w_packed % 16 == 0),
+                 "conv1 (tcgen05, TP): x_tp, its strides and w_packed must be 16 B aligned");
 #ifdef BC_ABLATE   // timing experiments only (knowingly wrong results): compiled out of the shipped library
     static const int ablate = getenv("BC_C1FW_ABLATE") ? atoi(getenv("BC_C1FW_ABLATE")) : 0;
 #else
     constexpr int ablate = 0;
 #endif
-    bc::launch_pdl(c1tp::conv1_tp_kernel, dim3(grid), dim3(c1tp::NTHREADS), c1tp::SMEM_BYTES, (cudaStream_t)stream,
-        (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const __nv_bfloat16*)c->w_packed, c->params + a.b[0],
-        c->act[0], c->amax[0], (__nv_bfloat16*)c->act_bf16[0], (c->conv_mode & 16) ? c->amax0_p8 : nullptr, c->batch, c->err_flag, ablate);
-    BC_CUDA_LAUNCH_CHECK("conv1_tp_kernel");
-    return BC_OK;
+    if (c->obs_size == 12) {
+        // three camera streams: camera `cam` owns the network's channels cam, 3+cam, 6+cam, 9+cam = its own 4-frame window. With the
+        // stacked sliding window (stride_n == 3 * stride_c: sample s = planes 3s .. 3s+11) the stream is again a sliding window
+        // (both strides 3 planes) and its planes are shared by 4 samples; a materialised batch keeps stride_n.
+        BC_CHECK_ARG(c->c1_acc && (uintptr_t)c->c1_acc % 16 == 0, "conv1 (tcgen05, TP), obs_size 12: c1_acc (batch*14*126*64 f32) is null or unaligned");
+        const int64_t sc = 3 * c->x_tp_stride_c, sn = c->x_tp_stride_n == 3 * c->x_tp_stride_c ? sc : c->x_tp_stride_n;
+        int rc = conv1_tp_launch_one<false, true>(c, 0, sn, sc, ablate, stream);
+        if (!rc) rc = conv1_tp_launch_one<true, true>(c, 1, sn, sc, ablate, stream);
+        if (!rc) rc = conv1_tp_launch_one<true, false>(c, 2, sn, sc, ablate, stream);
+        return rc;
+    }
+    // BC_C1FW_GEN=4 selects the swapped-role kernel (conv1_fwd4.cu: same results, register-local pooling; measured 31 us against
+    // 28 us here because its M=128 x N=128 MMAs fetch 8 KB of operands per 64 cycles = the whole shared-memory bandwidth)
+    static const bool gen4 = getenv("BC_C1FW_GEN") && atoi(getenv("BC_C1FW_GEN")) == 4;
+    if (gen4) return bc_conv1_fwd4_launch(c, stream);
+    return conv1_tp_launch_one<false, false>(c, 0, c->x_tp_stride_n, c->x_tp_stride_c, ablate, stream);
 }
 
 int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
@@ -695,7 +736,7 @@ int bc_conv1_tc_launch(const bc_ctx* c, void* stream) {
 }
 
 int bc_conv1_wgrad_tp_grid(const bc_ctx* c) {
-    const bool sliding = c->x_tp_stride_n == c->x_tp_stride_c;
+    const bool sliding = c->x_tp_stride_n == (c->obs_size / 4) * c->x_tp_stride_c;
     const int njobs = (sliding ? c->batch + 3 : 4 * c->batch) * c1tc::TILES_PER_FRAME;
     int grid = bc::num_sms();
     if (grid > bc::kWgradParts[0]) grid = bc::kWgradParts[0];
@@ -708,7 +749,10 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c->err_flag && c->partials && (compact ? (c->gact0_p8 && c->amax0_p8) : (c->gact[0] && c->act[0] && c->amax[0])),
                  "conv1 wgrad (tcgen05, TP): null buffer (%s gradient path)", compact ? "compact P8" : "f32 NCHW");
     BC_CHECK_ARG(!compact || ((uintptr_t)c->gact0_p8 % 16 == 0 && (uintptr_t)c->amax0_p8 % 8 == 0), "conv1 wgrad (tcgen05, TP): gact0_p8 / amax0_p8 alignment");
-    BC_CHECK_ARG(c->obs_size == 4, "conv1 wgrad (tcgen05, TP): obs_size 4 only");
+    BC_CHECK_ARG(c->obs_size == 4 || c->obs_size == 12, "conv1 wgrad (tcgen05, TP): obs_size 4 or 12");
+    const bool window = c->x_tp_stride_n == (c->obs_size / 4) * c->x_tp_stride_c;      // the (stacked) sliding window: planes shared between samples
+    BC_CHECK_ARG(c->obs_size == 4 || (compact && window), "conv1 wgrad (tcgen05, TP), obs_size 12: needs the stacked sliding window (x_tp_stride_n == 3 * "
+                 "x_tp_stride_c, stage_frames(frame_skip=12, step=3)) and the compact gradient path (conv_mode bit 16)");
     BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0,
                  "conv1 wgrad (tcgen05, TP): x_tp and its strides must be 16 B aligned");
     // ring depths: the compact builders are fast enough that a deeper gradient ring pays (3 plane + 7 gradient slots); the f32
@@ -736,7 +780,7 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     constexpr int ablate = 0;
 #endif
     static const bool gen2 = getenv("BC_C1WG_GEN") && atoi(getenv("BC_C1WG_GEN")) == 2;     // measurement switch: second-generation kernel
-    if (compact && c->x_tp_stride_n == c->x_tp_stride_c && !gen2)
+    if (compact && window && (!gen2 || c->obs_size == 12))
         return bc_conv1_wgrad3_launch(c, ar, pl, grid, stream);                                 // third generation (conv1_wgrad3.cu)
     if (compact)
         bc::launch_pdl(ring45 ? kc45 : kc, dim3(grid), dim3(c1wg2::NTHREADS), ring45 ? RF::SMEM_BYTES : RC::SMEM_BYTES, (cudaStream_t)stream,

@@ -75,7 +75,11 @@ struct SegIter {
 template <typename PL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4* __restrict__ g8, const uint2* __restrict__ a8,
-                    float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate) {
+                    float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate,
+                    int cin, int cstep, int coff) {
+    // (cin, cstep, coff) = (4, 1, 0): the 4-channel network. obs_size 12 (3 cameras x 4 frames): three launches over the cameras' own
+    // sliding windows (x + cam planes, plane stride 3), launch `coff` = cam fills the network's channels 3*ci + cam of every
+    // partial slot; the bias gradient and the zeroing of the slots no CTA owns belong to launch 0.
     constexpr int NA = PL::NA, NDY = PL::NDY, VPAD = PL::VPAD, A_SLOT = PL::A_SLOT, OFF_A = PL::OFF_A, OFF_DY = PL::OFF_DY,
                   OFF_BAR = PL::OFF_BAR, NBAR = PL::NBAR;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -281,9 +285,10 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
         // ---- epilogue (both groups; group g takes ci = 2g, 2g+1): add the two issuers' accumulators (fixed order), fold the
         // Toeplitz rows back to 7 taps and write this CTA's partial in arena order; then the bias gradient from the builders' sums
         float* dst = part + (size_t)blockIdx.x * seg_len;
-        if (grp == 0 && (int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
+        const int nw = 16 * cin * 49;
+        if (coff == 0 && grp == 0 && (int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
             for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
-                for (int i = te; i < 3136 + 16; i += 128) part[(size_t)s2 * seg_len + (i < 3136 ? w_off + i : b_off + i - 3136)] = 0.f;
+                for (int i = te; i < nw + 16; i += 128) part[(size_t)s2 * seg_len + (i < nw ? w_off + i : b_off + i - nw)] = 0.f;
         }
         const bool fin = ok && tc05::mbar_wait(done, 0, err);
         if (fin && !(ablate & 16)) {              // ablate bit 4: no epilogue
@@ -316,7 +321,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
                         const int srcl = (lane & 16) + ((3 * j + p) & 15);
                         a += __shfl_sync(0xffffffffu, v[j * 16 + co], srcl);
                     }
-                    if (wrow) dst[w_off + ((size_t)(co * 4 + ci) * 7 + ky) * 7 + p] = a;
+                    if (wrow) dst[w_off + ((size_t)(co * cin + ci * cstep + coff) * 7 + ky) * 7 + p] = a;
                 }
             }
         }
@@ -327,7 +332,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
             for (int q = 0; q < 8; ++q) scratch[(grp * 112 + te) * 8 + q] = bsum[q];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (fin && grp == 0 && te < 16) {
+        if (fin && coff == 0 && grp == 0 && te < 16) {
             const int cg = te >> 3, q = te & 7;
             float a = 0.f;
             for (int g2 = 0; g2 < 2; ++g2)
@@ -362,9 +367,13 @@ int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Parti
     constexpr int ablate = 0;
 #endif
     static const bool plan55 = getenv("BC_C1WG_PLAN") && atoi(getenv("BC_C1WG_PLAN")) == 55;    // measurement switch (same results)
-    bc::launch_pdl(plan55 ? k55 : k47, dim3(grid), dim3(c1wg3::NTHREADS), plan55 ? P55::SMEM_BYTES : P47::SMEM_BYTES, (cudaStream_t)stream,
-        (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_c, (const uint4*)c->gact0_p8, (const uint2*)c->amax0_p8,
-        c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
-    BC_CUDA_LAUNCH_CHECK("conv1_wgrad3_kernel");
+    const int ncam = c->obs_size == 12 ? 3 : 1;
+    for (int cam = 0; cam < ncam; ++cam) {
+        bc::launch_pdl(plan55 ? k55 : k47, dim3(grid), dim3(c1wg3::NTHREADS), plan55 ? P55::SMEM_BYTES : P47::SMEM_BYTES, (cudaStream_t)stream,
+            (const __nv_bfloat16*)c->x_tp + (int64_t)cam * c->x_tp_stride_c, (int64_t)ncam * c->x_tp_stride_c, (const uint4*)c->gact0_p8, (const uint2*)c->amax0_p8,
+            c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate,
+            c->obs_size, ncam, cam);
+        BC_CUDA_LAUNCH_CHECK("conv1_wgrad3_kernel");
+    }
     return BC_OK;
 }

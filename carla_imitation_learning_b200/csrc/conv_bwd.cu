@@ -334,7 +334,7 @@ extern "C" int bc_conv_bwd_wgrad(const bc_ctx* c, int layer, void* stream) {
     const float* gP = layer == 3 ? c->ghead : c->gact[layer];
     BC_CHECK_ARG(gP, "bc_conv_bwd_wgrad: gradient buffer for layer %d is null", layer);
     if ((c->conv_mode & 4) && layer >= 1 && c->act_bf16[layer - 1]) return bc_wgrad_tc_launch(c, layer, stream);
-    if ((c->conv_mode & 8) && layer == 0 && c->x_tp && c->obs_size == 4 && c->err_flag) return bc_conv1_wgrad_tc_launch(c, stream);
+    if ((c->conv_mode & 8) && layer == 0 && c->x_tp && c->err_flag) return bc_conv1_wgrad_tc_launch(c, stream);
     cudaStream_t s = (cudaStream_t)stream;
     const int B = c->batch, np = bc::kWgradParts[layer];
     switch (layer) {
@@ -390,7 +390,7 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     a.grads_epoch = c->grads_epoch; a.grads_stride = c->grads_stride;
     for (int k = 0; k < 5; ++k) { a.seg_off[k] = ar.seg_off[k]; a.seg_len[k] = ar.seg_len[k]; a.poff[k] = pl.off[k]; a.nparts[k] = pl.nparts[k]; }
     // the tcgen05 conv1 wgrad writes one partial per CTA, i.e. fewer slots than the layout reserves: read only those
-    if ((c->conv_mode & 8) && c->x_tp && c->obs_size == 4 && c->err_flag) a.nparts[4] = bc_conv1_wgrad_tp_grid(c);
+    if ((c->conv_mode & 8) && c->x_tp && c->err_flag) a.nparts[4] = bc_conv1_wgrad_tp_grid(c);
     a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
     a.begin = ar.seg_off[seg_lo];
     a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];

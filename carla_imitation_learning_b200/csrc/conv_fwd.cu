@@ -241,7 +241,7 @@ extern "C" int bc_conv_relu_pool_fwd(const bc_ctx* c, int layer, void* stream) {
     switch (layer) {
     case 0: {
         BC_CHECK_ARG(c->x || c->x_tp, "bc_conv_relu_pool_fwd: x is null");
-        if ((c->conv_mode & 1) && c->x_tp && c->obs_size == 4) return bc_conv1_tc_launch(c, stream);
+        if ((c->conv_mode & 1) && c->x_tp) return bc_conv1_tc_launch(c, stream);
         BC_CHECK_ARG(c->x, "bc_conv_relu_pool_fwd: the exact-f32 conv1 reads plain planes (x), only x_tp was given");
         const int esz = c->x_dtype == BC_F32 ? 4 : 2;
         BC_CHECK_ARG(c->x_dtype == BC_F32 || c->x_dtype == BC_BF16, "bad x_dtype %d", c->x_dtype);

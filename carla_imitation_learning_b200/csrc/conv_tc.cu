@@ -10,7 +10,7 @@ using ctc::kPackD2; using ctc::kPackD3; using ctc::kPackD4; using ctc::kPackTota
 size_t bc_conv_tc_pack_total() { return kPackTotal; }
 
 namespace ctc {
-struct PackArgs { const float* w1; const float* w2; const float* w3; const float* w4; uint8_t* base; };
+struct PackArgs { const float* w1; const float* w2; const float* w3; const float* w4; uint8_t* base; int obs; };
 
 constexpr int kNW2 = L2::COUT * L2::CIN * L2::KS * L2::KS, kNW3 = L3::COUT * L3::CIN * L3::KS * L3::KS, kNW4 = L4::COUT * L4::CIN * L4::KS * L4::KS;
 constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz image, element-ordered (it has structural zeros)
@@ -21,16 +21,22 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
     bc::pdl_wait();
     bc::pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < kNC1) {
-        // step s = (ky,ci): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu)
+    const int ncam = a.obs == 12 ? 3 : 1;
+    if (i < ncam * kNC1) {
+        // step s = (ky,ci): 64 rows n = (j*16+co) x 16 k; Wt[(j,co)][(ci,ky,p)] = W[co][ci][ky][p - 3j] or 0 (conv1_tc.cu);
+        // obs_size 12: one such image per camera, its channel ci = frame is the network's channel 3*frame + cam
+        const int cam = i / kNC1;
+        i -= cam * kNC1;
         const int k = i & 15, n = (i >> 4) & 63, st = i >> 10;
         const int ky = st >> 2, ci = st & 3, j = n >> 4, co = n & 15;     // steps ordered [ky][ci]: consecutive channels = consecutive B rows
         const int kx = k - 3 * j;
-        const float v = (kx >= 0 && kx < 7) ? a.w1[((co * 4 + ci) * 7 + ky) * 7 + kx] : 0.f;
-        reinterpret_cast<__nv_bfloat16*>(a.base)[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
+        const int cnet = a.obs == 12 ? 3 * ci + cam : ci;
+        const float v = (kx >= 0 && kx < 7) ? a.w1[((co * a.obs + cnet) * 7 + ky) * 7 + kx] : 0.f;
+        reinterpret_cast<__nv_bfloat16*>(a.base + c1_cam_off(cam))[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = __float2bfloat16_rn(v);
         return;
     }
-    i -= kNC1;
+    i -= ncam * kNC1;
+    if (a.obs == 12) i += kNC1V4;          // the swapped-role image exists for obs_size 4 only: skip its index range
     if (i < kNC1V4) {
         // block (ky, ci) = 1 + 5 ky + (3 - ci), zero blocks at 5 ky; row = co*4 + j; Wt[(co,j)][p] = W[co][ci][ky][p - 3j] or 0
         const int k = i & 15, r = (i >> 4) & 63, blk = i >> 10;
@@ -51,8 +57,8 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
 
 int bc_conv_tc_pack(const bc_ctx* c, void* stream) {
     const bc::Arena a = bc::arena_layout(c->obs_size, c->n_actions);
-    ctc::PackArgs pa{c->params + a.w[0], c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed};
-    bc::launch_pdl(ctc::pack_all_kernel, dim3((ctc::kPackElems + 255) / 256), dim3(256), 0, (cudaStream_t)stream, pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
+    ctc::PackArgs pa{c->params + a.w[0], c->params + a.w[1], c->params + a.w[2], c->params + a.w[3], (uint8_t*)c->w_packed, c->obs_size};
+    bc::launch_pdl(ctc::pack_all_kernel, dim3((ctc::kPackElems + 2 * ctc::kNC1 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, pa, kPackOff2, kPackOff3, kPackOff4, kPackD2, kPackD3, kPackD4);
     BC_CUDA_LAUNCH_CHECK("pack_all_kernel");
     return BC_OK;
 }

@@ -37,9 +37,15 @@ constexpr size_t kPackD3 = kPackD2 + DCfg<L2>::B_BYTES, kPackD4 = kPackD3 + DCfg
 // [W(ci) ; W(ci-1)] of two consecutive window samples are one contiguous slice for every ci = 0..4
 constexpr int kC1V4Blocks = 36, kC1V4Bytes = kC1V4Blocks * 2048;
 constexpr size_t kPackC1V4 = kPackD4 + DCfg<L4>::B_BYTES;
-constexpr size_t kPackTotal = kPackC1V4 + kC1V4Bytes;
+// obs_size 12 (BASELINE configs[3]: 3 cameras x 4 frames, channel = 3*frame + camera): conv1 runs as three 4-channel camera
+// streams accumulated into one result (conv1_tc.cu), each with its own Toeplitz image [ky][frame]: camera 0 at kPackOff1, 1 and 2 here
+constexpr int kC1CamBytes = 57344;
+constexpr size_t kPackC1Cam1 = kPackC1V4 + kC1V4Bytes;
+constexpr size_t kPackTotal = kPackC1Cam1 + 2 * kC1CamBytes;
+__host__ __device__ constexpr size_t c1_cam_off(int cam) { return cam == 0 ? kPackOff1 : kPackC1Cam1 + (size_t)(cam - 1) * kC1CamBytes; }
 __host__ __device__ constexpr int c1v4_block(int ky, int ci) { return 1 + 5 * ky + (3 - ci); }
 constexpr int kNC1W = 16 * 4 * 7 * 7;                      // conv1 weights (obs_size 4)
+constexpr int kNC1W12 = 16 * 12 * 7 * 7;                   // conv1 weights (obs_size 12)
 
 // One source weight W[co][ci][tap] of conv2-4 -> its position in the forward image and in the dgrad image.
 template <typename C>
@@ -75,20 +81,39 @@ __device__ __forceinline__ void pack_conv1_elem(float w, __nv_bfloat16* __restri
     }
 }
 
+// obs_size 12: W[co][ci = 3*frame + cam][ky][kx] -> image of camera `cam`, step (ky, frame), same Toeplitz rows as above
+__device__ __forceinline__ void pack_conv1x12_elem(float w, uint8_t* __restrict__ base, int i) {
+    const int kx = i % 7, ky = (i / 7) % 7, ci = (i / 49) % 12, co = i / 588;
+    const __nv_bfloat16 v = __float2bfloat16_rn(w);
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(base + c1_cam_off(ci % 3));
+    const int st = ky * 4 + ci / 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = kx + 3 * j, n = j * 16 + co;
+        if (k < 16) img[(size_t)st * 1024 + op_off(n, k >> 3) / 2 + (k & 7)] = v;
+    }
+}
+
 // Where the conv weights live in the parameter arena (float offsets) + the image base: what an optimiser kernel needs
 // to refresh the operand images of the floats it updates. base == nullptr: no refresh (fp32 mode).
 struct PackMap {
     uint8_t* base;
     int64_t w1, w2, w3, w4;
+    int obs;                 // 4 or 12: which conv1 images exist
 };
-__host__ inline PackMap pack_map(const bc::Arena& a, void* w_packed) {
-    return PackMap{(uint8_t*)w_packed, a.w[0], a.w[1], a.w[2], a.w[3]};
+__host__ inline PackMap pack_map(const bc::Arena& a, void* w_packed, int obs) {
+    return PackMap{(uint8_t*)w_packed, a.w[0], a.w[1], a.w[2], a.w[3], obs};
 }
 // `idx` = arena index of the first of four consecutive floats `v` (tensors are padded to 32 floats: never straddled)
 __device__ __forceinline__ void pack_updated4(const PackMap& pm, int64_t idx, const float* v) {
     if (pm.base == nullptr) return;
     if (idx >= pm.w1) {
         const int i = (int)(idx - pm.w1);
+        if (pm.obs == 12) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i + k < kNC1W12) pack_conv1x12_elem(v[k], pm.base, i + k);
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) if (i + k < kNC1W) pack_conv1_elem(v[k], (__nv_bfloat16*)pm.base, (__nv_bfloat16*)(pm.base + kPackC1V4), i + k);
     } else if (idx >= pm.w2) {

@@ -67,16 +67,18 @@ class StagedBatch:
     (include/bc_b200.h, BC_BF16_TP). `plain` (n,256,256) bf16 is optional: the same gray values as ordinary
     planes (diagnostics, or the exact-f32 kernels), written by the same pass of the staging kernel."""
 
-    def __init__(self, tp: torch.Tensor, plain: Optional[torch.Tensor] = None, frame_skip: int = 4):
-        self.tp, self.plain, self.frame_skip = tp, plain, frame_skip
+    def __init__(self, tp: torch.Tensor, plain: Optional[torch.Tensor] = None, frame_skip: int = 4, step: int = 1):
+        # step = planes a sample advances by: 1 = the reference's 4-frame window; 3 with frame_skip 12 = BASELINE configs[3],
+        # three cameras interleaved frame by frame (sample i = planes [3i, 3i+12), channel = 3*frame + camera)
+        self.tp, self.plain, self.frame_skip, self.step = tp, plain, frame_skip, step
 
     @property
     def x(self) -> Optional[torch.Tensor]:
-        return None if self.plain is None else sliding_window(self.plain, self.frame_skip)
+        return None if self.plain is None else sliding_window(self.plain, self.frame_skip, self.step)
 
     @property
     def shape(self):
-        return (self.tp.shape[0] - self.frame_skip, self.frame_skip, H, W)
+        return ((self.tp.shape[0] - self.frame_skip) // self.step, self.frame_skip, H, W)
 
     @property
     def device(self):
@@ -87,7 +89,7 @@ class StagedBatch:
 
 
 def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, frame_skip: int = 4,
-                 plain: bool = False) -> StagedBatch:
+                 plain: bool = False, step: int = 1) -> StagedBatch:
     """(n,256,256,3) u8 RGB on the device -> StagedBatch. The bf16-mode replacement of SequentialTorchDataset's
     per-sample numpy work (imitation_dataset.py:115-133): gray conversion, /255, 4-frame stacking (as a view) and
     the MMA operand layout of conv1 in one fused kernel."""
@@ -99,7 +101,7 @@ def stage_frames(frames_u8: torch.Tensor, out: Optional[StagedBatch] = None, fra
         raise ValueError(f"need more than {frame_skip} frames, got {n}")
     if out is None:
         out = StagedBatch(torch.empty((n, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=frames_u8.device),
-                          torch.empty((n, H, W), dtype=torch.bfloat16, device=frames_u8.device) if plain else None, frame_skip)
+                          torch.empty((n, H, W), dtype=torch.bfloat16, device=frames_u8.device) if plain else None, frame_skip, step)
     elif out.tp.shape[0] != n:
         raise ValueError("out was staged for a different number of frames")
     _lib.check(_lib.lib().bc_stage_gray_tp(frames_u8.data_ptr(), out.tp.data_ptr(),
@@ -154,6 +156,7 @@ class StepBuffers:
     amax0_p8: Optional[torch.Tensor] = None                      # bf16 mode: conv1's pool routing again in P8 order
     x_tp: Optional[torch.Tensor] = None                          # bf16 mode: the input as Toeplitz-ready planes
     x_tp_strides: tuple = (0, 0)                                 # (sample, channel) element strides into x_tp
+    c1_acc: Optional[torch.Tensor] = None                        # bf16 mode, obs_size 12: raw conv1 accumulators between the camera launches
 
 
 class BCEngine:
@@ -204,9 +207,12 @@ class BCEngine:
             hid1=e(batch, 64), hid2=e(batch, 32), logits=e(batch, self.n_actions),
             dlogits=e(batch, self.n_actions), loss=torch.zeros((), dtype=f32, device=dev))
         if staged is not None:
-            bufs.x_tp, bufs.x_tp_strides = staged.tp, (_lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
-        elif (self.conv_mode & 1) and self.obs_size == 4 and batch:
+            bufs.x_tp, bufs.x_tp_strides = staged.tp, (staged.step * _lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
+        elif (self.conv_mode & 1) and batch:
             bufs.x_tp, bufs.x_tp_strides = self.to_tp(x)
+        if (self.conv_mode & 1) and self.obs_size == 12:
+            # the raw conv1 accumulators the three camera launches hand to each other (bc_ctx.c1_acc)
+            bufs.c1_acc = torch.empty((max(batch, 1), 14, 126, 64), dtype=f32, device=dev)
         if self.conv_mode & 1:
             # bf16 copies feeding the next layer's MMAs: act1, act2 as P8 = (B, C/8, H*W, 8) for the shifted-window
             # kernels (csrc/conv_sw.cu), act3 as P8B = (C/8, B, H*W, 8) for conv4 (csrc/conv4_sw.cu)
@@ -231,20 +237,22 @@ class BCEngine:
         A sliding-window view (sliding_window()) is converted once per PLANE, not per sample."""
         B = x.shape[0]
         P = H * W
-        sliding = x.stride(0) == P and x.stride(1) == P
+        step = self.obs_size // 4                                   # planes per sample step of the (stacked) sliding window: 1, or 3 for obs 12
+        sliding = x.stride(0) == step * P and x.stride(1) == P
         if not sliding and not (x.stride(1) == P and x.stride(0) == self.obs_size * P):
             x = x.contiguous()
-        n_planes = B + self.obs_size - 1 if sliding else B * self.obs_size
+        n_planes = step * (B - 1) + self.obs_size if sliding else B * self.obs_size
         tp = out if out is not None else torch.empty((n_planes, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=x.device)
         code = _lib.BC_F32 if x.dtype == torch.float32 else _lib.BC_BF16
         _lib.check(self.lib.bc_planes_to_tp(x.data_ptr(), code, n_planes, P, tp.data_ptr(), _stream_ptr()), "bc_planes_to_tp")
         e = _lib.TP_PLANE_ELEMS
-        return tp, ((e, e) if sliding else (self.obs_size * e, e))
+        return tp, ((step * e, e) if sliding else (self.obs_size * e, e))
 
     def check_input(self, x):
         if isinstance(x, StagedBatch):
-            if not (self.conv_mode & 1) or self.obs_size != 4:
-                raise ValueError("a StagedBatch feeds the bf16 tensor-core mode (precision='bf16', obs_size 4)")
+            if not (self.conv_mode & 1) or (x.frame_skip, x.step) != (self.obs_size, self.obs_size // 4):
+                raise ValueError("a StagedBatch feeds the bf16 tensor-core mode (precision='bf16'): frame_skip 4 for obs_size 4, "
+                                 "stage_frames(frame_skip=12, step=3) for obs_size 12")
             if x.device != self.device:
                 raise RuntimeError(f"x is on {x.device}, parameters on {self.device}")
             return x
@@ -290,6 +298,8 @@ class BCEngine:
             c.grads_epoch, c.grads_stride = self.grads_epoch.data_ptr(), self.grads_stride
         if b.gact0_p8 is not None:
             c.gact0_p8, c.amax0_p8 = b.gact0_p8.data_ptr(), b.amax0_p8.data_ptr()
+        if b.c1_acc is not None:
+            c.c1_acc = b.c1_acc.data_ptr()
         return c
 
     def static_buffers(self, batch: int, x, y: Optional[torch.Tensor]) -> StepBuffers:
@@ -301,13 +311,14 @@ class BCEngine:
             return b
         staged = x if isinstance(x, StagedBatch) else None
         if staged is not None:
-            b.x, b.x_tp, b.x_tp_strides = staged.x, staged.tp, (_lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
+            b.x, b.x_tp, b.x_tp_strides = staged.x, staged.tp, (staged.step * _lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
         else:
             b.x = x
-            if (self.conv_mode & 1) and self.obs_size == 4 and batch:
+            if (self.conv_mode & 1) and batch:
                 # a plain batch in bf16 mode: converted per call into a persistent plane buffer (stable pointer for graphs)
-                sliding = x.stride(0) == H * W and x.stride(1) == H * W
-                n_planes = batch + self.obs_size - 1 if sliding else batch * self.obs_size
+                step = self.obs_size // 4
+                sliding = x.stride(0) == step * H * W and x.stride(1) == H * W
+                n_planes = step * (batch - 1) + self.obs_size if sliding else batch * self.obs_size
                 own = getattr(b, "_tp_own", None)
                 if own is None or own.shape[0] != n_planes:
                     own = b._tp_own = torch.empty((n_planes, _lib.TP_PLANE_ELEMS), dtype=torch.bfloat16, device=self.device)
@@ -403,8 +414,8 @@ class BCEngine:
             self.pack_weights()
 
     def packed_ptr(self) -> Optional[int]:
-        """w_packed for the optimiser kernels: the images follow the weights only in bf16 mode (obs_size 4)."""
-        return self.w_packed.data_ptr() if (self.conv_mode and self.obs_size == 4) else None
+        """w_packed for the optimiser kernels: the images follow the weights only in bf16 mode."""
+        return self.w_packed.data_ptr() if self.conv_mode else None
 
     _ERRORS = {1: "a tcgen05 pipeline wait timed out inside a kernel (mbarrier protocol error)",
                3: "a label outside [0, n_actions) reached the CrossEntropy kernel (nn.CrossEntropyLoss raises on it too)"}

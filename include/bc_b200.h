@@ -77,7 +77,8 @@ typedef struct {
     void* act_bf16[3];       /* bf16 mode: bf16 copies of act[0..2] in the layouts the shifted-window kernels read
                                 (csrc/conv_sw.cu, conv4_sw.cu): act1 P8 (B,2,784,8), act2 P8 (B,4,144,8),
                                 act3 P8B (8,B,16,8) = [c/8][b][pixel][8]; written by the conv epilogues     */
-    void* reserved0;         /* (was: dense dY scratch; the routed gradients are now built in shared memory)  */
+    void* c1_acc;            /* obs_size 12 in bf16 mode only (else NULL): batch*14*126*64 f32, the raw conv1 accumulators the three
+                                camera launches of the tcgen05 conv1 hand to each other (csrc/conv1_tc.cu)                       */
     const void* x_tp;        /* bf16 mode: the input as BC_BF16_TP planes (bc_stage_gray / bc_planes_to_tp); sample n,
                                 channel c is the plane at x_tp + n*x_tp_stride_n + c*x_tp_stride_c (elements).
                                 stride_n == stride_c is the sliding window: consecutive samples share 3 of 4 planes

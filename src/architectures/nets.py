@@ -178,7 +178,7 @@ class ConvNet1(_Base):
                     "ConvNet1 runs only on a CUDA sm_100 (B200) device: move it with .to('cuda'). "
                     "There is deliberately no CPU / PyTorch fallback for the hot path.")
             self._engine = BCEngine(self._arena, self.obs_size, self.n_actions)
-            if self.precision == 'bf16' and self.obs_size == 4:
+            if self.precision == 'bf16':         # obs_size 4, and 12 = three 4-frame camera streams (BASELINE configs[3])
                 self._engine.set_mode('bf16')
             self._engine.overlap = self.overlap_backward
             params, arena = self._ordered_params, self._arena

@@ -450,12 +450,12 @@ def test_inference_sweep_batches_match_oracle(mode):
 
 def test_stacked_12_channel_variant_matches_oracle():
     """BASELINE configs[3]: obs_size = 12 (3 cameras x 4 frames channel-stacked) at the 256x256 the architecture
-    hard-codes (nets.py:14); forward, loss and all 14 gradients vs the f64 oracle given the device's routing.
-    (precision='bf16' falls back to the exact kernels for obs_size != 4: the Toeplitz operand is built for 4 planes.)"""
+    hard-codes (nets.py:14), exact-f32 kernels: forward, loss and all 14 gradients vs the f64 oracle given the device's routing.
+    (The tensor-core mode of this variant: tests/test_gpu_stacked12.py.)"""
     from src.architectures.nets import ConvNet1
     dev = _dev()
     torch.manual_seed(7)
-    net = ConvNet1({"obs_size": 12, "n_actions": 9, "precision": "bf16"}).to(dev)
+    net = ConvNet1({"obs_size": 12, "n_actions": 9}).to(dev)
     assert net.engine().conv_mode == 0
     params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
     assert params["cnn_base.0.weight"].shape == (16, 12, 7, 7)
