@@ -623,7 +623,7 @@ def run_stacked12(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.build()
-    B = args.batch if args.batch != 256 else 64
+    B = args.batch                                        # 256 per GPU like configs[1] (the exact-f32 mode is ~8x slower per frame: use --batch 64 --mode fp32 for it)
     torch.manual_seed(12345)
     net = ConvNet1({"obs_size": 12, "n_actions": 9, "precision": args.mode}).to(dev)
     eng = net.engine()

@@ -416,7 +416,10 @@ template <bool COMPACT, typename R>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc,
                       const void* __restrict__ gP_, const float* __restrict__ aP, const uint8_t* __restrict__ amax,
-                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate) {
+                      float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate,
+                      int cin, int cstep, int coff) {
+    // (cin, cstep, coff) = (4, 1, 0) for the 4-channel network; obs_size 12: launch coff = camera fills channels 3*ci + cam of
+    // every partial slot, the bias gradient and the zeroing of unowned slots belong to launch 0 (see conv1_wgrad3.cu)
     constexpr int NA = R::NA, NDY = R::NDY, OFF_A = R::OFF_A, OFF_DY = R::OFF_DY, OFF_BAR = R::OFF_BAR, NBAR = R::NBAR;
     const float* __restrict__ gP = reinterpret_cast<const float*>(gP_);
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -628,9 +631,10 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
         // ---- epilogue (warps 4-7): fold the Toeplitz rows back to 7 taps and write this CTA's partial in arena order
         if (grp) goto fin;
         float* dst = part + (size_t)blockIdx.x * seg_len;
-        if ((int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
+        const int nw = 16 * cin * 49;
+        if (coff == 0 && (int)blockIdx.x + (int)gridDim.x < nparts) {           // slots this launch does not own must read as zero
             for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
-                for (int i = te; i < 3136 + 16; i += 128) part[(size_t)s2 * seg_len + (i < 3136 ? w_off + i : b_off + i - 3136)] = 0.f;
+                for (int i = te; i < nw + 16; i += 128) part[(size_t)s2 * seg_len + (i < nw ? w_off + i : b_off + i - nw)] = 0.f;
         }
         if (ok && tc05::mbar_wait(done, 0, err)) {
             tc05::tc_fence_after();
@@ -658,8 +662,8 @@ conv1_wgrad_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t s
                         const float o = __shfl_sync(0xffffffffu, v[j * 16 + co], srcl);
                         acc += brow ? v[j * 16 + co] : o;
                     }
-                    if (wrow) dst[w_off + ((size_t)(co * 4 + ci) * 7 + ky) * 7 + p] = acc;
-                    else if (brow) dst[b_off + co] = acc;
+                    if (wrow) dst[w_off + ((size_t)(co * cin + ci * cstep + coff) * 7 + ky) * 7 + p] = acc;
+                    else if (brow && coff == 0) dst[b_off + co] = acc;
                 }
             }
         }
@@ -751,8 +755,6 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(!compact || ((uintptr_t)c->gact0_p8 % 16 == 0 && (uintptr_t)c->amax0_p8 % 8 == 0), "conv1 wgrad (tcgen05, TP): gact0_p8 / amax0_p8 alignment");
     BC_CHECK_ARG(c->obs_size == 4 || c->obs_size == 12, "conv1 wgrad (tcgen05, TP): obs_size 4 or 12");
     const bool window = c->x_tp_stride_n == (c->obs_size / 4) * c->x_tp_stride_c;      // the (stacked) sliding window: planes shared between samples
-    BC_CHECK_ARG(c->obs_size == 4 || (compact && window), "conv1 wgrad (tcgen05, TP), obs_size 12: needs the stacked sliding window (x_tp_stride_n == 3 * "
-                 "x_tp_stride_c, stage_frames(frame_skip=12, step=3)) and the compact gradient path (conv_mode bit 16)");
     BC_CHECK_ARG(((uintptr_t)c->x_tp % 16 == 0) && (c->x_tp_stride_n * 2) % 16 == 0 && (c->x_tp_stride_c * 2) % 16 == 0,
                  "conv1 wgrad (tcgen05, TP): x_tp and its strides must be 16 B aligned");
     // ring depths: the compact builders are fast enough that a deeper gradient ring pays (3 plane + 7 gradient slots); the f32
@@ -782,15 +784,20 @@ static int conv1_wgrad_tp_launch(const bc_ctx* c, void* stream) {
     static const bool gen2 = getenv("BC_C1WG_GEN") && atoi(getenv("BC_C1WG_GEN")) == 2;     // measurement switch: second-generation kernel
     if (compact && window && (!gen2 || c->obs_size == 12))
         return bc_conv1_wgrad3_launch(c, ar, pl, grid, stream);                                 // third generation (conv1_wgrad3.cu)
-    if (compact)
-        bc::launch_pdl(ring45 ? kc45 : kc, dim3(grid), dim3(c1wg2::NTHREADS), ring45 ? RF::SMEM_BYTES : RC::SMEM_BYTES, (cudaStream_t)stream,
-            (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const void*)c->gact0_p8, (const float*)nullptr, (const uint8_t*)c->amax0_p8,
-            c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
-    else
-        bc::launch_pdl(kf, dim3(grid), dim3(c1wg2::NTHREADS), RF::SMEM_BYTES, (cudaStream_t)stream,
-            (const __nv_bfloat16*)c->x_tp, c->x_tp_stride_n, c->x_tp_stride_c, (const void*)c->gact[0], (const float*)c->act[0], (const uint8_t*)c->amax[0],
-            c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate);
-    BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
+    const int ncam = c->obs_size == 12 ? 3 : 1;
+    const int64_t sc1 = (int64_t)ncam * c->x_tp_stride_c, sn1 = window ? sc1 : c->x_tp_stride_n;     // the camera stream's channel / sample strides
+    for (int cam = 0; cam < ncam; ++cam) {
+        const __nv_bfloat16* xc = (const __nv_bfloat16*)c->x_tp + (int64_t)cam * c->x_tp_stride_c;
+        if (compact)
+            bc::launch_pdl(ring45 ? kc45 : kc, dim3(grid), dim3(c1wg2::NTHREADS), ring45 ? RF::SMEM_BYTES : RC::SMEM_BYTES, (cudaStream_t)stream,
+                xc, sn1, sc1, (const void*)c->gact0_p8, (const float*)nullptr, (const uint8_t*)c->amax0_p8,
+                c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate, c->obs_size, ncam, cam);
+        else
+            bc::launch_pdl(kf, dim3(grid), dim3(c1wg2::NTHREADS), RF::SMEM_BYTES, (cudaStream_t)stream,
+                xc, sn1, sc1, (const void*)c->gact[0], (const float*)c->act[0], (const uint8_t*)c->amax[0],
+                c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate, c->obs_size, ncam, cam);
+        BC_CUDA_LAUNCH_CHECK("conv1_wgrad_tp_kernel");
+    }
     return BC_OK;
 }
 

@@ -110,6 +110,17 @@ def test_bf16_whole_step_obs12_matches_oracle_given_device_decisions():
     worst = {k: _rel(got[k], ref[k]) for k in O.PARAM_ORDER}
     print("obs 12, bf16 step vs f64 oracle given routing + ReLU masks:", {k: f"{v:.2e}" for k, v in worst.items()})
     assert max(worst.values()) <= REL_BF16, worst
+    # the same batch in the reference's own format, a materialised (B,12,256,256) f32 tensor: planes are not shared, the weight
+    # gradient runs on the second-generation kernel (three camera launches as well) -- same loss and gradients
+    from carla_imitation_learning_b200 import sliding_window, stage_gray
+    g_view, l_view = eng.grads.clone(), float(bufs.loss)
+    xm = sliding_window(stage_gray(torch.from_numpy(frames).to(dev)), 12, 3).contiguous()
+    bm = eng.train_forward_backward(xm, y.to(dev))
+    torch.cuda.synchronize()
+    eng.check_device_errors()
+    assert bm.x_tp_strides[0] == 12 * bm.x_tp_strides[1]
+    assert abs(float(bm.loss) - l_view) <= 1e-6 * l_view
+    assert _rel(eng.grads, g_view) <= 1e-4
 
 
 def test_obs12_adam_keeps_the_three_camera_images_current_and_modes_agree():
