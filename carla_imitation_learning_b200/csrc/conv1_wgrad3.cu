@@ -72,14 +72,17 @@ struct SegIter {
     }
 };
 
-template <typename PL>
+template <typename PL, bool CAM3>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4* __restrict__ g8, const uint2* __restrict__ a8,
                     float* __restrict__ part, int64_t seg_len, int64_t w_off, int64_t b_off, int nparts, int B, int* err, int ablate,
-                    int cin, int cstep, int coff) {
-    // (cin, cstep, coff) = (4, 1, 0): the 4-channel network. obs_size 12 (3 cameras x 4 frames): three launches over the cameras' own
+                    int cam) {
+    // the 4-channel network is CAM3 = false with compile-time (cin, cstep, coff) = (4, 1, 0) -- as runtime values they cost the
+    // builders registers (measured: 29.8 -> 32.3 us). obs_size 12 (3 cameras x 4 frames): three launches over the cameras' own
     // sliding windows (x + cam planes, plane stride 3), launch `coff` = cam fills the network's channels 3*ci + cam of every
     // partial slot; the bias gradient and the zeroing of the slots no CTA owns belong to launch 0.
+    constexpr int cin = CAM3 ? 12 : 4, cstep = CAM3 ? 3 : 1;
+    const int coff = CAM3 ? cam : 0;
     constexpr int NA = PL::NA, NDY = PL::NDY, VPAD = PL::VPAD, A_SLOT = PL::A_SLOT, OFF_A = PL::OFF_A, OFF_DY = PL::OFF_DY,
                   OFF_BAR = PL::OFF_BAR, NBAR = PL::NBAR;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -352,12 +355,14 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
 int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Partials& pl, int grid, void* stream) {
     using P47 = c1wg3::Plan<4, 7, 2048>;
     using P55 = c1wg3::Plan<5, 5, 2016>;
-    auto k47 = c1wg3::conv1_wgrad3_kernel<P47>;
-    auto k55 = c1wg3::conv1_wgrad3_kernel<P55>;
+    auto k47 = c1wg3::conv1_wgrad3_kernel<P47, false>;
+    auto k55 = c1wg3::conv1_wgrad3_kernel<P55, false>;
+    auto k47c = c1wg3::conv1_wgrad3_kernel<P47, true>;      // obs_size 12: one launch per camera
     static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k47, cudaFuncAttributeMaxDynamicSharedMemorySize, P47::SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k55, cudaFuncAttributeMaxDynamicSharedMemorySize, P55::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k47c, cudaFuncAttributeMaxDynamicSharedMemorySize, P47::SMEM_BYTES);
         if (e != cudaSuccess) return bc::fail(BC_ERR_DEVICE, "conv1 wgrad v3: smem opt-in failed: %s", cudaGetErrorString(e));
         configured = true;
     }
@@ -369,10 +374,10 @@ int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Parti
     static const bool plan55 = getenv("BC_C1WG_PLAN") && atoi(getenv("BC_C1WG_PLAN")) == 55;    // measurement switch (same results)
     const int ncam = c->obs_size == 12 ? 3 : 1;
     for (int cam = 0; cam < ncam; ++cam) {
-        bc::launch_pdl(plan55 ? k55 : k47, dim3(grid), dim3(c1wg3::NTHREADS), plan55 ? P55::SMEM_BYTES : P47::SMEM_BYTES, (cudaStream_t)stream,
+        bc::launch_pdl(ncam == 3 ? k47c : plan55 ? k55 : k47, dim3(grid), dim3(c1wg3::NTHREADS), (plan55 && ncam == 1) ? P55::SMEM_BYTES : P47::SMEM_BYTES, (cudaStream_t)stream,
             (const __nv_bfloat16*)c->x_tp + (int64_t)cam * c->x_tp_stride_c, (int64_t)ncam * c->x_tp_stride_c, (const uint4*)c->gact0_p8, (const uint2*)c->amax0_p8,
             c->partials + pl.off[4], ar.seg_len[4], ar.w[0] - ar.seg_off[4], ar.b[0] - ar.seg_off[4], grid, c->batch, c->err_flag, ablate,
-            c->obs_size, ncam, cam);
+            cam);
         BC_CUDA_LAUNCH_CHECK("conv1_wgrad3_kernel");
     }
     return BC_OK;
