@@ -152,3 +152,65 @@ def test_conv1_merged_n_mma_gives_every_sample_its_own_convolution(S):
         want = sum(A[s + ci, ky] @ Wt[ci, ky].T for ci in range(4) for ky in range(7))
         assert np.array_equal(D[:, (3 - s) * 64:(4 - s) * 64], want), s
     assert n_instr == 7 * (S + 3) + S - 1                     # vs 28 * S one-sample instructions
+
+
+def test_stacked_camera_conv_is_the_sum_of_three_four_frame_camera_streams():
+    """csrc/conv1_tc.cu (obs_size 12): with three cameras interleaved frame by frame, channel 3f + cam of sample s is plane
+    3(s + f) + cam, so camera `cam` alone is a 4-frame sliding window over planes cam, cam + 3, ... (both strides 3 planes) with
+    the weights W[:, 3f + cam], and the 12-channel convolution is the sum of the three 4-channel ones -- integer arithmetic, exact."""
+    rng = np.random.default_rng(12)
+    B, Hh, K, S = 3, 25, 7, 3
+    planes = rng.integers(-8, 9, size=(3 * (B - 1) + 12, Hh, Hh)).astype(np.int64)
+    W = rng.integers(-4, 5, size=(16, 12, K, K)).astype(np.int64)
+    ho = (Hh - K) // S + 1
+
+    def conv(x, w):            # x (C,H,H), w (16,C,K,K) -> (16,ho,ho)
+        out = np.zeros((16, ho, ho), np.int64)
+        for oy in range(ho):
+            for ox in range(ho):
+                out[:, oy, ox] = np.tensordot(w, x[:, S * oy:S * oy + K, S * ox:S * ox + K], axes=([1, 2, 3], [0, 1, 2]))
+        return out
+    for s in range(B):
+        full = conv(planes[3 * s:3 * s + 12], W)
+        acc = np.zeros_like(full)
+        for cam in range(3):
+            stream = planes[cam::3]                                  # the camera's own plane sequence
+            acc += conv(stream[s:s + 4], W[:, cam::3])               # its 4-frame window of sample s, channels 3f + cam
+        assert np.array_equal(acc, full)
+        # and the weight gradient splits the same way: dW[:, 3f + cam] is the 4-channel wgrad of camera cam's stream
+    dY = rng.integers(-3, 4, size=(B, 16, ho, ho)).astype(np.int64)
+
+    def wgrad(xs, dys):        # list of (C,H,H), (16,ho,ho) -> (16,C,K,K)
+        g = np.zeros((16, xs[0].shape[0], K, K), np.int64)
+        for x, dy in zip(xs, dys):
+            for oy in range(ho):
+                for ox in range(ho):
+                    g += dy[:, oy, ox][:, None, None, None] * x[None, :, S * oy:S * oy + K, S * ox:S * ox + K]
+        return g
+    full = wgrad([planes[3 * s:3 * s + 12] for s in range(B)], dY)
+    for cam in range(3):
+        stream = planes[cam::3]
+        assert np.array_equal(wgrad([stream[s:s + 4] for s in range(B)], dY), full[:, cam::3])
+
+
+def test_swapped_role_conv1_blocks_and_quad_exchange():
+    """csrc/conv1_fwd4.cu (BC_C1FW_GEN=4). (a) Weight image order [Z][ky: ci 3,2,1,0][Z]...: for every plane offset d = 0..4 of a
+    sample pair the 128 A rows [W(ci = d) ; W(ci = d - 1)] are two consecutive blocks, zero blocks standing in for ci = 4 and -1.
+    (b) Quad exchange: lane j of a channel's quad holds conv columns 4g + j; after rotating its three group values by
+    r0 = (3 * (3j % 4)) // 4 and shuffling from lane (3L + t) % 4, lane L holds exactly columns 3L .. 3L+2 of the 12-column period."""
+    block = lambda ky, ci: 1 + 5 * ky + (3 - ci)
+    for ky in range(7):
+        for d in range(5):
+            hi, lo = block(ky, d), block(ky, d) + 1
+            assert hi == (5 * ky if d == 4 else block(ky, d))        # ci = 4 -> the zero block in front of the kernel row
+            assert lo == (5 * (ky + 1) if d == 0 else block(ky, d - 1))   # ci = -1 -> the zero block behind it
+            assert all(b % 5 != 0 for b, c in ((hi, d), (lo, d - 1)) if 0 <= c <= 3)
+    cols = np.arange(12)                                             # one period: value = its conv column
+    V = {j: [cols[4 * g + j] for g in range(3)] for j in range(4)}   # lane j: group registers g = 0..2
+    for L in range(4):
+        got = []
+        for t in range(3):
+            src = (3 * L + t) % 4                                    # the lane asked at step t
+            r0 = (3 * ((3 * src) % 4)) // 4
+            got.append(V[src][(r0 + t) % 3])                         # what that lane sends at step t
+        assert got == [3 * L, 3 * L + 1, 3 * L + 2]
