@@ -322,23 +322,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_fwd_kernel(const FwdArgs a) {
 template <int CIN_, int COUT_, int KS_, int HIN_, int HP_>
 struct DCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, KS = KS_, HIN = HIN_, HP = HP_;
-    static constexpr int N = CIN;                           // GEMM N = input channels
+    static constexpr int N = CIN;                           // GEMM N of ONE tap = input channels
     static constexpr int CG = COUT / 8, CB = COUT / 16, NSTEP = KS * KS * CB;
-    static constexpr int WP = HIN + KS - 1;                 // padded routed-gradient image, square: conv output + (KS-1) zeros on every side
+    // padded routed-gradient image, square: conv output + (KS-1) zeros on every side, the pitch rounded up to a divisor of 128 so
+    // that a 128-row tile is whole image rows and a warp's 32 rows are whole image rows too (the Toeplitz fold below shuffles
+    // along the row)
+    static constexpr int WP = (HIN + KS - 1) <= 16 ? 16 : 32;
+    // "Toeplitz in N": the KS horizontal taps of a kernel row share ONE A operand (the window at kx' = 0); their weight blocks sit
+    // side by side in B, so one MMA of N = KS * CIN columns does what took KS instructions (an N = 16 / 32 instruction costs its
+    // A fetch, 41-43 cycles, whatever its width). Column block j holds the tap-kx' = j products of pixel m, i.e. a contribution to
+    // output pixel m - j:   dX[m] = sum_j D[m + j][block j]   -- folded by the epilogue with warp shuffles (m + j stays in the
+    // image row: valid ix < HIN and HIN + KS - 1 <= WP).
+    static constexpr int NT = KS * N;                       // columns of one Toeplitz MMA
+    static constexpr int NMMA = KS * CB;                    // MMAs per tile (one per kernel row and 16-channel block of dY)
     static constexpr int PLANE = WP * WP * 16, IMG = CG * PLANE;
     static constexpr int MROWS = HIN * WP;                  // GEMM rows per image: (iy, ix') with ix' < WP, valid ix' < HIN
     static constexpr int TPI = (MROWS + 127) / 128;
     static constexpr int B_STEP = N * 32, B_BYTES = NSTEP * B_STEP;
     static constexpr int NIMG = 2;
-    static constexpr int NACC = cmin(8, 512 / (N < 32 ? 32 : N));
-    static constexpr int ACCW = N < 32 ? 32 : N;            // TMEM columns per accumulator
+    static constexpr int ACCW = NT <= 128 ? 128 : 256;      // TMEM columns per accumulator
+    static constexpr int NACC = 512 / ACCW;
     static constexpr int OFF_B = 0;
     static constexpr int OFF_IMG = (B_BYTES + 127) / 128 * 128;
     static constexpr int OVER = ((TPI * 128 + (KS - 1) * WP + KS) * 16 > PLANE ? (TPI * 128 + (KS - 1) * WP + KS) * 16 - PLANE : 0);
     static constexpr int OFF_BAR = (OFF_IMG + NIMG * IMG + OVER + 127) / 128 * 128;
     static constexpr int NBAR = 1 + 2 * NIMG + 2 * NACC;
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
-    static_assert(WP >= 2 * HP + 2 * (KS - 1), "the pooled region plus the zero border must fit");
+    static_assert(WP >= 2 * HP + 2 * (KS - 1) && WP >= HIN + KS - 1 && 128 % WP == 0, "the pooled region plus the zero border must fit; tiles = whole rows");
+    static_assert(NT % 16 == 0 && NT <= 256, "one MMA per kernel row");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
     } else if (warp <= 3 || warp == 12) {
         // ------------------------------------------------------------------ 4 MMA issuers
         const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, C::NT, 0, 0);
         const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_IMG), C::PLANE, 128, tc05::SW_NONE);
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_B), 128, 256, tc05::SW_NONE);
         bool ok = tc05::mbar_wait(b_full, 0, err);
@@ -417,12 +428,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
                 const uint64_t a0 = ad0 + (uint64_t)((slot * C::IMG + t * 128 * 16) >> 4);
                 const uint32_t d_tmem = tmem_base + acc * C::ACCW;
 #pragma unroll
-                for (int s = 0; s < C::NSTEP; ++s) {
-                    // window shift (ky', kx') pairs with the FLIPPED kernel tap (K-1-ky', K-1-kx')
-                    const int tp = s / C::CB, cb = s % C::CB;
-                    const int wstep = (KS * KS - 1 - tp) * C::CB + cb;
-                    tc05::mma_bf16(d_tmem, a0 + (uint64_t)(((tp / KS) * WP + tp % KS) + 2 * cb * (C::PLANE >> 4)),
-                                   bd0 + (uint64_t)(wstep * (C::B_STEP >> 4)), idesc, s > 0);
+                for (int s = 0; s < C::NMMA; ++s) {
+                    // kernel row ky' of the window (the image is stored flipped: pack.cuh), 16-channel block cb of dY; the KS weight
+                    // blocks of the row follow each other in the operand image: steps (s * KS .. s * KS + KS - 1)
+                    const int kyp = s / C::CB, cb = s % C::CB;
+                    tc05::mma_bf16(d_tmem, a0 + (uint64_t)(kyp * WP + 2 * cb * (C::PLANE >> 4)),
+                                   bd0 + (uint64_t)(s * KS * (C::B_STEP >> 4)), idesc, s > 0);
                 }
                 tc05::mma_commit(t_full + acc);
             }
@@ -440,6 +451,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
         const int tb = threadIdx.x - 128;                     // 0..255
         const int ew = warp & 3;
         PooledGrad<COUT, HP> pg;
+        // 16 channels of this thread's pixel: dX[m][c] = sum_j D[m + j][j * N + c] (fixed order j = 0..KS-1); row m + j is lane + j of the
+        // same warp (whole image rows per warp; the lanes that would reach past it are the row's padding, never stored)
+        auto fold16 = [&](uint32_t taddr, float* v) {
+            float tj[16];
+            tc05::tmem_ld16(taddr, v);
+#pragma unroll
+            for (int j = 1; j < KS; ++j) {
+                tc05::tmem_ld16(taddr + j * N, tj);
+                tc05::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __shfl_down_sync(0xffffffffu, tj[i], j);
+            }
+            tc05::tmem_ld_wait();
+        };
         auto build = [&](int bimg, uint32_t kimg, int bnext) -> bool {      // pg holds image bimg; fetches bnext (if >= 0) afterwards
             const uint32_t slot = kimg % NIMG;
             if (!tc05::mbar_wait(img_empty + slot, ((kimg / NIMG) & 1) ^ 1, err)) return false;
@@ -472,23 +497,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
             const uint32_t acc = c % NACC, par = (use >> acc) & 1;
             use ^= 1u << acc;
             if (warp >= 8) continue;                          // warps 8-11 only build
-            ok = ok && tc05::mbar_wait(t_full + acc, par, err);
-            if (!ok) break;
-            tc05::tc_fence_after();
             const int m = t * 128 + ew * 32 + lane;           // GEMM row inside the image
             const int iy = m / WP, ix = m % WP;
             const bool valid = m < C::MROWS && ix < HIN;
+            uint4 avp[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if constexpr (N == 16) {
+                // compact path: the activation words that mask this pixel's gradient do not depend on the accumulator --
+                // fetched before the wait, so their latency is not paid per tile behind it
+                if (a.gin_p8 && valid) {
+#pragma unroll
+                    for (int cg = 0; cg < 2; ++cg)
+                        avp[cg] = __ldg(reinterpret_cast<const uint4*>(a.act_in_p8) + ((size_t)b * 2 + cg) * (HIN * HIN) + iy * HIN + ix);
+                }
+            }
+            ok = ok && tc05::mbar_wait(t_full + acc, par, err);
+            if (!ok) break;
+            tc05::tc_fence_after();
             if constexpr (N == 16) {
                 if (a.gin_p8) {
                     // compact path: one pixel x 16 channels per thread = two 16 B stores, masked by the bf16 activation
                     float v[16];
-                    tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW, v);
-                    tc05::tmem_ld_wait();
+                    fold16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW, v);
                     if (valid) {
 #pragma unroll
                         for (int cg = 0; cg < 2; ++cg) {
                             const size_t idx = ((size_t)b * 2 + cg) * (HIN * HIN) + iy * HIN + ix;
-                            const uint4 av = __ldg(reinterpret_cast<const uint4*>(a.act_in_p8) + idx);
+                            const uint4 av = avp[cg];
                             const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
                             uint32_t o[4];
 #pragma unroll
@@ -510,8 +544,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
 #pragma unroll
             for (int c0 = 0; c0 < N; c0 += 16) {
                 float v[16];
-                tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW + c0, v);
-                tc05::tmem_ld_wait();
+                fold16(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * C::ACCW + c0, v);
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) a.gin[(((size_t)b * N + c0 + j) * HIN + iy) * HIN + ix] = v[j];

@@ -58,8 +58,11 @@ __device__ __forceinline__ void pack_src_elem(float w, __nv_bfloat16* __restrict
         const int sidx = tap * C::CB + (ci >> 4), k = ci & 15;
         fwd[(size_t)sidx * (C::B_STEP / 2) + op_off(co, k >> 3) / 2 + (k & 7)] = v;
     }
-    {   // dgrad: step (tap, co/16), row ci, k = co%16
-        const int sidx = tap * D::CB + (co >> 4), k = co & 15;
+    {   // dgrad: row ci, k = co%16. conv2 / conv3 (conv_sw.cu, "Toeplitz in N"): the image is stored FLIPPED and with the taps of a
+        // kernel row adjacent -- step ((KS-1-ky) * CB + co/16) * KS + (KS-1-kx) -- so that one MMA reads the KS weight blocks of a
+        // window row as N = KS * CIN consecutive rows; conv4 (conv4_sw.cu) keeps step (tap, co/16)
+        const int ky = tap / C::KS, kx = tap % C::KS, k = co & 15;
+        const int sidx = C::KS >= 4 ? ((C::KS - 1 - ky) * D::CB + (co >> 4)) * C::KS + (C::KS - 1 - kx) : tap * D::CB + (co >> 4);
         dgr[(size_t)sidx * (D::B_STEP / 2) + op_off(ci, k >> 3) / 2 + (k & 7)] = v;
     }
 }

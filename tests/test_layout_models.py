@@ -214,3 +214,37 @@ def test_swapped_role_conv1_blocks_and_quad_exchange():
             r0 = (3 * ((3 * src) % 4)) // 4
             got.append(V[src][(r0 + t) % 3])                         # what that lane sends at step t
         assert got == [3 * L, 3 * L + 1, 3 * L + 2]
+
+
+@pytest.mark.parametrize("hin,ks,wp", [(28, 5, 32), (12, 4, 16)])
+def test_dgrad_toeplitz_in_n_fold(hin, ks, wp):
+    """csrc/conv_sw.cu dgrad, "Toeplitz in N": per window row ky' ONE product of the padded gradient at kx' = 0 with the KS flipped
+    weight blocks side by side; block j of pixel m is a contribution to pixel m - j, so dX[m] = sum_j D[m + j][block j], and m + j
+    never leaves the image row of a valid pixel (pitch wp >= hin + ks - 1, 128 % wp == 0: tiles and warps are whole rows)."""
+    rng = np.random.default_rng(hin)
+    cin, cout, ho = 3, 2, hin - ks + 1
+    dy = rng.integers(-3, 4, size=(cout, ho, ho)).astype(np.int64)
+    W = rng.integers(-3, 4, size=(cout, cin, ks, ks)).astype(np.int64)
+    # direct definition: dX[ci][iy][ix] = sum dY[co][iy-ky][ix-kx] W[co][ci][ky][kx]
+    want = np.zeros((cin, hin, hin), np.int64)
+    for ky in range(ks):
+        for kx in range(ks):
+            want[:, ky:ky + ho, kx:kx + ho] += np.einsum("oyx,oc->cyx", dy, W[:, :, ky, kx])
+    # kernel: padded gradient (ks-1 zeros around), linear pixel index with pitch wp
+    pad = np.zeros((cout, wp + ks, wp), np.int64)
+    pad[:, ks - 1:ks - 1 + ho, ks - 1:ks - 1 + ho] = dy
+    lin = pad.reshape(cout, -1)
+    nrows = hin * wp
+    D = np.zeros((nrows + ks, ks, cin), np.int64)              # accumulator rows x column blocks
+    for kyp in range(ks):
+        A = lin[:, kyp * wp: kyp * wp + nrows + ks].T          # row m = gradient pixel m + ky' wp (window column 0)
+        for j in range(ks):                                     # block j = flipped tap (ks-1-ky', ks-1-j)
+            D[:, j] += A @ W[:, :, ks - 1 - kyp, ks - 1 - j]
+    got = np.zeros_like(want)
+    for iy in range(hin):
+        for ix in range(hin):
+            m = iy * wp + ix
+            assert (m + ks - 1) // wp == iy and (m % 32) + ks - 1 < 32          # the fold stays in the row and in the warp
+            got[:, iy, ix] = sum(D[m + j, j] for j in range(ks))
+    assert np.array_equal(got, want)
+    assert 128 % wp == 0 and wp >= hin + ks - 1
