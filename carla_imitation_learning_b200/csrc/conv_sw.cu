@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ warps 4-11: build dYp of every image, warps 4-7 then drain the tiles
+        // ------------------------------------------------------------------ warps 4-11: build dYp of every image and drain the tiles (two groups, alternate tiles)
         // Building is interleaved with the epilogue in program order: before the epilogue of the first tile of image
         // k the builders have already produced image k+1 (NIMG = 2), so the issuers never wait for a gradient image.
         const int tb = threadIdx.x - 128;                     // 0..255
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
             const uint32_t c = cnt++;
             const uint32_t acc = c % NACC, par = (use >> acc) & 1;
             use ^= 1u << acc;
-            if (warp >= 8) continue;                          // warps 8-11 only build
+            if ((c & 1u) != (warp >= 8 ? 1u : 0u)) continue;  // both builder groups drain: warps 4-7 the even tiles, warps 8-11 the odd ones
             const int m = t * 128 + ew * 32 + lane;           // GEMM row inside the image
             const int iy = m / WP, ix = m % WP;
             const bool valid = m < C::MROWS && ix < HIN;
