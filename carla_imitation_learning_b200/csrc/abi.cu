@@ -56,6 +56,9 @@ __global__ void adam_tick_kernel(double* st) {
 __device__ __forceinline__ void adam_scalars(const double* st, double* s_sc) {
     const double step = st[4] + 1.0;
     s_sc[0] = step;
+#ifdef BC_ADAM_NOPOW      // timing experiment only (wrong bias corrections): what the two f64 pow cost at the head of the kernel
+    s_sc[1] = st[0]; s_sc[2] = 1.0; return;
+#endif
     s_sc[1] = st[0] / (1.0 - pow(st[1], step));
     s_sc[2] = sqrt(1.0 - pow(st[2], step));
 }
