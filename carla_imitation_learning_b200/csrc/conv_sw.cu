@@ -560,6 +560,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
     if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);
 }
 
+#ifndef BC_WGRAD_M64
+#define BC_WGRAD_M64 1
+#endif
 // ================================================================================================ wgrad
 //   dW[co][ci][ky][kx] = sum_{b, m = oy*W_in + ox}  X[b][m + ky*W_in + kx][ci] * dY[b][m][co]
 // Both operands MN-major, K = pixels m (16 per instruction). The A operand of (ky, 8-channel group cg) is the input
@@ -581,6 +584,7 @@ struct WCfg {
     static constexpr int NIMG = 2;
     static constexpr int ACCW = COUT < 32 ? 32 : COUT;
     static constexpr int NACC = CG;
+    static constexpr int MMA_M = (KS <= 8 && BC_WGRAD_M64) ? 64 : 128;
     static constexpr int OFF_X = 0;
     static constexpr int XSLOT = (XIMG + 1023) / 1024 * 1024;
     static constexpr int OFF_XPAD = OFF_X + NIMG * XSLOT;   // over-read of the shifted windows of the last plane
@@ -655,7 +659,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
     } else if (warp <= 3 || warp == 12) {
         // ------------------------------------------------------------------ issuer w owns the accumulators acc % 4 == w (acc = cg)
         const int w = warp == 12 ? 0 : warp;
-        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, COUT, 1, 1);
+        // M = 64: 8 pixel shifts x 8 channels (KS <= 8 of them real) -- an M = 64 instruction costs 31.9 / 35.9 cycles at N = 32 / 64
+        // against 41.7 / 48.6 for M = 128 (tools/mma_bench.py), and half of the M = 128 rows were shifts nobody reads
+        constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, C::MMA_M, COUT, 1, 1);
         const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_X), 128, 16, tc05::SW_NONE);       // M-cores = pixel shifts
         const uint64_t bd0 = tc05::smem_desc(tc05::smem_u32(smem + C::OFF_D), 128, C::DPLANE, tc05::SW_NONE);
         bool ok = true, first = true;
@@ -740,7 +746,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
         {
             const bool any = b_hi > b_lo;
             if (okd) {
-                const int row = ew * 32 + lane, kx = row >> 3, ci8 = row & 7;
+                // M = 64 accumulators sit in lanes 0..15 of every 32-lane quadrant: row = 16 * quadrant + lane
+                const int row = C::MMA_M == 64 ? (lane < 16 ? ew * 16 + lane : 127) : ew * 32 + lane, kx = row >> 3, ci8 = row & 7;
 #pragma unroll 1
                 for (int acc = 0; acc < C::NACC; ++acc) {
 #pragma unroll 1
