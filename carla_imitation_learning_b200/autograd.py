@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .engine import StagedBatch, _stream_ptr
+from .engine import on_device, StagedBatch, _stream_ptr
 
 
 def _param_grads(net, flat: torch.Tensor):
@@ -129,7 +129,7 @@ class FusedStepFunction(torch.autograd.Function):
         g = gloss.reshape(1)
         if g.dtype != torch.float32:
             g = g.float()
-        with torch.cuda.device(eng.device):
+        with on_device(eng.device):
             _lib.check(eng.lib.bc_scale_inplace(flat.data_ptr(), flat.numel(), g.data_ptr(), _stream_ptr()), "bc_scale_inplace")
         for p, v in zip(net._ordered_params, views):
             if p.grad is None:

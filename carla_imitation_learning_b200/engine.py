@@ -7,6 +7,7 @@ numeric op is a call into libbc_b200.so. PyTorch provides device memory and stre
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -19,8 +20,24 @@ ACT_SHAPES = ((16, 28, 28), (32, 12, 12), (64, 4, 4), (128, 1, 1))
 H = W = 256
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr() -> int:
+    """cudaStream_t of the current stream of the current device. The raw getter skips building a torch.cuda.Stream object:
+    the module path is host-bound once the device step is shorter than the Python loop (tools/module_host_profile.py)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def on_device(dev: torch.device):
+    """`with torch.cuda.device(dev)` when another device is current, nothing otherwise (the context manager costs ~10 us of
+    Python per use; one process per GPU means the device is already current in every hot call)."""
+    return _NO_SWITCH if dev.index is None or torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -384,7 +401,7 @@ class BCEngine:
         if self._side is None:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("create the engine's side stream before capturing (run one eager step first)")
-            with torch.cuda.device(self.device):
+            with on_device(self.device):
                 side = torch.cuda.Stream(self.device)
                 evs = [torch.cuda.Event() for _ in range(4)]
                 for e in evs:
@@ -403,7 +420,7 @@ class BCEngine:
         c = _lib.BcCtx()
         c.obs_size, c.n_actions = self.obs_size, self.n_actions
         c.params, c.w_packed = self.arena.data_ptr(), self.w_packed.data_ptr()
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _lib.check(self.lib.bc_pack_weights(C.byref(c), _stream_ptr()), "bc_pack_weights")
         self._packed_version = self.weights_version()
 
@@ -441,7 +458,7 @@ class BCEngine:
         b = self.alloc(x.shape[0], x, y, backward)
         c = self.ctx(b, loss_scale)
         s = _stream_ptr()
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             for layer in range(4):
                 _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
             _lib.check(self.lib.bc_head(C.byref(c), 1 if y is not None else 0, s), "head forward")
@@ -453,7 +470,7 @@ class BCEngine:
         """Gradients of every parameter from b.dlogits (already holding d loss / d logits). Returns self.grads."""
         self._alloc_bwd(b)
         c = self.ctx(b, loss_scale)
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             _lib.check(self.lib.bc_backward(C.byref(c), 0, _stream_ptr()), "bc_backward")
         return self.grads
 
@@ -477,7 +494,7 @@ class BCEngine:
         self._check_labels(b)
         c = self.ctx(b, loss_scale)
         s = _stream_ptr()
-        with torch.cuda.device(self.device):
+        with on_device(self.device):
             for layer in range(4):   # the head's forward is fused into bc_backward's first launch
                 _lib.check(self.lib.bc_conv_relu_pool_fwd(C.byref(c), layer, s), f"conv{layer + 1} forward")
             if self.overlap or dp_split:

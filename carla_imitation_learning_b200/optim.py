@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .engine import _stream_ptr
+from .engine import on_device, _stream_ptr
 
 # state vector layout (csrc/abi.cu), f64: lr beta1 beta2 eps step grad_scale step_size bc2_sqrt
 _LR, _B1, _B2, _EPS, _STEP, _GS, _SS, _BC2 = range(8)
@@ -144,7 +144,7 @@ class FusedAdam(torch.optim.Optimizer):
             self._sync_scalars(st)
         wp, obs, na = self._packed()
         lib, s = _lib.lib(), _stream_ptr()
-        with torch.cuda.device(arena.device):
+        with on_device(arena.device):
             _lib.check(lib.bc_adam_tick_step(arena.data_ptr(), flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
                                              st.data_ptr(), arena.numel(), wp, obs, na, s), "bc_adam_tick_step")
 
@@ -158,7 +158,7 @@ class FusedAdam(torch.optim.Optimizer):
         wp, obs, na = self._packed()
         lib = _lib.lib()
         s = _stream_ptr() if stream is None else stream
-        with torch.cuda.device(arena.device):
+        with on_device(arena.device):
             _lib.check(lib.bc_adam_step_exchange(arena.data_ptr(), m.data_ptr(), v.data_ptr(), st.data_ptr(), arena.numel(),
                                                  peer.c_struct, lo, arena.numel() if hi is None else hi, bucket, int(publish),
                                                  wp, obs, na, s), "bc_adam_step_exchange")

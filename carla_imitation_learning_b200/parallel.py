@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .engine import on_device
 
 
 def grad_buckets(obs_size: int, n_actions: int) -> List[Tuple[int, int]]:
@@ -134,7 +135,7 @@ class PeerExchangeStep:
             main = torch.cuda.current_stream(eng.device)
             opt.step_exchange(peer, lo0, hi0, bucket=0, publish=False, stream=side.cuda_stream)   # under conv1's wgrad
             c = eng.ctx(self._bufs)
-            with torch.cuda.device(eng.device):
+            with on_device(eng.device):
                 _lib.check(eng.lib.bc_reduce_partials_range(C.byref(c), 4, 5, 0, main.cuda_stream), "reduce [conv1]")
             evs[3].record(side)
             main.wait_event(evs[3])
@@ -195,12 +196,12 @@ class DataParallelStep:
 
     # the step as three kernel segments; the exchange is launched between them
     def _seg_a(self, bufs, loss_scale=None) -> None:
-        from .engine import _stream_ptr
+        from .engine import on_device, _stream_ptr
         eng, lib = self.eng, self.eng.lib
         c = eng.ctx(bufs, loss_scale)
         s, ref = _stream_ptr(), None
         ref = C.byref(c)
-        with torch.cuda.device(eng.device):
+        with on_device(eng.device):
             for layer in range(4):
                 _lib.check(lib.bc_conv_relu_pool_fwd(ref, layer, s), "conv forward")
             _lib.check(lib.bc_head(ref, 3, s), "head")
@@ -213,7 +214,7 @@ class DataParallelStep:
         from .engine import _stream_ptr
         eng, lib = self.eng, self.eng.lib
         c = eng.ctx(bufs, loss_scale)
-        with torch.cuda.device(eng.device):
+        with on_device(eng.device):
             _lib.check(lib.bc_conv_bwd_wgrad(C.byref(c), 0, _stream_ptr()), "conv1 wgrad")
             _lib.check(lib.bc_reduce_partials_range(C.byref(c), 4, 5, 0, _stream_ptr()), "reduce [conv1]")
 

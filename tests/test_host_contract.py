@@ -149,3 +149,20 @@ def test_imitation_aux_and_raw_segment_mirror_the_reference_contract():
     assert str(g["raw_segment_error"]) == "TypeError"
     with pytest.raises(IndexError):       # one-column labels: the reference indexes y[:, 1]
         M.lossCriterion(model, None, [torch.zeros(2, 4, 256, 256), torch.zeros(2, dtype=torch.int64)])
+
+
+def test_stacked_camera_window_is_a_view_with_the_channel_order_frame_major():
+    """BASELINE configs[3] on the host side: planes of 3 cameras interleaved frame by frame; sliding_window(frame_skip=12, step=3)
+    gives sample i = planes [3i, 3i+12) without a copy, channel 3*f + cam = frame i+f of camera cam; StagedBatch reports the same shape."""
+    from carla_imitation_learning_b200 import StagedBatch, sliding_window
+    B, h = 5, 4
+    planes = torch.arange(3 * (B + 4) * h * h, dtype=torch.float32).reshape(3 * (B + 4), h, h)
+    x = sliding_window(planes, frame_skip=12, step=3)
+    assert tuple(x.shape) == (B, 12, h, h) and x.data_ptr() == planes.data_ptr()
+    assert x.stride(0) == 3 * h * h and x.stride(1) == h * h
+    for i in (0, 2, B - 1):
+        for f in range(4):
+            for cam in range(3):
+                assert torch.equal(x[i, 3 * f + cam], planes[3 * (i + f) + cam])
+    sb = StagedBatch(torch.empty((3 * (B + 4), 8)), None, 12, 3)
+    assert sb.shape == (B, 12, 256, 256) and StagedBatch(torch.empty((B + 4, 8))).shape == (B, 4, 256, 256)
