@@ -30,6 +30,18 @@
 
 namespace c1wg3 {
 
+#ifdef BC_TRACE      // timeline of one CTA (tools/c1wg3_trace.py): per warp a list of (event << 56 | id << 40 | cycles since the CTA started)
+__device__ unsigned long long g_trace[16][1024];
+__device__ int g_trace_cta = 0;
+#define TRACE_DECL uint32_t tr_n = 0; const bool tr_on = (int)blockIdx.x == g_trace_cta && lane == 0;
+#define TRACE(ev, id) do { if (tr_on && tr_n < 1023) g_trace[warp][tr_n++] = ((unsigned long long)(ev) << 56) | ((unsigned long long)((id) & 0xffff) << 40) | (unsigned long long)((clock64() - tr_t0) & 0xffffffffffull); } while (0)
+#define TRACE_END do { if (tr_on) g_trace[warp][tr_n] = ~0ull; } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(ev, id) do {} while (0)
+#define TRACE_END do {} while (0)
+#endif
+
 constexpr int NG = 21, TILES_PER_FRAME = 14;
 constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, warps 1-3 and 12 issuers, warps 4-7 / 8-11 builder groups (both fold in the epilogue)
 constexpr int ROWB = 336;
@@ -111,8 +123,14 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef BC_TRACE
+    const long long tr_t0 = clock64();
+#endif
+    TRACE_DECL
+    TRACE(0, 0);
     tc05::pdl_trigger();
     tc05::pdl_wait();
+    TRACE(10, 0);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: 14 bulk copies per job, one per lane
@@ -133,6 +151,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
                     if (lane == 0) tc05::mbar_arrive(a_full + slot);
                     continue;
                 }
+                TRACE(1, k);
                 if (lane == 0) tc05::mbar_expect_tx(a_full + slot, 14 * VIEW);
                 __syncwarp();
                 if (lane < 14) tc05::bulk_g2s(dst + dst_off, src + src_off, VIEW, a_full + slot);
@@ -164,6 +183,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
                 if (v_lo) ok = ok && tc05::mbar_wait(dy_full + d_lo, (kb_lo / NDY) & 1, err);
                 if (v_hi) ok = ok && tc05::mbar_wait(dy_full + d_hi, (kb_hi / NDY) & 1, err);
                 tc05::tc_fence_after();
+                TRACE(3, k);
                 if (ok && tc05::elect_one()) {
                     const uint64_t a_st = ad0 + (uint64_t)((slot * A_SLOT) >> 4);
                     const uint64_t b_lo = bd0 + (uint64_t)((d_lo * DY_BYTES) >> 4);      // the older sample's slot; the newer one is the
@@ -191,6 +211,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
                     if (v_hi) tc05::mma_commit(dy_empty + d_hi);
                 }
                 __syncwarp();
+                TRACE(4, k);
                 f_hi = f_hi && !v_hi;
                 f_lo = f_lo && !v_lo;
             }
@@ -264,8 +285,10 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
 #pragma unroll 1
         for (uint32_t n = 0; ok && cur.valid; ++n) {
             const uint32_t slot = cur.kb % NDY;
+            TRACE(5, cur.kb);
             ok = tc05::mbar_wait(dy_empty + slot, ((cur.kb / NDY) & 1) ^ 1, err);
             if (!ok) break;
+            TRACE(6, cur.kb);
             uint8_t* dy = smem + OFF_DY + slot * DY_BYTES;
             // a (sample, tile) is counted once for the bias gradient: by the CTA that owns the job in which it is channel role 0
             const bool cb = cur.smp >= cur.sg.Pa && cur.smp <= cur.sg.Pb;
@@ -281,6 +304,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
                     for (int i = uses; i < 4; ++i) tc05::mbar_arrive(dy_empty + slot);
                 }
             }
+            TRACE(7, cur.kb);
             if (!(ablate & 8)) { if (n & 1) fetch(gb, ab, ahead); else fetch(ga, aa, ahead); }   // the set just stored is free: load two group-builds ahead (ablate bit 3: no gradient loads)
             cur.step_group();
             if (ahead.valid) ahead.step_group();
@@ -293,7 +317,9 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
             for (int s2 = blockIdx.x + gridDim.x; s2 < nparts; s2 += gridDim.x)
                 for (int i = te; i < nw + 16; i += 128) part[(size_t)s2 * seg_len + (i < nw ? w_off + i : b_off + i - nw)] = 0.f;
         }
+        TRACE(8, 0);
         const bool fin = ok && tc05::mbar_wait(done, 0, err);
+        TRACE(9, 0);
         if (fin && !(ablate & 16)) {              // ablate bit 4: no epilogue
             tc05::tc_fence_after();
             const int ky = 2 * ew + (lane >> 4), p = lane & 15;     // accumulator row m = ky*16 + p
@@ -335,21 +361,39 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
             for (int q = 0; q < 8; ++q) scratch[(grp * 112 + te) * 8 + q] = bsum[q];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (fin && coff == 0 && grp == 0 && te < 16) {
-            const int cg = te >> 3, q = te & 7;
+        if (fin && coff == 0 && grp == 0) {
+            // 16 channels x 112 partial sums each (2 groups x 56 units of the channel's group). Eight threads per channel take 14 values
+            // each in a fixed order and meet in a fixed xor tree -- the CTA timeline (profiles/r2U) showed the earlier version, one thread
+            // per channel walking all 224 scratch rows, as a 7 us serial tail of the kernel
+            const int ch = te >> 3, part = te & 7, cg = ch >> 3, q = ch & 7;
             float a = 0.f;
-            for (int g2 = 0; g2 < 2; ++g2)
-                for (int u = 0; u < 112; ++u)
-                    if (((u / 28) & 1) == cg) a += scratch[(g2 * 112 + u) * 8 + q];
-            dst[b_off + te] = a;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+                const int v = part + 8 * i, g2 = v / 56, w = v % 56;
+                const int u = (w / 28) * 56 + 28 * cg + w % 28;
+                a += scratch[(g2 * 112 + u) * 8 + q];
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            if (part == 0) dst[b_off + ch] = a;
         }
     }
+    TRACE(11, 0);
+    TRACE_END;
     tc05::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace c1wg3
+
+#ifdef BC_TRACE
+extern "C" int bc_debug_c1wg3_trace(unsigned long long* host_out, int cta) {     // debug builds only: not part of the ABI
+    if (host_out == nullptr) return cudaMemcpyToSymbol(c1wg3::g_trace_cta, &cta, sizeof(int)) == cudaSuccess ? 0 : -1;
+    return cudaMemcpyFromSymbol(host_out, c1wg3::g_trace, sizeof(unsigned long long) * 16 * 1024) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // sliding-window batch + compact gradient inputs (bc_ctx.conv_mode bit 16); everything else: conv1_tc.cu's kernel
 int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Partials& pl, int grid, void* stream) {

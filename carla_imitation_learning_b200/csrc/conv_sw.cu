@@ -735,10 +735,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
                     for (int q = 0; q < 8; ++q) bs[(cg * 8 + q) * (HP * HP) + wl] = bsum[j][q];
                 }
             asm volatile("bar.sync 3, 256;" ::: "memory");
-            if (tb < COUT) {
+            {
+                // 256 / COUT threads per channel, each a fixed stride of the channel's HP*HP pixel sums, met in a fixed xor tree
+                // (one thread per channel walking 144 values was a 2 us serial tail of the ky = 0 CTAs)
+                constexpr int TPC = 256 / COUT;
+                const int ch = tb / TPC, part = tb % TPC;
                 float acc = 0.f;
-                for (int i = 0; i < HP * HP; ++i) acc += bs[tb * (HP * HP) + i];
-                dst[a.b_off + tb] = acc;
+                for (int i = part; i < HP * HP; i += TPC) acc += bs[ch * (HP * HP) + i];
+#pragma unroll
+                for (int o = 1; o < TPC; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (part == 0) dst[a.b_off + ch] = acc;
             }
         }
         if (warp >= 8) goto fin;
