@@ -28,8 +28,8 @@ FLOPS_FWD = (44255232, 14745600, 5308416, 589824)          # SURVEY 8(d), per fr
 FLOPS_TRAIN = 150505152
 FRAME_BYTES = 256 * 256 * 3
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B=256 from the `ncu --set full` captures under profiles/
-TRAFFIC = {"conv1_fwd": 45459712,      # profiles/r1i_ncu_full_conv1_tp_raw.csv
-           "conv1_wgrad": 73400000}    # profiles/r1g_ncu_full_conv1_sw_stage_raw.csv (71.0 MB read + 2.4 MB written)
+TRAFFIC = {"conv1_fwd": 45933056,      # dram read + write per launch, profiles/r2P_ncu_full_raw.csv (44.81 MB + 1.12 MB)
+           "conv1_wgrad": 54615552}    # same capture: 54.38 MB read (44.9 MB of planes, 1.21x) + 0.24 MB written
 
 
 def load_peaks():
@@ -454,7 +454,7 @@ def run_b200(args):
         conv_k = {k: v for k, v in breakdown.items() if k.startswith("conv")}
         dom = max(conv_k, key=conv_k.get)                      # the longest kernel of the step
         names = {"conv1_fwd": "conv1_tp_kernel (tcgen05 Toeplitz implicit GEMM + ReLU + pool3, bf16)",
-                 "conv1_wgrad": "conv1_wgrad_tp_kernel (tcgen05, plane-regrouped Toeplitz wgrad, bf16)"}
+                 "conv1_wgrad": "conv1_wgrad3_kernel (tcgen05, plane-regrouped Toeplitz wgrad, bf16)"}
 
         def tensor_roofline(k):
             fl = FLOPS_FWD[int(k[4]) - 1] * B                  # fwd = dgrad = wgrad FLOPs per layer
@@ -486,6 +486,7 @@ def run_b200(args):
             "gpu_launches": 15 * args.steps,
             "roofline": roof,
             "roofline_conv1_fwd": tensor_roofline("conv1_fwd"),
+            "roofline_conv1_wgrad": tensor_roofline("conv1_wgrad"),
             "roofline_hbm": {"kernel": ("stage_gray_tp_kernel" if args.mode == "bf16" else "stage_gray_kernel"), "bound": "hbm", "achieved": stage_bytes / (stage_ms * 1e-3) / 1e9,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": stage_bytes / (stage_ms * 1e-3) / 1e9 / peaks["hbm"],
                              "bytes_per_launch": stage_bytes, "kernel_ms": stage_ms,
