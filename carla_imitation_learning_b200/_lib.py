@@ -99,7 +99,7 @@ _lib = None
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into libbc_b200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("bc_common.cuh", "tc05.cuh", "pack.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("bc_common.cuh", "tc05.cuh", "pack.cuh", "trace.cuh")] + [os.path.join(os.path.dirname(HERE), "include", "bc_b200.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")

@@ -23,20 +23,10 @@
 #include "bc_common.cuh"
 #include "tc05.cuh"
 #include "pack.cuh"
+#include "trace.cuh"
 
 namespace c1f4 {
 
-#ifdef BC_TRACE      // timeline of one CTA (tools/c1f4_trace.py): per warp a list of (event << 56 | id << 40 | cycles since the CTA started)
-__device__ unsigned long long g_trace[16][768];
-__device__ int g_trace_cta = 0;
-#define TRACE_DECL uint32_t tr_n = 0; const bool tr_on = (int)blockIdx.x == g_trace_cta && lane == 0;
-#define TRACE(ev, id) do { if (tr_on && tr_n < 768) g_trace[warp][tr_n++] = ((unsigned long long)(ev) << 56) | ((unsigned long long)((id) & 0xffff) << 40) | (unsigned long long)((clock64() - tr_t0) & 0xffffffffffull); } while (0)
-#define TRACE_END do { if (tr_on && tr_n < 768) g_trace[warp][tr_n] = ~0ull; } while (0)
-#else
-#define TRACE_DECL
-#define TRACE(ev, id) do {} while (0)
-#define TRACE_END do {} while (0)
-#endif
 
 constexpr int NG = 21;                       // groups of 4 output columns per conv row
 constexpr int TILES_PER_FRAME = 14;          // tile = 6 conv rows x 84 columns of one frame (= 2 pooled rows)
@@ -108,9 +98,7 @@ conv1_fwd4_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, c
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-#ifdef BC_TRACE
-    const long long tr_t0 = clock64();
-#endif
+    TRACE_T0
     TRACE_DECL
     tc05::pdl_trigger();
     tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
@@ -330,12 +318,7 @@ conv1_fwd4_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, c
 
 }  // namespace c1f4
 
-#ifdef BC_TRACE
-extern "C" int bc_debug_c1f4_trace(unsigned long long* host_out, int cta) {     // debug builds only: not part of the ABI
-    if (host_out == nullptr) return cudaMemcpyToSymbol(c1f4::g_trace_cta, &cta, sizeof(int)) == cudaSuccess ? 0 : -1;
-    return cudaMemcpyFromSymbol(host_out, c1f4::g_trace, sizeof(unsigned long long) * 16 * 768) == cudaSuccess ? 0 : -1;
-}
-#endif
+BC_TRACE_EXPORT(bc_debug_c1f4_trace)       // debug builds only: not part of the ABI
 
 int bc_conv1_fwd4_launch(const bc_ctx* c, void* stream) {
     static bc::PerDeviceOnce once_; bool& configured = once_();

@@ -18,6 +18,7 @@
 #include "bc_common.cuh"
 #include "tc05.cuh"
 #include "pack.cuh"
+#include "trace.cuh"
 
 namespace c1tc {
 
@@ -123,8 +124,12 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TRACE_T0
+    TRACE_DECL
+    TRACE(0, 0);
     tc05::pdl_trigger();
-    tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
+    tc05::pdl_wait();
+    TRACE(10, 0);                    // everything above overlapped the previous kernel's tail; global memory from here on
     if (threadIdx.x >= 128 && threadIdx.x < 144) reinterpret_cast<float*>(smem + OFF_BIAS)[threadIdx.x - 128] = bias[threadIdx.x - 128];
     if (warp >= 4 && warp < 12) asm volatile("bar.sync 3, 256;" ::: "memory");   // the epilogue warps read the bias from smem
 
@@ -152,6 +157,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                         if (lane == 0) tc05::mbar_arrive(slot_full + slot);
                         continue;
                     }
+                    TRACE(1, k);
                     if (lane == 0) tc05::mbar_expect_tx(slot_full + slot, SLOT_BYTES);
                     __syncwarp();
                     if (lane < 6)
@@ -203,6 +209,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                     tc05::tc_fence_after();
                 }
                 const int done_s = j - 3;                  // the sample whose last channel this plane is
+                TRACE(3, k);
                 if (ok && tc05::elect_one()) {
                     const uint64_t so = (uint64_t)((slot * SLOT_BYTES) >> 4);
                     const int n = s_hi - s_lo + 1, ci_lo = j - s_hi;
@@ -226,6 +233,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                     if (done_s >= 0 && done_s < S) tc05::mma_commit(t_full + set * 4 + done_s);
                 }
                 __syncwarp();
+                TRACE(4, k);
                 if (done_s >= 0 && done_s < S) use ^= 1u << (set * 4 + done_s);
             }
             ++iter;
@@ -251,9 +259,11 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 const uint32_t par = (use >> idx) & 1;
                 use ^= 1u << idx;
                 if ((int)(cnt & 1) != eg) continue;
+                TRACE(5, cnt);
                 ok = tc05::mbar_wait(t_full + idx, par, err);
                 if (!ok) break;
                 tc05::tc_fence_after();
+                TRACE(6, cnt);
                 float v[64];
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 16) tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + col + c0, v + c0);
@@ -261,6 +271,7 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 tc05::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(t_empty + idx);   // accumulator drained
+                TRACE(7, cnt);
                 if constexpr (ADD_IN || RAW_OUT) {
                     if (r < MROWS) {
                         float4* a4 = reinterpret_cast<float4*>(acc + (((size_t)(b0 + s) * TILES_PER_FRAME + ty) * MROWS + r) * 64);
@@ -332,10 +343,13 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
                 // the tile is 56 consecutive pixels of each of the two 8-channel planes
                 if (ybf && te < 112)
                     reinterpret_cast<uint4*>(ybf)[((size_t)b * 2 + te / 56) * 784 + 2 * ty * 28 + te % 56] = reinterpret_cast<const uint4*>(P_)[te];
+                TRACE(8, cnt);
                 // S_ and P_ are rewritten only after the next tile's first barrier, which every thread reaches after this store
             }
         }
     }
+    TRACE(11, 0);
+    TRACE_END;
     tc05::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc05::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -675,6 +689,8 @@ fin:
 }
 
 }  // namespace c1wg2
+
+BC_TRACE_EXPORT(bc_debug_c1tc_trace)       // debug builds only: not part of the ABI
 
 extern "C" int bc_pack_weights(const bc_ctx* c, void* stream) {
     BC_CHECK_ARG(c && c->params && c->w_packed, "bc_pack_weights: null buffer");

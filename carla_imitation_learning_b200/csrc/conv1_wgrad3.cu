@@ -27,20 +27,10 @@
 #include <stdlib.h>
 #include "bc_common.cuh"
 #include "tc05.cuh"
+#include "trace.cuh"
 
 namespace c1wg3 {
 
-#ifdef BC_TRACE      // timeline of one CTA (tools/c1wg3_trace.py): per warp a list of (event << 56 | id << 40 | cycles since the CTA started)
-__device__ unsigned long long g_trace[16][1024];
-__device__ int g_trace_cta = 0;
-#define TRACE_DECL uint32_t tr_n = 0; const bool tr_on = (int)blockIdx.x == g_trace_cta && lane == 0;
-#define TRACE(ev, id) do { if (tr_on && tr_n < 1023) g_trace[warp][tr_n++] = ((unsigned long long)(ev) << 56) | ((unsigned long long)((id) & 0xffff) << 40) | (unsigned long long)((clock64() - tr_t0) & 0xffffffffffull); } while (0)
-#define TRACE_END do { if (tr_on) g_trace[warp][tr_n] = ~0ull; } while (0)
-#else
-#define TRACE_DECL
-#define TRACE(ev, id) do {} while (0)
-#define TRACE_END do {} while (0)
-#endif
 
 constexpr int NG = 21, TILES_PER_FRAME = 14;
 constexpr int NTHREADS = 13 * 32;            // warp 0 loader + TMEM alloc, warps 1-3 and 12 issuers, warps 4-7 / 8-11 builder groups (both fold in the epilogue)
@@ -123,9 +113,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-#ifdef BC_TRACE
-    const long long tr_t0 = clock64();
-#endif
+    TRACE_T0
     TRACE_DECL
     TRACE(0, 0);
     tc05::pdl_trigger();
@@ -388,12 +376,7 @@ conv1_wgrad3_kernel(const __nv_bfloat16* __restrict__ x, int64_t sc, const uint4
 
 }  // namespace c1wg3
 
-#ifdef BC_TRACE
-extern "C" int bc_debug_c1wg3_trace(unsigned long long* host_out, int cta) {     // debug builds only: not part of the ABI
-    if (host_out == nullptr) return cudaMemcpyToSymbol(c1wg3::g_trace_cta, &cta, sizeof(int)) == cudaSuccess ? 0 : -1;
-    return cudaMemcpyFromSymbol(host_out, c1wg3::g_trace, sizeof(unsigned long long) * 16 * 1024) == cudaSuccess ? 0 : -1;
-}
-#endif
+BC_TRACE_EXPORT(bc_debug_c1wg3_trace)      // debug builds only: not part of the ABI
 
 // sliding-window batch + compact gradient inputs (bc_ctx.conv_mode bit 16); everything else: conv1_tc.cu's kernel
 int bc_conv1_wgrad3_launch(const bc_ctx* c, const bc::Arena& ar, const bc::Partials& pl, int grid, void* stream) {

@@ -1,6 +1,6 @@
-"""Timeline of one CTA of the swapped-role conv1 forward (needs a library built with BC_NVCC_EXTRA=-DBC_TRACE).
-    python tools/c1f4_trace.py [cta]   -> per warp the event list: 1 plane load issued (id = plane), 2 accumulator free (pair),
-    3 plane ready for visit (pair*8+d), 4 visit issued, 5 epilogue asks for pair, 6 pair complete, 7 accumulator drained, 8 tile stored, 9 warp done."""
+"""Timeline of one CTA of the default conv1 forward (conv1_tp_kernel) (needs a library built with BC_NVCC_EXTRA=-DBC_TRACE).
+    python tools/c1tc_trace.py [cta]   -> per warp the event list: 0 CTA start, 10 predecessor complete, 1 plane load issued (plane), 3 issuer has the plane (plane), 4 issued (plane),
+    5 epilogue asks for sample tile n, 6 accumulator complete, 7 drained into registers, 8 tile stored, 11 warp done."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -19,13 +19,13 @@ bufs = eng.train_forward_backward(stage_frames(fr), y)
 c = eng.ctx(bufs)
 s = torch.cuda.current_stream().cuda_stream
 l = C.CDLL(_lib.LIB_PATH)
-l.bc_debug_c1f4_trace.argtypes = [C.c_void_p, C.c_int]
-l.bc_debug_c1f4_trace(None, cta)
+l.bc_debug_c1tc_trace.argtypes = [C.c_void_p, C.c_int]
+l.bc_debug_c1tc_trace(None, cta)
 for _ in range(3):
     eng.lib.bc_conv_relu_pool_fwd(C.byref(c), 0, s)
 torch.cuda.synchronize()
 out = np.zeros((20, 1024), np.uint64)
-l.bc_debug_c1f4_trace(out.ctypes.data, cta)
+l.bc_debug_c1tc_trace(out.ctypes.data, cta)
 for w in range(20):
     ev = []
     for v in out[w]:

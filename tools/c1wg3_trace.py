@@ -24,9 +24,9 @@ l.bc_debug_c1wg3_trace(None, cta)
 for _ in range(3):
     eng.lib.bc_conv_bwd_wgrad(C.byref(c), 0, s)
 torch.cuda.synchronize()
-out = np.zeros((16, 1024), np.uint64)
+out = np.zeros((20, 1024), np.uint64)
 l.bc_debug_c1wg3_trace(out.ctypes.data, cta)
-for w in range(16):
+for w in range(20):
     ev = []
     for v in out[w]:
         v = int(v)
