@@ -39,15 +39,34 @@ namespace {
 // ---- K10: fused multi-tensor Adam over the flat arena ---------------------------------------
 // state (doubles, like the Python scalars torch.optim.Adam works with):
 //   [0] lr [1] beta1 [2] beta2 [3] eps [4] step [5] grad_scale [6] step_size (out) [7] bc2_sqrt (out)
+// beta1 ** step and beta2 ** step for the integer-valued step count, by binary exponentiation with the two chains
+// interleaved: ~2 log2(step) dependent f64 multiplies (a few hundred cycles) where two calls of the general pow() cost
+// 1.3 us at the head of a 10 us kernel (profiles/README.md). The products differ from the correctly rounded power by
+// < 1e-14 relative; the bias corrections they enter are rounded to f32 before use.
+__device__ __forceinline__ void beta_powers(double b1, double b2, double step, double& p1, double& p2) {
+    if (!(step >= 1.0 && step < 9.0e15) || step != floor(step)) { p1 = pow(b1, step); p2 = pow(b2, step); return; }
+    unsigned long long n = (unsigned long long)step;
+    double r1 = 1.0, r2 = 1.0;
+    while (true) {
+        if (n & 1ull) { r1 *= b1; r2 *= b2; }
+        n >>= 1;
+        if (!n) break;
+        b1 *= b1; b2 *= b2;
+    }
+    p1 = r1; p2 = r2;
+}
+
 __global__ void adam_tick_kernel(double* st) {
     bc::pdl_wait();
     bc::pdl_trigger();
     // torch/optim/adam.py (single-tensor path): bias_correction1 = 1 - beta1 ** step;
     // step_size = lr / bias_correction1; bias_correction2_sqrt = sqrt(1 - beta2 ** step) -- all in f64.
     const double step = st[4] + 1.0;
+    double p1, p2;
+    beta_powers(st[1], st[2], step, p1, p2);
     st[4] = step;
-    st[6] = st[0] / (1.0 - pow(st[1], step));
-    st[7] = sqrt(1.0 - pow(st[2], step));
+    st[6] = st[0] / (1.0 - p1);
+    st[7] = sqrt(1.0 - p2);
 }
 
 // tick folded into the update: every CTA derives the step's scalars from st[4] + 1 itself (same f64 formulas as
@@ -59,8 +78,10 @@ __device__ __forceinline__ void adam_scalars(const double* st, double* s_sc) {
 #ifdef BC_ADAM_NOPOW      // timing experiment only (wrong bias corrections): what the two f64 pow cost at the head of the kernel
     s_sc[1] = st[0]; s_sc[2] = 1.0; return;
 #endif
-    s_sc[1] = st[0] / (1.0 - pow(st[1], step));
-    s_sc[2] = sqrt(1.0 - pow(st[2], step));
+    double p1, p2;
+    beta_powers(st[1], st[2], step, p1, p2);
+    s_sc[1] = st[0] / (1.0 - p1);
+    s_sc[2] = sqrt(1.0 - p2);
 }
 __device__ __forceinline__ void adam_publish(double* st, const double* s_sc) {   // called by thread 0 of every CTA after its work
     __threadfence();
@@ -95,26 +116,34 @@ __global__ void __launch_bounds__(256) adam_tick_step_kernel(float4* __restrict_
                                                              double* __restrict__ st, int64_t n4, const ctc::PackMap pm) {
     __shared__ double s_sc[3];
     bc::pdl_wait();
-    bc::pdl_trigger();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the first (normally the only) float4 of every thread is in flight while thread 0 derives the step's scalars
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pp = z4, mm = z4, vv = z4, gg = z4;
+    if (i < n4) { pp = p[i]; mm = m[i]; vv = v[i]; gg = g[i]; }
     if (threadIdx.x == 0) adam_scalars(st, s_sc);
     __syncthreads();
     const AdamK k = adam_consts(st, s_sc[1], s_sc[2]);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 pp = p[i], mm = m[i], vv = v[i];
-        adam4(pp, g[i], mm, vv, k);
+    while (i < n4) {
+        adam4(pp, gg, mm, vv, k);
         p[i] = pp; m[i] = mm; v[i] = vv;
         ctc::pack_updated4(pm, 4 * i, &pp.x);
+        i += stride;
+        if (i < n4) { pp = p[i]; mm = m[i]; vv = v[i]; gg = g[i]; }
     }
     __syncthreads();
     if (threadIdx.x == 0) adam_publish(st, s_sc);
+    // writer of the parameters / operand images: dependents are released only after the last write (the conv and head kernels
+    // fetch their weights BEFORE their own griddepcontrol.wait)
+    __threadfence();
+    bc::pdl_trigger();
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v,
                                                    const double* __restrict__ st, int64_t n4) {
     bc::pdl_wait();
-    bc::pdl_trigger();
     const AdamK k = adam_consts(st, st[6], st[7]);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -122,6 +151,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
         adam4(pp, g[i], mm, vv, k);
         p[i] = pp; m[i] = mm; v[i] = vv;
     }
+    // writer of the parameters / operand images: dependents are released only after the last write (the conv and head kernels
+    // fetch their weights BEFORE their own griddepcontrol.wait)
+    __threadfence();
+    bc::pdl_trigger();
 }
 
 // ---- K11 + K10 fused: the data-parallel gradient exchange inside the Adam step, over NVLink peer memory -------------
@@ -182,8 +215,7 @@ struct ExchangeArgs {
 __global__ void __launch_bounds__(128) adam_exchange_kernel(const ExchangeArgs a) {
     __shared__ int s_last;
     __shared__ double s_sc[3];
-    bc::pdl_wait();
-    bc::pdl_trigger();
+    bc::pdl_wait();                                         // no early release of the dependents: this kernel writes the parameters (see adam_tick_step_kernel)
     if (threadIdx.x == 0) adam_scalars(a.st, s_sc);        // the tick is folded in (published by the last CTA of the publishing launch)
     const uint32_t epoch = a.sync[0] + 1;
     const int64_t par = (int64_t)(epoch & 1u) * a.arena4;
@@ -220,6 +252,7 @@ __global__ void __launch_bounds__(128) adam_exchange_kernel(const ExchangeArgs a
     }
     __syncthreads();
     if (s_last && threadIdx.x == 0) { a.sync[1] = 0; a.sync[0] = epoch; a.st[4] = s_sc[0]; a.st[6] = s_sc[1]; a.st[7] = s_sc[2]; }
+    // early returns above release the dependents implicitly when the grid completes
 }
 
 }  // namespace

@@ -100,15 +100,17 @@ conv1_fwd4_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, c
     const uint32_t tmem_base = *tmem_slot;
     TRACE_T0
     TRACE_DECL
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(w_full, W_BYTES);
+        tc05::bulk_g2s(smem + OFF_W, wimg, W_BYTES, w_full);
+    }
     tc05::pdl_trigger();
     tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: 6 bulk copies per plane, one per lane
-        if (lane == 0) {
-            tc05::mbar_expect_tx(w_full, W_BYTES);
-            tc05::bulk_g2s(smem + OFF_W, wimg, W_BYTES, w_full);
-        }
         RunIter it(B, sliding);
         int ty, b0, S;
         uint32_t k = 0;

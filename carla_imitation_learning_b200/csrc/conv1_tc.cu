@@ -127,6 +127,12 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     TRACE_T0
     TRACE_DECL
     TRACE(0, 0);
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(b_full, B_BYTES);
+        tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+    }
     tc05::pdl_trigger();
     tc05::pdl_wait();
     TRACE(10, 0);                    // everything above overlapped the previous kernel's tail; global memory from here on
@@ -136,10 +142,6 @@ conv1_tp_kernel(const __nv_bfloat16* __restrict__ x, int64_t sn, int64_t sc, con
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: 6 bulk copies per plane, one per lane
         {
-            if (lane == 0) {
-                tc05::mbar_expect_tx(b_full, B_BYTES);
-                tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
-            }
             TileIter it(B, smax);
             int ty, b0, S;
             uint32_t k = 0;

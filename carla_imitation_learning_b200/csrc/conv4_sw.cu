@@ -55,14 +55,16 @@ conv4_fwd_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __re
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(b_full, B_BYTES);
+        tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+    }
     tc05::pdl_trigger();
     tc05::pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, B_BYTES);
-            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
-        }
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             if (!tc05::mbar_wait(a_empty, (it & 1) ^ 1, err)) break;
@@ -206,14 +208,16 @@ conv4_dgrad_kernel(const float* __restrict__ gP, const float* __restrict__ aP, c
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(b_full, B_BYTES);
+        tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
+    }
     tc05::pdl_trigger();
     tc05::pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, B_BYTES);
-            tc05::bulk_g2s(smem + OFF_B, wpk, B_BYTES, b_full);
-        }
     } else if (warp == 1) {
         constexpr uint32_t idesc = tc05::instr_desc(tc05::FMT_BF16, 128, N, 0, 0);
         const uint64_t ad0 = tc05::smem_desc(tc05::smem_u32(smem + OFF_IMG), PLANE, 128, tc05::SW_NONE);
@@ -389,45 +393,51 @@ conv4_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                 r = routed_unit(gP, aP, amax, b, cgo, b < b_hi);
             }
         }
-        const bool okd = ok && tc05::mbar_wait(done, 0, err);
-        tc05::tc_fence_after();
-        float* dst = part + (size_t)blockIdx.x * seg_len;
         if (blockIdx.y == 0) {
             // bias gradient = sum over the slot's images of the masked pooled gradient: fixed-order fold through smem
+            // (the gradient slots are free once every MMA has completed)
+            const bool okd = ok && tc05::mbar_wait(done, 0, err);
+            float* dst = part + (size_t)blockIdx.x * seg_len;
             float* bs = reinterpret_cast<float*>(smem + OFF_D);
-            if (tb < 128) {
+            if (tb < 128 && okd) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) bs[il * COUT + cgo * 8 + k] = bsum[k];
             }
             asm volatile("bar.sync 3, 256;" ::: "memory");
-            if (tb < COUT) {
+            if (tb < COUT && okd) {
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc += bs[i * COUT + tb];
                 dst[b_off + tb] = acc;
             }
         }
-        if (warp < 8 && okd) {
-            // D[w] row (kx', ci8), column co -> dW[co][8 (cg0 + w) + ci8][ky][kx']
-            const int row = ew * 32 + lane, kx = row >> 3, ci8 = row & 7;
-            const bool any = nchunk > 0;
+    }
+    // Epilogue. D[w] row (kx', ci8), column co -> dW[co][8 (cg0 + w) + ci8][ky][kx']: only rows kx' < KS = 24 rows carry a
+    // weight gradient and they all sit in TMEM lane quadrant 0, which only the warps with warp % 4 == 0 may read: warps 0
+    // (loader), 4 and 8 (builders) and 12 (an issuer) drain one accumulator each once their own role is finished -- one
+    // warp walking all four accumulators was a 512-store serial tail.
+    if ((warp & 3) == 0) {
+        const int w = warp >> 2;
+        const bool okd = tc05::mbar_wait(done, 0, err);
+        tc05::tc_fence_after();
+        float* dst = part + (size_t)blockIdx.x * seg_len;
+        const int kx = lane >> 3, ci8 = lane & 7;
+        const bool any = nchunk > 0;
+        if (okd) {
 #pragma unroll 1
-            for (int w = 0; w < 4; ++w) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < COUT; c0 += 16) {
-                    float v[16];
-                    if (any) {
-                        tc05::tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + w * COUT + c0, v);
-                        tc05::tmem_ld_wait();
-                    } else {
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+                float v[16];
+                if (any) {
+                    tc05::tmem_ld16(tmem_base + w * COUT + c0, v);
+                    tc05::tmem_ld_wait();
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                    }
-                    if (kx < KS) {
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                if (kx < KS) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            dst[w_off + (((size_t)(c0 + j) * CIN + (cg0 + w) * 8 + ci8) * KS + ky) * KS + kx] = v[j];
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        dst[w_off + (((size_t)(c0 + j) * CIN + (cg0 + w) * 8 + ci8) * KS + ky) * KS + kx] = v[j];
                 }
             }
         }

@@ -258,43 +258,46 @@ struct ReduceArgs {
     int64_t loss_off; int n_loss; int64_t begin, end; int with_loss;
 };
 
-// 32 consecutive arena elements per CTA x 8 part-groups: thread (e, g) sums copies p = g, g+8, ... in
-// order, the 8 group sums are then added in fixed order => deterministic, with 8x the loads in flight of
-// a one-thread-per-element walk over up to 296 copies.
+// 128 consecutive arena elements per CTA (one float4 per lane: 512 B per warp and copy) x 8 part-groups: thread (e, g)
+// sums copies p = g, g+8, ... in order, the 8 group sums are then added in fixed order => deterministic, with 8x the
+// loads in flight of a one-thread-per-element walk over up to 296 copies. Segments are padded to 32 floats, so a float4
+// never straddles two of them; the association order per element is the one the scalar version of this kernel used.
+__device__ __forceinline__ void add4(float4& s, const float4 v) { s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
-    __shared__ float red[8][33];
+    __shared__ float4 red[8][33];
     bc::pdl_wait();
     bc::pdl_trigger();
     const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int64_t i = a.begin + (int64_t)blockIdx.x * 32 + e;
-    float acc = 0.f;
+    const int64_t i = a.begin + ((int64_t)blockIdx.x * 32 + e) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < a.end) {
         int s = 0;
 #pragma unroll
         for (int k = 1; k < 5; ++k) if (i >= a.seg_off[k]) s = k;
-        const float* p = a.part + a.poff[s] + (i - a.seg_off[s]);
-        const int64_t stride = a.seg_len[s];
+        const float4* p = reinterpret_cast<const float4*>(a.part + a.poff[s] + (i - a.seg_off[s]));
+        const int64_t stride = a.seg_len[s] / 4;
         const int n = a.nparts[s];
         // 4 independent chains per thread (fixed association order): 4 loads in flight instead of 2
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        float4 s0 = acc, s1 = acc, s2 = acc, s3 = acc;
         int q = g;
         for (; q + 24 < n; q += 32) {
-            s0 += p[(int64_t)q * stride]; s1 += p[(int64_t)(q + 8) * stride];
-            s2 += p[(int64_t)(q + 16) * stride]; s3 += p[(int64_t)(q + 24) * stride];
+            const float4 v0 = p[(int64_t)q * stride], v1 = p[(int64_t)(q + 8) * stride];
+            const float4 v2 = p[(int64_t)(q + 16) * stride], v3 = p[(int64_t)(q + 24) * stride];
+            add4(s0, v0); add4(s1, v1); add4(s2, v2); add4(s3, v3);
         }
-        if (q < n) s0 += p[(int64_t)q * stride];
-        if (q + 8 < n) s1 += p[(int64_t)(q + 8) * stride];
-        if (q + 16 < n) s2 += p[(int64_t)(q + 16) * stride];
-        acc = (s0 + s1) + (s2 + s3);
+        if (q < n) add4(s0, p[(int64_t)q * stride]);
+        if (q + 8 < n) add4(s1, p[(int64_t)(q + 8) * stride]);
+        if (q + 16 < n) add4(s2, p[(int64_t)(q + 16) * stride]);
+        acc = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
     }
     red[g][e] = acc;
     __syncthreads();
     if (g == 0 && i < a.end) {
-        float t = 0.f;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][e];
+        for (int k = 0; k < 8; ++k) add4(t, red[k][e]);
         const int64_t par = a.grads_epoch ? (int64_t)((*a.grads_epoch + 1u) & 1u) * a.grads_stride : 0;
-        a.grads[par + i] = t;
+        *reinterpret_cast<float4*>(a.grads + par + i) = t;
     }
     if (a.with_loss && blockIdx.x == 0 && threadIdx.x < 32) {
         float v = 0.f;
@@ -394,7 +397,7 @@ extern "C" int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi,
     a.loss_off = pl.loss_off; a.n_loss = bc::kHeadBlocks; a.with_loss = with_loss && c->loss != nullptr;
     a.begin = ar.seg_off[seg_lo];
     a.end = ar.seg_off[seg_hi - 1] + ar.seg_len[seg_hi - 1];
-    bc::launch_pdl(reduce_partials_kernel, dim3((unsigned)((a.end - a.begin + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, a);
+    bc::launch_pdl(reduce_partials_kernel, dim3((unsigned)((a.end - a.begin + 127) / 128)), dim3(256), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("reduce_partials_kernel");
     return BC_OK;
 }

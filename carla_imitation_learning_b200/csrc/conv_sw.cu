@@ -162,16 +162,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_fwd_kernel(const FwdArgs a) {
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(b_full, C::B_BYTES);
+        tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
+    }
     tc05::pdl_trigger();
-    tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; global memory from here on
+    tc05::pdl_wait();                    // everything above overlapped the previous kernel's tail; activations and gradients from here on
     if (threadIdx.x >= 128 && threadIdx.x < 128 + COUT) reinterpret_cast<float*>(smem + C::OFF_BIAS)[threadIdx.x - 128] = a.bias[threadIdx.x - 128];
     if (warp >= 4 && warp < 12) asm volatile("bar.sync 3, 256;" ::: "memory");   // the epilogue warps read the bias from smem
 
     if (warp == 0) {
         // ------------------------------------------------------------------ loader: one bulk copy per image
         if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, C::B_BYTES);
-            tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
             TileRange it(a.B, C::TPI);
             int b, t, lastb = -1;
             uint32_t k = 0;
@@ -391,14 +395,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_dgrad_kernel(const DgradArgs a
     __syncthreads();
     tc05::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // the weight operand image is written only by kernels that release their dependents after their last write (Adam / pack:
+    // abi.cu, conv_tc.cu), so it is fetched here, under the previous kernel's tail, and not after the wait
+    if (threadIdx.x == 0) {
+        tc05::mbar_expect_tx(b_full, C::B_BYTES);
+        tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
+    }
     tc05::pdl_trigger();
     tc05::pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            tc05::mbar_expect_tx(b_full, C::B_BYTES);
-            tc05::bulk_g2s(smem + C::OFF_B, a.wpk, C::B_BYTES, b_full);
-        }
     } else if (warp <= 3 || warp == 12) {
         // ------------------------------------------------------------------ 4 MMA issuers
         const uint32_t w = warp == 12 ? 0u : (uint32_t)warp;
@@ -747,15 +753,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
                 if (part == 0) dst[a.b_off + ch] = acc;
             }
         }
-        if (warp >= 8) goto fin;
-        // ---- epilogue: D[cg] row (kx', ci8), column co -> dW[co][8 cg + ci8][ky][kx']
+        // ---- epilogue: D[cg] row (kx', ci8), column co -> dW[co][8 cg + ci8][ky][kx']; both builder groups (warps 4-7 and 8-11
+        // cover the four TMEM lane quadrants once each) drain, group 0 the even accumulators and group 1 the odd ones
         {
             const bool any = b_hi > b_lo;
             if (okd) {
                 // M = 64 accumulators sit in lanes 0..15 of every 32-lane quadrant: row = 16 * quadrant + lane
                 const int row = C::MMA_M == 64 ? (lane < 16 ? ew * 16 + lane : 127) : ew * 32 + lane, kx = row >> 3, ci8 = row & 7;
 #pragma unroll 1
-                for (int acc = 0; acc < C::NACC; ++acc) {
+                for (int acc = warp >= 8 ? 1 : 0; acc < C::NACC; acc += 2) {
 #pragma unroll 1
                     for (int c0 = 0; c0 < COUT; c0 += 16) {
                         float v[16];
@@ -776,7 +782,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sw_wgrad_kernel(const WgradArgs a
             }
         }
     }
-fin:
     tc05::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc05::tmem_dealloc(tmem_base, 512);

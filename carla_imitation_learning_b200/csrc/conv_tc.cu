@@ -17,9 +17,8 @@ constexpr int kNC1 = 28 * 64 * 16;                         // conv1's Toeplitz i
 constexpr int kNC1V4 = kC1V4Blocks * 1024;                 // the swapped-role image of conv1 (conv1_fwd4.cu), element-ordered as well
 constexpr int kPackElems = kNC1 + kNC1V4 + kNW2 + kNW3 + kNW4;
 // all seven operand images (conv1 Toeplitz, conv2-4 forward + dgrad) in one launch
-__global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
-    bc::pdl_wait();
-    bc::pdl_trigger();
+// (the dependents are released only after the last write: the conv kernels fetch these images before their own wait)
+__device__ __forceinline__ void pack_all_body(const PackArgs& a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int ncam = a.obs == 12 ? 3 : 1;
     if (i < ncam * kNC1) {
@@ -52,6 +51,12 @@ __global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o
     if (i < kNW2) { pack_src_elem<L2>(a.w2[i], (__nv_bfloat16*)(a.base + o2), (__nv_bfloat16*)(a.base + d2), i); return; } i -= kNW2;
     if (i < kNW3) { pack_src_elem<L3>(a.w3[i], (__nv_bfloat16*)(a.base + o3), (__nv_bfloat16*)(a.base + d3), i); return; } i -= kNW3;
     if (i < kNW4) pack_src_elem<L4>(a.w4[i], (__nv_bfloat16*)(a.base + o4), (__nv_bfloat16*)(a.base + d4), i);
+}
+__global__ void pack_all_kernel(const PackArgs a, size_t o2, size_t o3, size_t o4, size_t d2, size_t d3, size_t d4) {
+    bc::pdl_wait();
+    pack_all_body(a, o2, o3, o4, d2, d3, d4);
+    __threadfence();
+    bc::pdl_trigger();
 }
 }  // namespace ctc
 

@@ -27,8 +27,6 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
-    bc::pdl_wait();
-    bc::pdl_trigger();
     __shared__ __align__(16) float s_w0[64 * 128];
     __shared__ __align__(16) float s_w2[32 * 64];
     __shared__ __align__(16) float s_w4[MAXA * 32];
@@ -37,25 +35,29 @@ __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NA = a.NA;
     // 42 KB of weights per CTA as 16 B loads, all of a thread's loads in flight at once (arena tensors are padded to 32 floats:
-    // 16 B aligned); the scalar version of this prologue was a quarter of the kernel's time
+    // 16 B aligned); the scalar version of this prologue was a quarter of the kernel's time. The parameters are written only
+    // by kernels that release their dependents after their last write (Adam: abi.cu), so this prologue runs BEFORE the wait,
+    // under conv4's forward; L2 loads (ld.cg): an L1 line of an earlier launch on this SM could be stale.
     {
         const float4* w0v = reinterpret_cast<const float4*>(a.w0);
         float4 t[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = __ldg(w0v + tid + NT * q);
+        for (int q = 0; q < 8; ++q) t[q] = __ldcg(w0v + tid + NT * q);
         const float4* w2v = reinterpret_cast<const float4*>(a.w2);
-        float4 u0 = __ldg(w2v + tid), u1 = __ldg(w2v + tid + NT);
+        float4 u0 = __ldcg(w2v + tid), u1 = __ldcg(w2v + tid + NT);
         const bool has4 = tid < NA * 8;
-        float4 u4 = has4 ? __ldg(reinterpret_cast<const float4*>(a.w4) + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 u4 = has4 ? __ldcg(reinterpret_cast<const float4*>(a.w4) + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(s_w0)[tid + NT * q] = t[q];
         reinterpret_cast<float4*>(s_w2)[tid] = u0;
         reinterpret_cast<float4*>(s_w2)[tid + NT] = u1;
         if (has4) reinterpret_cast<float4*>(s_w4)[tid] = u4;
     }
-    if (tid < 64) s_b0[tid] = a.b0[tid];
-    if (tid < 32) s_b2[tid] = a.b2[tid];
-    if (tid < NA) s_b4[tid] = a.b4[tid];
+    if (tid < 64) s_b0[tid] = __ldcg(a.b0 + tid);
+    if (tid < 32) s_b2[tid] = __ldcg(a.b2 + tid);
+    if (tid < NA) s_b4[tid] = __ldcg(a.b4 + tid);
+    bc::pdl_trigger();
+    bc::pdl_wait();                       // activations, labels and every output from here on
 
     float acc0[32], acc2[8], acc4[2], accb = 0.f, block_loss = 0.f;
 #pragma unroll
