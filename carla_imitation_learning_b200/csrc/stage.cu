@@ -97,42 +97,59 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // segments). Every pixel is converted once (12 conversions per thread, not 16).
 // `plain` (optional): the same gray values also as plain (n,256,256) bf16 planes.
 constexpr int TP_NU = TP_NG + 1;
+
+// The bf16 value of a pixel, bf16_rn(f32 gray), needs less than the correctly rounded f32 quotient: s * r followed by one
+// compensation step fma(s, r_lo, .) (r + r_lo = 1/255000 to 2^-48) lands on the same side of every bf16 rounding boundary as
+// the exact quotient for all 247,023 distinct s (a single FMUL fails for s = 106333, 180791, 212666, 244541, which lie within
+// 2^-25 of a bf16 midpoint) -- host-checked exhaustively (tests/test_stage_model.py) and on the device for all 2^24 triples
+// (tests/test_gpu_parity.py). s itself is two dp4a over the pixel's bytes (R, G, B, G) gathered by ONE byte permute,
+// 299 = 255 + 44, 587 = 255 + 255 + 77, 114 = 114, accumulated on top of the bit pattern of 2^23: the integer sum IS the float
+// 2^23 + s, and one FADD makes it s (no I2F on the quarter-rate XU pipe, no shift / mask pairs). The first version of this
+// kernel spent 25 instructions per pixel (11 of them 64-bit unit-index arithmetic) and was issue-bound at 42 % of the copy
+// rate on the DRAM bytes it moves; this one spends about 10.
+__device__ __forceinline__ float gray_px_bf16_exact(uint32_t px /* bytes R, G, B, G */) {
+    uint32_t acc = __dp4a(px, 0xFF72FFFFu, 0x4B000000u);       // 255 R + 255 G + 114 B + 255 G + bits(2^23)
+    acc = __dp4a(px, 0x00004D2Cu, acc);                        //  44 R +  77 G
+    const float s = __uint_as_float(acc) - 8388608.0f;         // exact: s <= 255000 < 2^23
+    constexpr float r = 1.0f / 255000.0f;
+    constexpr float r_lo = (float)(1.0 / 255000.0 - (double)r);
+    return __fmaf_rn(s, r_lo, __fmul_rn(s, r));
+}
+
 __global__ void __launch_bounds__(256) stage_gray_tp_kernel(const uint8_t* __restrict__ rgb, __nv_bfloat16* __restrict__ out,
-                                                            __nv_bfloat16* __restrict__ plain, int64_t n_units) {
+                                                            __nv_bfloat16* __restrict__ plain, uint32_t n_units) {
     bc::pdl_wait();          // the previous step's kernels still read the planes this one overwrites
     bc::pdl_trigger();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {
-        const int g = (int)(u % TP_NU), q = (int)((u / TP_NU) % TP_NQ), c = (int)((u / (TP_NU * TP_NQ)) % 3);
-        const int64_t plane = u / (TP_NU * TP_NQ * 3);
-        const int R = 3 * q + c;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += stride) {      // 32-bit unit arithmetic
+        const uint32_t t1 = u / TP_NU, g = u - t1 * TP_NU;
+        const uint32_t t2 = t1 / TP_NQ, q = t1 - t2 * TP_NQ;
+        const uint32_t plane = t2 / 3u, c = t2 - plane * 3u;
+        const uint32_t R = 3u * q + c;
         uint32_t pk[6] = {0, 0, 0, 0, 0, 0};                 // 12 gray values as bf16 pairs; rows R >= 256 stay zero
         if (R < BC_H) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + ((plane * BC_H + R) * BC_W + 12 * g) * 3);
-            uint32_t w[9];
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + ((size_t)plane * (BC_H * BC_W) + R * BC_W + 12u * g) * 3);
+            uint32_t w[10];
 #pragma unroll
             for (int i = 0; i < 9; ++i) w[i] = (g < TP_NG || i < 3) ? __ldg(src + i) : 0u;     // g' = 21 has 4 pixels = 12 bytes left
+            w[9] = 0u;
             float v[12];
 #pragma unroll
             for (int p = 0; p < 12; ++p) {
-                uint32_t ch[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int byte = 3 * p + k;
-                    ch[k] = (w[byte >> 2] >> (8 * (byte & 3))) & 0xffu;
-                }
-                v[p] = gray_px(ch[0], ch[1], ch[2]);
+                constexpr uint32_t sel[4] = {0x1210u, 0x2321u, 0x3432u, 0x4543u};               // bytes o, o+1, o+2, o+1 = R, G, B, G
+                const int o = (3 * p) & 3, i = (3 * p) >> 2;
+                v[p] = gray_px_bf16_exact(__byte_perm(w[i], w[i + 1], sel[o]));
             }
 #pragma unroll
             for (int i = 0; i < 6; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             if (plain) {
-                uint2* dst = reinterpret_cast<uint2*>(plain + (plane * BC_H + R) * BC_W + 12 * g);
+                uint2* dst = reinterpret_cast<uint2*>(plain + ((size_t)plane * BC_H + R) * BC_W + 12u * g);
                 dst[0] = make_uint2(pk[0], pk[1]);
                 if (g < TP_NG) { dst[1] = make_uint2(pk[2], pk[3]); dst[2] = make_uint2(pk[4], pk[5]); }
             }
         }
-        __nv_bfloat16* row0 = out + plane * BC_TP_PLANE_ELEMS + ((int64_t)(c * 2) * TP_NQ + q) * (TP_NG * 8);   // (c, h=0, q)
-        __nv_bfloat16* row1 = row0 + TP_NQ * TP_NG * 8;                                                          // (c, h=1, q)
+        __nv_bfloat16* row0 = out + (size_t)plane * BC_TP_PLANE_ELEMS + ((c * 2u) * TP_NQ + q) * (TP_NG * 8);   // (c, h=0, q)
+        __nv_bfloat16* row1 = row0 + TP_NQ * TP_NG * 8;                                                         // (c, h=1, q)
         if (g < TP_NG) {
             *reinterpret_cast<uint4*>(row0 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint2*>(row1 + g * 8) = make_uint2(pk[4], pk[5]);
@@ -276,9 +293,10 @@ extern "C" int bc_stage_gray_tp(const uint8_t* rgb, void* tp, void* plain_bf16, 
     BC_CHECK_ARG(((uintptr_t)rgb % 4 == 0) && ((uintptr_t)tp % 16 == 0) && ((uintptr_t)plain_bf16 % 8 == 0), "bc_stage_gray_tp: alignment");
     if (n_frames == 0) return BC_OK;
     const int64_t units = n_frames * 3 * TP_NQ * TP_NU;
+    BC_CHECK_ARG(units < (int64_t)0x7fffffff - 0x1000000, "bc_stage_gray_tp: %lld frames in one call (the unit index is 32-bit: at most 378,000)", (long long)n_frames);
     const int64_t cap = (int64_t)bc::num_sms() * 16;
     const int blocks = (int)((units + 255) / 256 < cap ? (units + 255) / 256 : cap);
-    bc::launch_pdl(stage_gray_tp_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, units);
+    bc::launch_pdl(stage_gray_tp_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, rgb, (__nv_bfloat16*)tp, (__nv_bfloat16*)plain_bf16, (uint32_t)units);
     BC_CUDA_LAUNCH_CHECK("stage_gray_tp_kernel");
     return BC_OK;
 }
@@ -294,8 +312,9 @@ extern "C" int bc_stage_gray(const uint8_t* rgb, void* gray, int64_t n_pixels, i
     if (out_dtype == BC_BF16_TP) {
         BC_CHECK_ARG(n_pixels % (BC_H * BC_W) == 0, "bc_stage_gray: the TP layout is defined for whole 256x256 frames");
         const int64_t units = n_pixels / (BC_H * BC_W) * 3 * TP_NQ * TP_NU;
+        BC_CHECK_ARG(units < (int64_t)0x7fffffff - 0x1000000, "bc_stage_gray: too many frames in one call for the TP layout (32-bit unit index: at most 378,000)");
         int blocks = (int)((units + 255) / 256 < (int64_t)sms * 16 ? (units + 255) / 256 : (int64_t)sms * 16);
-        stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, nullptr, units);
+        stage_gray_tp_kernel<<<blocks, 256, 0, s>>>(rgb, (__nv_bfloat16*)gray, nullptr, (uint32_t)units);
     } else if (out_dtype == BC_F32) {
         int64_t groups = n_pixels / 4;
         int blocks = (int)((groups + 255) / 256 < (int64_t)sms * 16 ? (groups + 255) / 256 : (int64_t)sms * 16);

@@ -75,6 +75,26 @@ def test_stage_gray_bit_exact_all_rgb():
     assert np.array_equal(got16, ref16)
 
 
+def test_stage_frames_tp_bit_exact_all_rgb():
+    """The Toeplitz-ready bf16 staging kernel (its own, cheaper arithmetic: csrc/stage.cu::gray_px_bf16_exact) on every
+    (R,G,B) triple: both its outputs -- the plain bf16 planes and the TP planes -- equal bf16_rn(reference f32 gray)."""
+    from carla_imitation_learning_b200 import stage_frames, _lib
+    dev = _dev()
+    r = np.arange(256, dtype=np.uint8)
+    R, G, B = np.meshgrid(r, r, r, indexing="ij")
+    rgb = np.stack([R, G, B], -1).reshape(256, 256, 256, 3)
+    ref16 = torch.from_numpy(O.gray_stack(rgb)).to(torch.bfloat16)
+    st = stage_frames(torch.from_numpy(rgb).to(dev), plain=True)
+    tp, plain = st.tp, st.plain
+    torch.cuda.synchronize()
+    assert torch.equal(plain.cpu().view(torch.int16), ref16.view(torch.int16))
+    # TP planes = a pure rearrangement of the plain planes (bc_planes_to_tp is the independent re-layout)
+    tp2 = torch.empty_like(tp)
+    _lib.check(_lib.lib().bc_planes_to_tp(plain.data_ptr(), _lib.BC_BF16, 256, 256 * 256, tp2.data_ptr(), torch.cuda.current_stream().cuda_stream), "bc_planes_to_tp")
+    torch.cuda.synchronize()
+    assert torch.equal(tp.view(torch.int16), tp2.view(torch.int16))
+
+
 def test_stage_gray_golden_and_window(golden_dir):
     from carla_imitation_learning_b200 import stage_gray, sliding_window
     dev = _dev()

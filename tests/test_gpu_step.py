@@ -448,3 +448,49 @@ def test_module_path_data_parallel_exchange_degenerates_to_adam_on_one_rank(tmp_
     mp.spawn(_module_dp_world1, args=(out, port), nprocs=1, join=True)
     w = np.load(out)
     assert np.array_equal(w[0], w[1])
+
+
+# ------------------------------------------------------------------------------- weight operands fetched before the dependency wait
+@pytest.mark.parametrize("B", [8, 256])
+def test_weights_fetched_before_the_dependency_wait_are_the_updated_ones(B):
+    """The conv and head kernels fetch their weight operands BEFORE griddepcontrol.wait, under the previous kernel's tail;
+    that is only sound because the kernels that WRITE parameters / operand images (Adam, pack) release their dependents
+    after their last write. Worst case for that protocol: Adam directly followed by conv1's forward (pre-staged planes: no
+    staging kernel in between) and Adam directly followed by the head, with a learning rate large enough that a stale
+    weight changes every output. Back-to-back enqueue == the same sequence with a device synchronisation after every
+    launch group, bitwise, over several steps."""
+    from carla_imitation_learning_b200 import FusedAdam, _lib, stage_frames
+    dev = _dev()
+    frames, labels = _uniform_frames(7, B + 4)
+    staged = stage_frames(torch.from_numpy(frames).to(dev))
+    y = torch.from_numpy(labels[4:4 + B].copy()).to(dev)
+    out = []
+    for sync in (False, True):
+        net = _net()
+        eng = net.engine()
+        opt = FusedAdam(list(net.parameters()), lr=3e-3)
+        opt.prepare()
+        eng.ensure_packed()
+        b = eng.static_buffers(B, staged, y)
+        torch.cuda.synchronize()
+        logits = []
+        for _ in range(5):
+            eng.enqueue_train(b)                 # conv1 forward is the first launch: it follows the previous Adam directly
+            if sync:
+                torch.cuda.synchronize()
+            opt.step_flat(eng.grads)
+            if sync:
+                torch.cuda.synchronize()
+            # Adam -> head: the head's forward on the (old) act3 with the NEW fc weights
+            _lib.check(eng.lib.bc_head(C.byref(eng.ctx(b)), 0, torch.cuda.current_stream().cuda_stream), "bc_head")
+            if sync:
+                torch.cuda.synchronize()
+            logits.append(b.logits.clone())
+        torch.cuda.synchronize()
+        eng.check_device_errors()
+        out.append((torch.stack(logits).cpu(), net._arena.clone().cpu(), eng.w_packed.clone().cpu()))
+    (la, pa, wa), (lb, pb, wb) = out
+    assert torch.isfinite(la).all()
+    assert torch.equal(pa, pb) and torch.equal(wa, wb)
+    assert torch.equal(la, lb)
+    assert not torch.equal(la[0], la[-1])                          # the updates did change the outputs
