@@ -73,14 +73,12 @@ __global__ void adam_tick_kernel(double* st) {
 // adam_tick_kernel), the last CTA to finish publishes them and the new step count. st has 9 doubles here: [8] is the
 // CTA counter (as u32). Saves one launch per step.
 __device__ __forceinline__ void adam_scalars(const double* st, double* s_sc) {
-    const double step = st[4] + 1.0;
+    // L2 loads: the step count was published by another SM's CTA of the previous optimiser launch
+    const double step = __ldcg(st + 4) + 1.0;
     s_sc[0] = step;
-#ifdef BC_ADAM_NOPOW      // timing experiment only (wrong bias corrections): what the two f64 pow cost at the head of the kernel
-    s_sc[1] = st[0]; s_sc[2] = 1.0; return;
-#endif
     double p1, p2;
-    beta_powers(st[1], st[2], step, p1, p2);
-    s_sc[1] = st[0] / (1.0 - p1);
+    beta_powers(__ldcg(st + 1), __ldcg(st + 2), step, p1, p2);
+    s_sc[1] = __ldcg(st + 0) / (1.0 - p1);
     s_sc[2] = sqrt(1.0 - p2);
 }
 __device__ __forceinline__ void adam_publish(double* st, const double* s_sc) {   // called by thread 0 of every CTA after its work
@@ -115,14 +113,18 @@ __global__ void __launch_bounds__(256) adam_tick_step_kernel(float4* __restrict_
                                                              float4* __restrict__ m, float4* __restrict__ v,
                                                              double* __restrict__ st, int64_t n4, const ctc::PackMap pm) {
     __shared__ double s_sc[3];
-    bc::pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // the first (normally the only) float4 of every thread is in flight while thread 0 derives the step's scalars
+    // Parameters, moments and the step scalars were last written by the PREVIOUS optimiser launch (or by ordinary launches
+    // before it), and a launch that writes them releases its dependents only after its last write: they are fetched here,
+    // before the dependency wait, under the gradient reduction that precedes this kernel. Only the gradients wait.
+    // (L2 loads: no L1 line of an earlier launch on this SM can be served.)
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pp = z4, mm = z4, vv = z4, gg = z4;
-    if (i < n4) { pp = p[i]; mm = m[i]; vv = v[i]; gg = g[i]; }
+    if (i < n4) { pp = __ldcg(p + i); mm = __ldcg(m + i); vv = __ldcg(v + i); }
     if (threadIdx.x == 0) adam_scalars(st, s_sc);
+    bc::pdl_wait();
+    if (i < n4) gg = g[i];
     __syncthreads();
     const AdamK k = adam_consts(st, s_sc[1], s_sc[2]);
     while (i < n4) {
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) adam_tick_step_kernel(float4* __restrict_
         p[i] = pp; m[i] = mm; v[i] = vv;
         ctc::pack_updated4(pm, 4 * i, &pp.x);
         i += stride;
-        if (i < n4) { pp = p[i]; mm = m[i]; vv = v[i]; gg = g[i]; }
+        if (i < n4) { pp = __ldcg(p + i); mm = __ldcg(m + i); vv = __ldcg(v + i); gg = g[i]; }
     }
     __syncthreads();
     if (threadIdx.x == 0) adam_publish(st, s_sc);
