@@ -117,7 +117,8 @@ int bc_stage_augment(const uint8_t* rgb, int64_t n_frames, int src_h, int src_w,
 int bc_planes_to_tp(const void* planes, int in_dtype, int64_t n_planes, int64_t plane_stride, void* out_tp, void* stream);
 
 /* bf16 tensor-core mode: re-pack the f32 master weights into the smem images the tcgen05 kernels
- * read (conv1: Toeplitz-expanded [64 x 448] bf16). Call after every optimiser step. */
+ * read (conv1: Toeplitz-expanded [64 x 448] bf16). Call after the parameters changed from outside (load_state_dict, a foreign
+ * optimiser); bc_adam_tick_step / bc_adam_step_exchange with w_packed keep the images current themselves. */
 int bc_pack_weights(const bc_ctx* c, void* stream);
 size_t bc_packed_weight_bytes(void);
 
@@ -148,6 +149,14 @@ int bc_reduce_partials(const bc_ctx* c, int with_loss, void* stream); /* partial
  * data-parallel exchange reduces [0,4) first so its all-reduce overlaps conv1's wgrad */
 int bc_reduce_partials_range(const bc_ctx* c, int seg_lo, int seg_hi, int with_loss, void* stream);
 int bc_loss_reduce(const bc_ctx* c, void* stream);                 /* head CTAs' CE partials -> loss (forward-only / validation_step) */
+
+/* ---- Launch ordering contract (programmatic dependent launch). Every kernel of this library is launched with programmatic
+ * stream serialisation. Kernels that READ parameters -- the conv / dgrad kernels (their bf16 operand images in w_packed), the
+ * head (fc weights) and the optimiser kernels (params, moments, state) -- fetch them BEFORE griddepcontrol.wait, under the
+ * previous kernel's tail. That is sound because the kernels that WRITE parameters, moments, state or w_packed (bc_adam_step,
+ * bc_adam_tick_step, bc_adam_step_exchange, bc_pack_weights) release their dependents only after their last write. A caller
+ * that writes these buffers itself must do so with ordinary (fully serialising) launches or copies -- torch ops are --
+ * and never from a kernel of its own that calls griddepcontrol.launch_dependents before its last write. */
 
 /* ---- a11: Adam.step (src/models/imitation.py:82-87; torch.optim.Adam defaults).
  * state = 8 DOUBLES {lr, beta1, beta2, eps, step, grad_scale, step_size(out), bc2_sqrt(out)} on the
