@@ -516,7 +516,8 @@ def run_b200(args):
 # ----------------------------------------------------------------------------------------------
 def run_infer(args):
     """BASELINE configs[4]: inference-only policy forward + greedy action (imitation.py:34-36, src/data/stat.py:41), batch
-    1..4096 on one B200: staging + conv1..4 + head + argmax as ONE CUDA graph per batch size; p50 / p99 latency over
+    1..4096 on one B200: staging + conv1..4 + head (greedy action inside the head kernel) as ONE CUDA graph per batch size -- up
+    to engine.tail_batch conv3, conv4, the head and the argmax are one cluster launch (csrc/policy_tail.cu); p50 / p99 latency over
     `--steps` replays (CUDA events around each replay), frames/s = B / p50. One JSON line; `value` = best frames/s."""
     import ctypes as C
     import numpy as np
@@ -534,7 +535,7 @@ def run_infer(args):
     eng = net.engine()
     rng = np.random.Generator(np.random.PCG64(0))
     peaks = load_peaks()
-    sweep, best = [], None
+    sweep, best, launches = [], None, 0
     sampler = ClockSampler(dev.index)
     sampler.start()
     t_host0 = time.time()
@@ -550,45 +551,55 @@ def run_infer(args):
             bufs = eng.alloc(B, sliding_window(gray), None, False)
         actions = torch.empty(B, dtype=torch.int64, device=dev)
 
-        def enqueue(fr):
-            if bf16:
-                stage_frames(fr, out=staged)
-            else:
-                stage_gray(fr, out=gray)
-            c = eng.ctx(bufs)
-            s = torch.cuda.current_stream().cuda_stream
-            _lib.check(eng.lib.bc_forward(C.byref(c), s))
-            _lib.check(eng.lib.bc_argmax(bufs.logits.data_ptr(), actions.data_ptr(), B, 9, s))
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for k in range(3):
-                enqueue(frames[k % nrot])
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graphs = []
-        for fr in frames:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                enqueue(fr)
-            graphs.append(g)
-        for k in range(5):
-            graphs[k % nrot].replay()
-        torch.cuda.synchronize()
-        tsamples = []
-        for k in range(reps):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record(); graphs[k % nrot].replay(); a1.record()
+        def measure(tail):
+            """p50 / p99 latency (us) of one graph replay: staging + forward + greedy action; tail = conv3..argmax as one launch"""
+            def enqueue(fr):
+                if bf16:
+                    stage_frames(fr, out=staged)
+                else:
+                    stage_gray(fr, out=gray)
+                c = eng.ctx(bufs)
+                s = torch.cuda.current_stream().cuda_stream
+                _lib.check(eng.lib.bc_forward_act(C.byref(c), actions.data_ptr(), int(tail), s))
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for k in range(3):
+                    enqueue(frames[k % nrot])
+            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            tsamples.append(a0.elapsed_time(a1) * 1e3)
-        tsamples = np.sort(np.asarray(tsamples))
-        p50, p99 = float(tsamples[len(tsamples) // 2]), float(tsamples[min(len(tsamples) - 1, int(len(tsamples) * 0.99))])
+            graphs = []
+            for fr in frames:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    enqueue(fr)
+                graphs.append(g)
+            for k in range(5):
+                graphs[k % nrot].replay()
+            torch.cuda.synchronize()
+            ts = []
+            for k in range(reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(); graphs[k % nrot].replay(); a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1) * 1e3)
+            ts = np.sort(np.asarray(ts))
+            del graphs
+            return float(ts[len(ts) // 2]), float(ts[min(len(ts) - 1, int(len(ts) * 0.99))])
+        served_tail = B <= eng.tail_batch                    # the path ConvNet1.act() takes at this batch
+        p50, p99 = measure(served_tail)
         row = {"batch": B, "latency_us_p50": round(p50, 1), "latency_us_p99": round(p99, 1), "frames_per_s": round(B / (p50 * 1e-6)),
-               "tflops": round(64920128 * B / (p50 * 1e-6) / 1e12, 2)}
+               "tflops": round(64920128 * B / (p50 * 1e-6) / 1e12, 2), "path": "tail" if served_tail else "layers",
+               "launches": 4 if served_tail else 6}
+        if B <= 64:                                          # the other path at the same batch, for the crossover
+            o50, o99 = measure(not served_tail)
+            row["other_path_us_p50"], row["other_path_us_p99"] = round(o50, 1), round(o99, 1)
+            launches += reps * (6 if served_tail else 4)
+        launches += reps * row["launches"]
         sweep.append(row)
         if best is None or row["frames_per_s"] > best["frames_per_s"]:
             best = row
-        del frames, graphs, bufs
+        del frames, bufs
     eng.check_device_errors()
     t_host1 = time.time()
     time.sleep(0.25)
@@ -603,10 +614,10 @@ def run_infer(args):
                                "u8 RGB frames staged on the device, one CUDA graph per batch size", "best_batch": best["batch"],
                    "l2": "inputs rotate over 2-4 device buffers per batch size"},
         "sweep": sweep,
-        "roofline": {"kernel": "whole forward graph at the best batch (stage + conv1..4 + head + argmax)", "bound": "tensor", "achieved": ach,
+        "roofline": {"kernel": "whole forward graph at the best batch (stage + conv1..4 + head with the greedy action)", "bound": "tensor", "achieved": ach,
                      "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"], "traffic": None,
                      "flops_per_frame": 64920128, "peak_source": peaks["src"] + " (bf16 cuBLAS sustained)"},
-        "gpu_launches": 7 * reps * 13, "clocks": clocks}), flush=True)
+        "gpu_launches": launches, "clocks": clocks}), flush=True)
 
 
 def run_stacked12(args):

@@ -13,12 +13,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbc_b200.so")
-SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_fwd4.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "head_branched.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
+SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_fwd4.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "policy_tail.cu", "head_branched.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 # -cudart shared: the library reuses the libcudart.so.12 torch has already loaded (one CUDA runtime per process)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", os.environ.get("BC_CUDART", "shared"))
 
 BC_F32, BC_BF16, BC_BF16_TP = 0, 1, 2
+POLICY_TAIL_MAX_BATCH = 64      # BC_POLICY_TAIL_MAX_BATCH (include/bc_b200.h)
 TP_PLANE_ELEMS = 86688
 
 
@@ -82,6 +83,8 @@ EXPORTS = {
                                         C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bc_backward_overlap": (C.c_int, [C.POINTER(BcCtx), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "bc_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bc_forward_act": (C.c_int, [C.POINTER(BcCtx), C.c_void_p, C.c_int, C.c_void_p]),
+    "bc_policy_tail": (C.c_int, [C.POINTER(BcCtx), C.c_void_p, C.c_void_p]),
     "bc_head_branched": (C.c_int, [C.POINTER(BcBranched), C.c_int, C.c_void_p]),
     "bc_head_branched_partials_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "bc_head_branched_layout": (C.c_int64, [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -296,6 +296,15 @@ int bc_forward(const bc_ctx* c, void* stream) {
     return bc_head(c, 0, stream);
 }
 
+int bc_forward_act(const bc_ctx* c, int64_t* actions, int tail, void* stream) {
+    BC_CHECK_ARG(c && actions, "bc_forward_act: null ctx / actions");
+    for (int l = 0; l < (tail ? 2 : 4); ++l) {
+        int rc = bc_conv_relu_pool_fwd(c, l, stream);
+        if (rc) return rc;
+    }
+    return tail ? bc_policy_tail(c, actions, stream) : bc_head_launch(c, 0, actions, stream);
+}
+
 int bc_backward(const bc_ctx* c, int with_loss, void* stream) {
     BC_CHECK_ARG(c, "bc_backward: null ctx");
     // head: (CE from labels when with_loss, else the caller's dlogits) + MLP backward -> ghead

@@ -22,6 +22,7 @@ int bc_conv4_sw_fwd_launch(const bc_ctx* c, const uint8_t* wpk, void* stream);  
 int bc_conv4_sw_dgrad_launch(const bc_ctx* c, const uint8_t* wpk, void* stream);
 int bc_conv4_sw_wgrad_launch(const bc_ctx* c, void* stream);
 size_t bc_conv_tc_pack_total();
+int bc_head_launch(const bc_ctx* c, int head_mode, int64_t* actions, void* stream);           // head.cu (bc_head + the optional greedy action)
 
 namespace bc {
 

@@ -24,6 +24,7 @@ struct HeadArgs {
     int B, NA, mode;
     float loss_scale;
     int* err;            // device flag: 3 = a label outside [0, n_actions) (nn.CrossEntropyLoss raises there)
+    int64_t* actions;    // optional (B): greedy action = first maximum of the logits (serving: no separate argmax launch)
 };
 
 __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
@@ -100,6 +101,12 @@ __global__ void __launch_bounds__(NT) head_kernel(const HeadArgs a) {
         if (tid < 64) a.hid1[(size_t)b * 64 + tid] = s_h1[tid];
         if (tid < 32) a.hid2[(size_t)b * 32 + tid] = s_h2[tid];
         if (tid < NA) a.logits[(size_t)b * NA + tid] = s_z[tid];
+        if (a.actions && warp == 0) {
+            const float z = lane < NA ? s_z[lane] : -INFINITY;
+            const float m = bc::warp_max(z);
+            const unsigned hit = __ballot_sync(0xffffffffu, lane < NA && z == m);   // first maximum, like torch.argmax
+            if (lane == 0) a.actions[b] = hit ? (int64_t)(__ffs((int)hit) - 1) : 0;
+        }
         if (!do_ce && !do_bwd) continue;
         if (warp == 0) {
             if (do_ce) {
@@ -210,7 +217,7 @@ extern "C" int bc_scale_inplace(float* v, int64_t n, const float* scale_dev, voi
     return BC_OK;
 }
 
-extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) {
+int bc_head_launch(const bc_ctx* c, int head_mode, int64_t* actions, void* stream) {
     BC_CHECK_ARG(c && c->params && c->act[3] && c->hid1 && c->hid2 && c->logits, "bc_head: null buffer");
     BC_CHECK_ARG(c->n_actions >= 1 && c->n_actions <= MAXA, "bc_head: n_actions %d outside 1..%d", c->n_actions, MAXA);
     BC_CHECK_ARG(!(head_mode & 1) || (c->y && c->dlogits && c->partials), "bc_head: CE needs y, dlogits, partials");
@@ -229,11 +236,14 @@ extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) {
     a.seg_len = ar.seg_len[0];
     a.ow0 = ar.w[4]; a.ob0 = ar.b[4]; a.ow2 = ar.w[5]; a.ob2 = ar.b[5]; a.ow4 = ar.w[6]; a.ob4 = ar.b[6];
     a.B = c->batch; a.NA = c->n_actions; a.mode = head_mode; a.loss_scale = c->loss_scale; a.err = c->err_flag;
+    a.actions = actions;
     // the partial layout has a fixed number of copies, so the grid is fixed as well
     bc::launch_pdl(head_kernel, dim3(bc::kHeadBlocks), dim3(NT), 0, (cudaStream_t)stream, a);
     BC_CUDA_LAUNCH_CHECK("head_kernel");
     return BC_OK;
 }
+
+extern "C" int bc_head(const bc_ctx* c, int head_mode, void* stream) { return bc_head_launch(c, head_mode, nullptr, stream); }
 
 extern "C" int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream) {
     BC_CHECK_ARG(logits && actions && batch >= 0 && n_actions >= 1, "bc_argmax: bad arguments");

@@ -504,6 +504,32 @@ class BCEngine:
             else:
                 _lib.check(self.lib.bc_backward(C.byref(c), 1, s), "bc_backward")
 
+    tail_batch = 8       # serving: up to this batch conv3..head + argmax run as ONE cluster launch (bc_policy_tail). Measured crossover
+                         # (bench.py --workload infer, profiles/r2G): 20.6-22.3 us against 26.3-26.6 us up to B = 8, 30.6 against 28.6 at B = 16
+
+    def forward_act(self, x, out: Optional[torch.Tensor] = None, bufs: Optional[StepBuffers] = None,
+                    tail: Optional[bool] = None):
+        """The serving forward (imitation.py:34-36 + the argmax of src/data/stat.py:41): logits AND greedy actions without a
+        separate argmax launch; at small batch conv3, conv4, the head and the argmax are one launch (csrc/policy_tail.cu).
+        Returns (actions (B,) int64, StepBuffers with .logits). `bufs` = persistent buffers (eng.alloc(B, x, None, False)) for
+        a fixed-shape serving loop / CUDA graph; `tail` forces the path (None = by batch size)."""
+        x = self.check_input(x)
+        self.ensure_packed()
+        B = x.shape[0]
+        b = bufs if bufs is not None else self.alloc(B, x, None, False)
+        if out is None:
+            out = torch.empty(B, dtype=torch.int64, device=self.device)
+        if B == 0:
+            return out, b
+        if tail is None:
+            tail = B <= self.tail_batch
+        if tail and B > _lib.POLICY_TAIL_MAX_BATCH:
+            raise ValueError(f"the one-launch tail serves batches up to {_lib.POLICY_TAIL_MAX_BATCH}")
+        c = self.ctx(b)
+        with on_device(self.device):
+            _lib.check(self.lib.bc_forward_act(C.byref(c), out.data_ptr(), int(bool(tail)), _stream_ptr()), "bc_forward_act")
+        return out, b
+
     def argmax(self, logits: torch.Tensor) -> torch.Tensor:
         out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device)
         _lib.check(self.lib.bc_argmax(logits.data_ptr(), out.data_ptr(), logits.shape[0], logits.shape[1], _stream_ptr()), "bc_argmax")

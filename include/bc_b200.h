@@ -194,6 +194,19 @@ int bc_adam_step_exchange(float* params, float* exp_avg, float* exp_avg_sq, doub
 /* ---- K12: Imitation.forward + argmax (imitation.py:34-36, src/data/stat.py:41) */
 int bc_argmax(const float* logits, int64_t* actions, int batch, int n_actions, void* stream);
 
+/* ---- K13: the policy forward for closed-loop serving (BASELINE configs[4]; imitation.py:34-36 + the argmax of
+ * src/data/stat.py:41), greedy actions (batch) int64 out, no separate argmax launch.
+ * bc_forward_act, tail = 0: bc_forward with the first-maximum action taken inside the head kernel.
+ * tail = 1 (batch <= BC_POLICY_TAIL_MAX_BATCH; faster up to batch 8 on B200, where the forward is a chain of launch latencies):
+ *   conv1, conv2 as in bc_forward, then bc_policy_tail = conv3 + ReLU + pool, conv4 + ReLU + pool, the three Linear layers and the
+ *   argmax in ONE launch (an 8-CTA thread-block cluster per sample, exact f32 FFMA on the f32 master weights in both modes,
+ *   layers handed over through distributed shared memory). bc_policy_tail reads act[1] ((batch,32,12,12) f32, written by
+ *   bc_conv_relu_pool_fwd(layer 1) in both modes) and params; writes logits and actions, and act[2], act[3], hid1, hid2 when
+ *   those pointers are not NULL (amax[2], amax[3] are NOT written: inference only). */
+#define BC_POLICY_TAIL_MAX_BATCH 64
+int bc_forward_act(const bc_ctx* c, int64_t* actions, int tail, void* stream);
+int bc_policy_tail(const bc_ctx* c, int64_t* actions, void* stream);
+
 /* v[0..n) *= *scale_dev (a device scalar), nothing is touched when it is exactly 1: how `loss.backward(gradient=g)` reaches
  * gradients that the fused step has already computed for d loss (imitation.py:38-45 returns the loss, Lightning calls backward) */
 int bc_scale_inplace(float* v, int64_t n, const float* scale_dev, void* stream);

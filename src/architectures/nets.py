@@ -205,8 +205,7 @@ class ConvNet1(_Base):
     @torch.no_grad()
     def act(self, x):
         """Greedy action ids = argmax over logits (src/data/stat.py:41, imitation.py:177)."""
-        eng = self.engine()
-        return eng.argmax(eng.forward(self._to_device(x)).logits)
+        return self.engine().forward_act(self._to_device(x))[0]
 
 
 class ConvNetRawSegment(_Base):

@@ -449,23 +449,93 @@ def test_inference_sweep_batches_match_oracle(mode):
     fr = torch.from_numpy(frames).to(dev)
     gray = stage_gray(fr)
     ref_all = O.forward(params, torch.from_numpy(O.gray_stack(frames[:132])).unfold(0, 4, 1).permute(0, 3, 1, 2)[:128])
-    for B in (1, 2, 31, 128, 1024, 4096):
+    for B in (1, 2, 8, 9, 31, 128, 1024, 4096):      # up to engine.tail_batch = 8 the serving path is the one-launch tail
         if mode == "bf16":
             x = stage_frames(fr[:B + 4])
         else:
             x = sliding_window(gray[:B + 4])
         with torch.no_grad():
             logits = net(x)
-            actions = net.act(x)
+            actions, served = net.engine().forward_act(x)      # what net.act() returns + the logits of that same launch chain
+            assert torch.equal(net.act(x), actions)
         assert logits.shape == (B, 9) and actions.shape == (B,) and actions.dtype == torch.int64
         n = min(B, 128)
-        got, ref = logits[:n].cpu().double(), ref_all[:n].double()
-        assert float((got - ref).abs().max() / ref.abs().max()) <= tol, (mode, B)
+        ref = ref_all[:n].double()
+        for lg in (logits, served.logits):
+            got = lg[:n].cpu().double()
+            assert float((got - ref).abs().max() / ref.abs().max()) <= tol, (mode, B)
         top2 = ref.topk(2, dim=1).values
         clear = (top2[:, 0] - top2[:, 1]) > 2 * tol * ref.abs().max()
         assert torch.equal(actions[:n].cpu()[clear], ref.argmax(1)[clear])
-        assert torch.equal(actions.cpu(), logits.argmax(1).cpu())
+        assert torch.equal(actions.cpu(), served.logits.argmax(1).cpu())
     net.engine().check_device_errors()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_policy_tail_matches_layer_kernels_and_oracle(mode):
+    """csrc/policy_tail.cu (conv3 + conv4 + head + argmax as one 8-CTA-cluster launch, exact f32 arithmetic) against the
+    layer-by-layer kernels and the f64 oracle, both paths forced at the same batch; also replayed from a CUDA graph
+    (cluster launch + programmatic dependent launch inside a capture), as the serving loop of bench.py --workload infer does."""
+    from carla_imitation_learning_b200 import stage_frames, stage_gray, sliding_window
+    from src.architectures.nets import ConvNet1
+    dev = _dev()
+    torch.manual_seed(4321)
+    net = ConvNet1({"obs_size": 4, "n_actions": 9, "precision": mode}).to(dev)
+    eng = net.engine()
+    params = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    tol = REL_F32 if mode == "fp32" else 2e-2
+    frames, _ = O.synth_frames(77, 65 + 4)
+    fr = torch.from_numpy(frames).to(dev)
+    ref_all = O.forward(params, torch.from_numpy(O.gray_stack(frames)).unfold(0, 4, 1).permute(0, 3, 1, 2)[:64]).double()
+    for B in (1, 3, 16, 33, 64):
+        x = stage_frames(fr[:B + 4]) if mode == "bf16" else sliding_window(stage_gray(fr[:B + 4]))
+        a_tail, b_tail = eng.forward_act(x, tail=True)
+        a_std, b_std = eng.forward_act(x, tail=False)
+        torch.cuda.synchronize()
+        ref = ref_all[:B]
+        for lg in (b_tail.logits, b_std.logits):
+            assert float((lg.cpu().double() - ref).abs().max() / ref.abs().max()) <= tol, (mode, B)
+        assert torch.equal(a_tail.cpu(), b_tail.logits.argmax(1).cpu())
+        assert torch.equal(a_std.cpu(), b_std.logits.argmax(1).cpu())
+        if mode == "fp32":                     # same operands, different summation order only
+            for i in (2, 3):
+                assert _relerr(b_tail.act[i].cpu(), b_std.act[i].cpu()) <= REL_F32, (B, i)
+            assert _relerr(b_tail.hid1.cpu(), b_std.hid1.cpu()) <= REL_F32 and _relerr(b_tail.hid2.cpu(), b_std.hid2.cpu()) <= REL_F32
+            assert _relerr(b_tail.logits.cpu(), b_std.logits.cpu()) <= REL_F32
+    with pytest.raises(ValueError):
+        eng.forward_act(stage_frames(fr[:65 + 4]) if mode == "bf16" else sliding_window(stage_gray(fr[:65 + 4])), tail=True)
+    # graph replay over two inputs written into the same staging buffers
+    B = 2
+    staged = stage_frames(fr[:B + 4]) if mode == "bf16" else None
+    gray = None if mode == "bf16" else stage_gray(fr[:B + 4])
+    x = staged if mode == "bf16" else sliding_window(gray)
+    bufs = eng.alloc(B, x, None, False)
+    out = torch.empty(B, dtype=torch.int64, device=dev)
+    src = fr[:B + 4].clone()
+
+    def enqueue():
+        if mode == "bf16":
+            stage_frames(src, out=staged)
+        else:
+            stage_gray(src, out=gray)
+        eng.forward_act(x, out=out, bufs=bufs, tail=True)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        enqueue()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        enqueue()
+    for off in (10, 20, 0):
+        src.copy_(fr[off:off + B + 4])
+        g.replay()
+        torch.cuda.synchronize()
+        ref = ref_all[off:off + B]
+        assert float((bufs.logits.cpu().double() - ref).abs().max() / ref.abs().max()) <= tol, (mode, off)
+        assert torch.equal(out.cpu(), bufs.logits.argmax(1).cpu())
+    eng.check_device_errors()
 
 
 def test_stacked_12_channel_variant_matches_oracle():
