@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+T=${1:-r2H}
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x --timeout 150 -k "policy_tail or inference_sweep" > gpurun_out/${T}_pytest_tail.log 2>&1; tail -4 gpurun_out/${T}_pytest_tail.log | cut -c1-300
+python tools/infer_launches.py 2>&1 | tail -4
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_infer_launches.csv python tools/infer_launches.py > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
