@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libbc_b200.so")
+LIB_PATH = os.environ.get("BC_LIB_PATH") or os.path.join(HERE, "libbc_b200.so")     # BC_LIB_PATH: A/B runs of two builds on one box
 SOURCES = ("stage.cu", "conv_fwd.cu", "conv1_tc.cu", "conv1_fwd4.cu", "conv1_wgrad3.cu", "conv_tc.cu", "conv_sw.cu", "conv4_sw.cu", "head.cu", "policy_tail.cu", "head_branched.cu", "conv_bwd.cu", "abi.cu", "tc_selftest.cu")
 # -cudart shared: the library reuses the libcudart.so.12 torch has already loaded (one CUDA runtime per process)
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

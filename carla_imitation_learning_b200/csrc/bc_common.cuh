@@ -86,7 +86,13 @@ __host__ inline Arena arena_layout(int obs, int na) {
 }
 
 // partial-sum workspace: per segment, NPART[seg] copies of seg_len floats, then loss partials
-constexpr int kHeadBlocks = 128;    // partial copies of the head segment (= head CTAs: 2 samples each at B=256)
+// 128 = 2 samples per head CTA at B = 256. Measured against 256 (one sample per CTA, two CTAs per SM; same box, three alternating runs each,
+// profiles/r2M_ab_head_blocks.log): the head kernel alone drops from 11.0 to 7.4 us, but the STEP rises from 0.1911 to 0.1931 ms -- twice the partial
+// copies for the reduction to read cold and 256 x 42 KB of weight prologue under conv4's forward cost more than the head saves.
+#ifndef BC_HEAD_BLOCKS
+#define BC_HEAD_BLOCKS 128
+#endif
+constexpr int kHeadBlocks = BC_HEAD_BLOCKS;    // partial copies of the head segment (= head CTAs)
 constexpr int kWgradParts[4] = {296, 29, 37, 16};  // conv1..conv4: partial-sum slots = grid.x of the wgrad kernels (conv2: x 5 kernel rows = 145 CTAs, conv3: x 4 = 148, conv4: x 6 classes = 96)
 struct Partials { int64_t off[5]; int nparts[5]; int64_t loss_off; int64_t total; };
 __host__ inline Partials partials_layout(const Arena& a) {
