@@ -356,6 +356,8 @@ extern "C" int bc_policy_tail(const bc_ctx* c, int64_t* actions, void* stream) {
     BC_CHECK_ARG(c->batch >= 0 && c->batch <= BC_POLICY_TAIL_MAX_BATCH, "bc_policy_tail: batch %d outside 0..%d (one 8-CTA cluster per sample; "
                  "larger batches belong to the tensor-core kernels: bc_forward_act)", c->batch, BC_POLICY_TAIL_MAX_BATCH);
     if (c->batch == 0) return BC_OK;
+    BC_CHECK_ARG(((uintptr_t)c->params | (uintptr_t)c->act[1]) % 16 == 0 && (!c->act[2] || (uintptr_t)c->act[2] % 16 == 0),
+                 "bc_policy_tail: params, act[1] and act[2] are read / written as 16 B words");
     static bc::PerDeviceOnce once_; bool& configured = once_();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(policy_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

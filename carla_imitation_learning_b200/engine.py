@@ -517,6 +517,16 @@ class BCEngine:
         self.ensure_packed()
         B = x.shape[0]
         b = bufs if bufs is not None else self.alloc(B, x, None, False)
+        if b.batch != B or (out is not None and (out.dtype != torch.int64 or out.numel() != B or not out.is_cuda)):
+            raise ValueError(f"bufs / out were built for another batch (x has {B} samples): out is (B,) int64 on the device")
+        if bufs is not None:                     # persistent buffers: only the input is re-pointed
+            staged = x if isinstance(x, StagedBatch) else None
+            if staged is not None:
+                b.x, b.x_tp, b.x_tp_strides = staged.x, staged.tp, (staged.step * _lib.TP_PLANE_ELEMS, _lib.TP_PLANE_ELEMS)
+            elif self.conv_mode & 1:
+                raise ValueError("persistent serving buffers in bf16 mode take a StagedBatch (stage_frames(out=...)): a plain batch would be re-converted per call")
+            else:
+                b.x = x
         if out is None:
             out = torch.empty(B, dtype=torch.int64, device=self.device)
         if B == 0:

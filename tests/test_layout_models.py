@@ -248,3 +248,148 @@ def test_dgrad_toeplitz_in_n_fold(hin, ks, wp):
             got[:, iy, ix] = sum(D[m + j, j] for j in range(ks))
     assert np.array_equal(got, want)
     assert 128 % wp == 0 and wp >= hin + ks - 1
+
+
+def test_policy_tail_thread_mapping_reproduces_conv3_conv4_head():
+    """csrc/policy_tail.cu written out thread by thread in numpy: the shared-memory plan (padded channel pitches W3P / W4P / PTP /
+    A3P), the (2 channels x pooled row x 2 input channels) register tile of conv3, the partial reduction split over (px, dy, h, g)
+    lanes, the pull all-gather across the 8 CTAs of a cluster, conv4's (channel, 4 input channels) threads with the 16-lane fold, and
+    the lane-split Linear layers with their rotated inner index -- against the plain convolutions / matrix products (integers, exact)."""
+    rng = np.random.default_rng(5)
+    W3P, W4P, PTP, A3P = 516, 592, 36, 20
+    act2 = rng.integers(-3, 4, size=(32, 12, 12)).astype(np.int64)
+    w3 = rng.integers(-2, 3, size=(64, 32, 4, 4)).astype(np.int64)
+    b3 = rng.integers(-5, 6, size=64).astype(np.int64)
+    w4 = rng.integers(-2, 3, size=(128, 64, 3, 3)).astype(np.int64)
+    b4 = rng.integers(-5, 6, size=128).astype(np.int64)
+    f0 = rng.integers(-2, 3, size=(64, 128)).astype(np.int64); g0 = rng.integers(-3, 4, size=64).astype(np.int64)
+    f2 = rng.integers(-2, 3, size=(32, 64)).astype(np.int64); g2 = rng.integers(-3, 4, size=32).astype(np.int64)
+    NA = 9
+    f4 = rng.integers(-2, 3, size=(NA, 32)).astype(np.int64); g4 = rng.integers(-3, 4, size=NA).astype(np.int64)
+
+    # ---- reference: conv (valid) + ReLU + floor-mode 2x2 max pool, twice; three Linear layers
+    def conv_relu_pool(x, w, b):
+        co, ci, k, _ = w.shape
+        ho = x.shape[1] - k + 1
+        y = np.zeros((co, ho, ho), np.int64)
+        for ky in range(k):
+            for kx in range(k):
+                y += np.einsum("oc,chw->ohw", w[:, :, ky, kx], x[:, ky:ky + ho, kx:kx + ho])
+        y = np.maximum(y + b[:, None, None], 0)
+        hp = ho // 2
+        return y[:, :2 * hp, :2 * hp].reshape(co, hp, 2, hp, 2).max(axis=(2, 4))
+    ref3 = conv_relu_pool(act2, w3, b3)                       # (64,4,4)
+    ref4 = conv_relu_pool(ref3, w4, b4).reshape(128)          # (128,)
+    h1 = np.maximum(f0 @ ref4 + g0, 0); h2 = np.maximum(f2 @ h1 + g2, 0); ref_z = f4 @ h2 + g4
+
+    a2 = act2.reshape(-1)
+    tid = np.arange(256)
+    lane, warp = tid & 31, tid >> 5
+    s_a3 = np.full((8, 64 * A3P), -10 ** 9, np.int64)         # one copy per CTA of the cluster
+    for r in range(8):
+        # weight slice of CTA r with the padded channel pitch (float4 index i = co * 128 + rest -> co * (W3P / 4) + rest)
+        src = w3[8 * r:8 * r + 8].reshape(-1)
+        sw3 = np.full(8 * W3P, 10 ** 9, np.int64)
+        i4 = np.arange(1024)
+        dst = (i4 >> 7) * (W3P // 4) + (i4 & 127)
+        for q in range(4):
+            sw3[4 * dst + q] = src[4 * i4 + q]
+        cp, py, cs = tid & 3, (tid >> 2) & 3, 2 * warp + (lane >> 4)
+        assert np.array_equal(cs, tid >> 4)
+        acc = np.zeros((256, 2, 2, 8), np.int64)
+        for i in range(2):
+            ci = 2 * cs + i
+            base = ci * 144 + (2 * py) * 12
+            inn = a2[base[:, None] + np.arange(60)[None, :]].reshape(256, 5, 12)
+            for h in range(2):
+                wb = (2 * cp + h) * W3P + ci * 16
+                w = sw3[wb[:, None] + np.arange(16)[None, :]].reshape(256, 4, 4)
+                for ky in range(4):
+                    for dy in range(2):
+                        for ox in range(8):
+                            acc[:, h, dy, ox] += (w[:, ky, :] * inn[:, dy + ky, ox:ox + 4]).sum(1)
+        part = np.full(16 * 16 * PTP, 10 ** 9, np.int64)
+        pb = (cs * 16 + (tid & 15)) * PTP
+        part[pb[:, None] + np.arange(32)[None, :]] = acc.reshape(256, 32)
+        # reduction: thread = (px, dy, h, g); the dy partner is lane ^ 4, the row of four px is lanes ^1 ^2 ^3
+        px, dy, h, g = tid & 3, (tid >> 2) & 1, (tid >> 3) & 1, tid >> 4
+        cl, ppy = 2 * (g & 3) + h, g >> 2
+        pp = g * PTP + h * 16 + dy * 8 + 2 * px
+        s0 = sum(part[pp + k * 16 * PTP] for k in range(16)); s1 = sum(part[pp + k * 16 * PTP + 1] for k in range(16))
+        v = np.maximum(s0, s1)
+        v = np.maximum(v, v[tid ^ 4])
+        v = np.maximum(v + b3[8 * r + cl], 0)
+        row = np.stack([v, v[tid ^ 1], v[tid ^ 2], v[tid ^ 3]], 1)
+        sel = (px == 0) & (dy == 0)
+        off = (8 * r + cl) * A3P + ppy * 4
+        s_a3[r][off[sel, None] + np.arange(4)[None, :]] = row[sel]
+    own = s_a3.copy()
+    for r in range(8):                                        # pull: thread -> (source CTA d, channel cl, pooled row py), 16 B each
+        d, cl, py = tid >> 5, (tid >> 2) & 7, tid & 3
+        off = (8 * d + cl) * A3P + py * 4
+        for t in range(256):
+            if d[t] != r:
+                s_a3[r][off[t]:off[t] + 4] = own[d[t]][off[t]:off[t] + 4]
+    for r in range(8):
+        assert np.array_equal(s_a3[r].reshape(64, A3P)[:, :16].reshape(64, 4, 4), ref3), r
+
+    s_a4 = np.zeros(128, np.int64)
+    for r in range(8):
+        src = w4[16 * r:16 * r + 16].reshape(-1)
+        sw4 = np.full(16 * W4P, 10 ** 9, np.int64)
+        i4 = np.arange(2304)
+        dst = (i4 // 144) * (W4P // 4) + (i4 % 144)
+        for q in range(4):
+            sw4[4 * dst + q] = src[4 * i4 + q]
+        s, c = tid & 15, tid >> 4
+        o = np.zeros((256, 4), np.int64)
+        for i in range(4):
+            ci = s + 16 * i
+            inn = s_a3[r][(ci * A3P)[:, None] + np.arange(16)[None, :]].reshape(256, 4, 4)
+            wp = c * W4P + ci * 9
+            for ky in range(3):
+                for kx in range(3):
+                    w = sw4[wp + ky * 3 + kx]
+                    o[:, 0] += w * inn[:, ky, kx]; o[:, 1] += w * inn[:, ky, kx + 1]
+                    o[:, 2] += w * inn[:, ky + 1, kx]; o[:, 3] += w * inn[:, ky + 1, kx + 1]
+        for offx in (8, 4, 2, 1):
+            o = o + o[tid ^ offx]
+        feat = np.maximum(o.max(1) + b4[16 * r + c], 0)
+        s_a4[16 * r + c[s == 0]] = feat[s == 0]
+    assert np.array_equal(s_a4, ref4)
+
+    # head on CTA 0: rows split over neighbouring lanes, inner index rotated per lane
+    j, q = tid >> 2, tid & 3
+    p = np.zeros(256, np.int64)
+    for i in range(8):
+        k = (i + lane) & 7
+        for e in range(4):
+            p += f0.reshape(-1)[j * 128 + q * 32 + 4 * k + e] * s_a4[q * 32 + 4 * k + e]
+    p = p + p[tid ^ 1]; p = p + p[tid ^ 2]
+    s_h1 = np.zeros(64, np.int64); s_h1[j[q == 0]] = np.maximum(p + g0[j], 0)[q == 0]
+    assert np.array_equal(s_h1, h1)
+    j, e8 = tid >> 3, tid & 7
+    k0 = (e8 >> 2) & 1
+    p = np.zeros(256, np.int64)
+    for kk in (k0, k0 ^ 1):
+        for e in range(4):
+            p += f2.reshape(-1)[j * 64 + e8 * 8 + 4 * kk + e] * s_h1[e8 * 8 + 4 * kk + e]
+    for offx in (1, 2, 4):
+        p = p + p[tid ^ offx]
+    s_h2 = np.zeros(32, np.int64); s_h2[j[e8 == 0]] = np.maximum(p + g2[j], 0)[e8 == 0]
+    assert np.array_equal(s_h2, h2)
+    c, e8 = tid >> 3, tid & 7
+    cc = np.minimum(c, NA - 1)
+    p = np.zeros(256, np.int64)
+    for i in range(4):
+        k = (i + c) & 3
+        p += f4.reshape(-1)[cc * 32 + e8 * 4 + k] * s_h2[e8 * 4 + k]
+    for offx in (1, 2, 4):
+        p = p + p[tid ^ offx]
+    z = np.zeros(NA, np.int64)
+    ok = (e8 == 0) & (c < NA)
+    z[c[ok]] = (p + g4[cc])[ok]
+    assert np.array_equal(z, ref_z)
+    # first maximum: ballot of the lanes that hold the maximum, lowest set bit
+    m = z.max()
+    assert int(np.flatnonzero(z == m)[0]) == int(np.argmax(z))
