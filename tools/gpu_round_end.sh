@@ -2,7 +2,7 @@
 # artefacts at the final commit of the round: smoke, full GPU suite, default bench line, inference sweep (both serving paths up to B = 64),
 # launch list of the serving forward at B = 1 / 8
 set -x
-T=${1:-r2L}
+T=${1:-r2K}
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 BC_TEST_OUT=gpurun_out timeout 900 python -m pytest tests -q -m gpu --timeout 300 -rf > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -2 gpurun_out/${T}_pytest_gpu.log | cut -c1-300
