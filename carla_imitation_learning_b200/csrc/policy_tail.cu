@@ -13,8 +13,8 @@
 //   phase B  act2 of the sample (32x12x12 f32, 18 KB) -> shared memory; conv3 for the CTA's 8 channels at the 8x8 conv pixels
 //            the floor-mode pool keeps (row / column 8 of the 9x9 output is dropped by MaxPool2d(2), nets.py:26): a thread owns
 //            (2 channels, the 2 x 8 conv pixels of one pooled row, 2 of the 32 input channels) = 1,024 FMA on 5 input rows and
-//            32 weights held in registers (23 LDS.128 per 512 FMA: the first version, one 2x2 window per thread, was bound by
-//            shared-memory wavefronts); the 16 input-channel pairs meet in shared memory in fixed order, + bias, ReLU, 2x2 max; after a
+//            32 weights held in registers (23 LDS.128 per 512 FMA; the phase is FMA-issue bound at 2 warps per scheduler: a first
+//            version with 4x the shared-memory loads took the same 3.0 K cycles); the 16 input-channel pairs meet in shared memory in fixed order, + bias, ReLU, 2x2 max; after a
 //            cluster barrier every CTA pulls the other seven CTAs' 128 pooled values through distributed shared memory;
 //   phase C  conv4 for the CTA's 16 channels: a thread owns (channel, 4 of the 64 input channels) for all 2x2 conv pixels,
 //            16-lane xor tree, + bias, ReLU, max -> the 16 features go to CTA 0's shared memory;
